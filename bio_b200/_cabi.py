@@ -1,0 +1,225 @@
+"""ctypes binding of bio_b200/lib/libb200sketch.so (C ABI: include/b200sketch.h).
+
+This is the only way Python reaches the sketching path: there is no CPU
+fallback.  If the library is missing it is built with nvcc (in-tree); if that
+fails, or no CUDA device is present at call time, the error is raised to the
+caller.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200sketch.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+OK = 0
+ERR_INVALID_K = -1
+ERR_SHORT_SEQ = -2
+ERR_INVALID_W = -3
+ERR_INVALID_S = -4
+ERR_ILLEGAL_BASE = -5
+ERR_K_OVERFLOW = -6
+ERR_INVALID_FRAME = -7
+ERR_CODON_TABLE = -8
+ERR_TRANSLATE_SHORT = -9
+ERR_INVALID_CODON = -10
+ERR_CUDA = -100
+ERR_NO_DEVICE = -101
+ERR_UNSUPPORTED = -102
+ERR_CAPACITY = -103
+ERR_BAD_ARG = -104
+ERR_NOMEM = -105
+
+MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN = range(5)
+ALPHABET_DNA_REDUNDANT, ALPHABET_DNA, ALPHABET_RNA_REDUNDANT, ALPHABET_RNA, ALPHABET_UNLIMIT = range(5)
+
+# every symbol include/b200sketch.h declares (tests check the .so exports all of them)
+EXPORTS = (
+    "b200sk_create", "b200sk_destroy", "b200sk_alloc_pinned", "b200sk_free_pinned",
+    "b200sk_check_params", "b200sk_output_bound", "b200sk_run", "b200sk_run_device",
+    "b200sk_enqueue_device", "b200sk_strerror", "b200sk_last_error", "b200sk_kernel_launches",
+    "b200sk_version",
+)
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("k", C.c_int32), ("w", C.c_int32), ("s", C.c_int32),
+        ("canonical", C.c_int32), ("circular", C.c_int32), ("codon_table", C.c_int32),
+        ("frame", C.c_int32), ("alphabet", C.c_int32), ("want_pos", C.c_int32),
+        ("max_read_len", C.c_uint32), ("reserved", C.c_int32 * 5),
+    ]
+
+
+def make_params(mode, k, w=0, s=0, canonical=True, circular=False, codon_table=1, frame=1,
+                alphabet=ALPHABET_DNA_REDUNDANT, want_pos=True, max_read_len=0):
+    p = Params()
+    p.mode, p.k, p.w, p.s = mode, k, w, s
+    p.canonical, p.circular = int(bool(canonical)), int(bool(circular))
+    p.codon_table, p.frame, p.alphabet = codon_table, frame, alphabet
+    p.want_pos, p.max_read_len = int(bool(want_pos)), int(max_read_len)
+    return p
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", CSRC], stdout=None if verbose else subprocess.DEVNULL)
+
+
+def _needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for root in (CSRC, os.path.join(_HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cu", ".cuh", ".h")) and os.path.getmtime(os.path.join(root, f)) > t:
+                return True
+    return False
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _needs_build():
+        build()
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u64p, u32p, i32p = (C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+    PP = C.POINTER(Params)
+    L.b200sk_version.restype = C.c_int
+    L.b200sk_create.restype = C.c_int
+    L.b200sk_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.b200sk_destroy.restype = None
+    L.b200sk_destroy.argtypes = [vp]
+    L.b200sk_alloc_pinned.restype = C.c_void_p
+    L.b200sk_alloc_pinned.argtypes = [C.c_size_t]
+    L.b200sk_free_pinned.restype = None
+    L.b200sk_free_pinned.argtypes = [vp]
+    L.b200sk_check_params.restype = C.c_int
+    L.b200sk_check_params.argtypes = [PP]
+    L.b200sk_output_bound.restype = C.c_uint64
+    L.b200sk_output_bound.argtypes = [PP, C.c_uint64, C.c_uint64, C.c_int]
+    L.b200sk_run.restype = C.c_int
+    L.b200sk_run.argtypes = [vp, PP, u8p, u64p, C.c_uint64,
+                             C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                             C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.b200sk_run_device.restype = C.c_int
+    L.b200sk_run_device.argtypes = [vp, PP, u8p, u64p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, i32p,
+                                    C.c_uint64, vp, C.POINTER(C.c_uint64)]
+    L.b200sk_enqueue_device.restype = C.c_int
+    L.b200sk_enqueue_device.argtypes = [vp, PP, u8p, u64p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, i32p,
+                                        C.c_uint64, vp, u32p]
+    L.b200sk_strerror.restype = C.c_char_p
+    L.b200sk_strerror.argtypes = [C.c_int]
+    L.b200sk_last_error.restype = C.c_char_p
+    L.b200sk_last_error.argtypes = [vp]
+    L.b200sk_kernel_launches.restype = C.c_uint64
+    L.b200sk_kernel_launches.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def strerror(code):
+    return lib().b200sk_strerror(code).decode()
+
+
+class SketchError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = strerror(code)
+        if detail:
+            msg += " (" + detail + ")"
+        super().__init__(msg)
+
+
+class Context:
+    """One b200sk_ctx: a device, its streams and scratch buffers."""
+
+    def __init__(self, device=0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.b200sk_create(C.byref(h), device)
+        if rc != 0:
+            raise SketchError(rc)
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200sk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _raise(self, rc):
+        raise SketchError(rc, lib().b200sk_last_error(self._h).decode() if rc == ERR_CUDA else "")
+
+    def kernel_launches(self):
+        return int(lib().b200sk_kernel_launches(self._h))
+
+    # ---- host entry point: numpy in, numpy views of library-owned pinned memory out
+    def run(self, params, bases, read_off, copy=True):
+        import numpy as np
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n = len(read_off) - 1
+        ov, op, oo, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        total = C.c_uint64(0)
+        rc = lib().b200sk_run(self._h, C.byref(params), bases.ctypes.data, read_off.ctypes.data, n,
+                              C.byref(ov), C.byref(op), C.byref(oo), C.byref(st), C.byref(total))
+        if rc != 0:
+            self._raise(rc)
+        t = int(total.value)
+
+        def view(ptr, count, dt):
+            if not ptr.value or count == 0:
+                return np.zeros(0, dtype=dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dt).itemsize,))
+            a = a.view(dt)
+            return a.copy() if copy else a
+
+        return dict(val=view(ov, t, np.uint64), pos=view(op, t, np.uint32) if params.want_pos else None,
+                    off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t)
+
+    # ---- device entry points: torch CUDA tensors (plumbing only: pointers + the current stream)
+    def run_device(self, params, d_bases, d_off, n_bases, out_val, out_pos, out_off, status, stream=None):
+        import torch
+        n = d_off.numel() - 1
+        st = torch.cuda.current_stream(d_bases.device).cuda_stream if stream is None else stream
+        total = C.c_uint64(0)
+        rc = lib().b200sk_run_device(
+            self._h, C.byref(params), d_bases.data_ptr(), d_off.data_ptr(), n, n_bases,
+            out_val.data_ptr() if out_val is not None else None,
+            out_pos.data_ptr() if out_pos is not None else None,
+            out_off.data_ptr(), status.data_ptr() if status is not None else None,
+            out_val.numel() if out_val is not None else 0, st, C.byref(total))
+        if rc not in (0, ERR_CAPACITY):
+            self._raise(rc)
+        return rc, int(total.value)
+
+    def enqueue_device(self, params, d_bases, d_off, n_bases, out_val, out_pos, out_off, status, flags,
+                       stream=None):
+        import torch
+        n = d_off.numel() - 1
+        st = torch.cuda.current_stream(d_bases.device).cuda_stream if stream is None else stream
+        rc = lib().b200sk_enqueue_device(
+            self._h, C.byref(params), d_bases.data_ptr(), d_off.data_ptr(), n, n_bases,
+            out_val.data_ptr() if out_val is not None else None,
+            out_pos.data_ptr() if out_pos is not None else None,
+            out_off.data_ptr(), status.data_ptr() if status is not None else None,
+            out_val.numel() if out_val is not None else 0, st,
+            flags.data_ptr() if flags is not None else None)
+        if rc != 0:
+            self._raise(rc)

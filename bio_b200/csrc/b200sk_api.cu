@@ -1,0 +1,507 @@
+// Host side of libb200sketch.so: context, planning, the device entry points and
+// the pipelined host entry point.  C ABI declared in include/b200sketch.h.
+// No CPU fallback exists anywhere in this file: without a device every entry
+// point fails with B200SK_ERR_NO_DEVICE / B200SK_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "b200sk_kernels.cuh"
+
+namespace b200sk {
+cudaError_t launch_prepass(const KArgs &a, unsigned long long *meta, cudaStream_t st);
+cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *tile_state,
+                              unsigned long long *ticket, cudaStream_t st);
+cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st);
+int main_kernel_occupancy(const KArgs &a, int threads);
+cudaError_t launch_circularize(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, int k,
+                               uint8_t *bases2, uint64_t *off2, uint64_t *tile_state,
+                               unsigned long long *ticket, cudaStream_t st);
+} // namespace b200sk
+
+using namespace b200sk;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf { // pinned
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes, bool keep = false) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = bytes + bytes / 8 + 256;
+        void *q = nullptr;
+        cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) memcpy(q, p, cap);
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Plan {
+    int T = 128;
+    bool chunked = false;
+    uint32_t C = 0, span_max = 0, lcap = 0;
+    uint32_t sm_tile = 0, sm_tile_bytes = 0, sm_ring = 0, sm_ring_bytes = 0, sm_listv = 0, sm_listp = 0,
+             sm_total = 0;
+};
+
+const uint32_t kChunk = 256;        // positions per chunk for long reads
+const uint32_t kSingleMaxLen = 384; // reads up to this length are one item each
+const uint32_t kSmemCtl = 14336 + 256;
+const uint32_t kSmemLimit = 227 * 1024;
+
+inline uint32_t up16(uint32_t v) { return (v + 15u) & ~15u; }
+
+} // namespace
+
+struct b200sk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;  // compute stream of the host path
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    DevBuf meta;       // [0] ticket, [1] flags, [2] n_items, [3] max_len, [4] scan ticket  (u64 each)
+    DevBuf tile_state; // main kernel look-back words
+    DevBuf scan_state; // item scan look-back words
+    DevBuf item_first;
+    DevBuf circ_bases, circ_off;
+    // host path device buffers
+    DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;
+    HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
+    uint64_t launches = 0;
+    std::string last_error;
+};
+
+namespace {
+
+int cuda_fail(b200sk_ctx *ctx, cudaError_t e, const char *what) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    if (ctx) ctx->last_error = buf;
+    return B200SK_ERR_CUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); \
+    } while (0)
+
+// Build the tile plan for a batch whose longest read is max_len (0 = unknown -> chunked geometry).
+int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
+    const int mode = p.mode;
+    const int k = p.k, w = p.w, s = p.s;
+    const int d = mode == B200SK_MODE_SYNCMER ? k - s : 0;
+    const uint32_t ww = mode == B200SK_MODE_MINIMIZER ? (uint32_t)w : mode == B200SK_MODE_SYNCMER ? 2u * d : 0u;
+    uint64_t halo; // bases an item touches beyond its C positions
+    double density;
+    switch (mode) {
+    case B200SK_MODE_MINIMIZER: halo = (uint64_t)w + k - 1; density = 2.0 / (w + 1.0); break;
+    case B200SK_MODE_SYNCMER: halo = 2ull * d + s - 1; density = 2.0 / (d + 1.0); break;
+    default: halo = (uint64_t)k - 1; density = 1.0; break;
+    }
+    const uint64_t ext = p.circular ? (uint64_t)(k - 1) : 0;
+    if (max_len) max_len += ext;
+    pl.chunked = !(max_len && max_len <= kSingleMaxLen);
+    if (!pl.chunked) {
+        int32_t st;
+        uint32_t np = read_positions(mode, max_len, max_len, k, w, s, &st);
+        pl.C = np ? np : 1;
+        pl.span_max = (uint32_t)max_len;
+    } else {
+        pl.C = kChunk;
+        if ((uint64_t)pl.C + halo > 60000) return B200SK_ERR_UNSUPPORTED;
+        pl.span_max = (uint32_t)(pl.C + halo);
+    }
+    if (pl.span_max < 16) pl.span_max = 16;
+    const bool sparse = mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER;
+    pl.lcap = 0;
+    if (sparse) {
+        double e = pl.C * density * 1.5 + 8.0;
+        pl.lcap = (uint32_t)std::min<double>(pl.C, e);
+        if (pl.lcap < 1) pl.lcap = 1;
+    }
+    for (int T : {128, 64, 32}) {
+        pl.T = T;
+        pl.sm_tile = kSmemCtl;
+        pl.sm_tile_bytes = up16((uint32_t)T * pl.span_max + 32);
+        pl.sm_ring = pl.sm_tile + pl.sm_tile_bytes;
+        uint64_t ring = (uint64_t)ww * T * 8 + (uint64_t)d * T * 8 + (uint64_t)ww * T * 2;
+        if (ring > kSmemLimit) continue;
+        pl.sm_ring_bytes = up16((uint32_t)ring);
+        pl.sm_listv = pl.sm_ring + pl.sm_ring_bytes;
+        pl.sm_listp = pl.sm_listv + up16(pl.lcap * T * 8);
+        pl.sm_total = pl.sm_listp + up16(pl.lcap * T * 2);
+        if (pl.sm_total <= 112 * 1024) return 0;
+    }
+    if (pl.sm_total <= kSmemLimit) return 0; // T = 32, one CTA per SM
+    return B200SK_ERR_UNSUPPORTED;
+}
+
+int ensure_meta(b200sk_ctx *ctx) {
+    CK(ctx->meta.reserve(64));
+    return 0;
+}
+
+// Everything that runs on the device for one batch (no host synchronisation unless the longest
+// read must be measured).  d_flags: where the kernels OR their flags (device memory).
+int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, const uint64_t *d_off,
+            uint64_t n_reads, uint64_t n_bases, uint64_t *d_val, uint32_t *d_pos, uint64_t *d_ooff,
+            int32_t *d_status, uint64_t capacity, uint64_t out_base, cudaStream_t st, uint32_t *d_flags) {
+    int rc = b200sk_check_params(&p);
+    if (rc) return rc;
+    if (!d_off || !d_ooff || (n_bases && !d_bases)) return B200SK_ERR_BAD_ARG;
+    if (((uintptr_t)d_bases & 15u) != 0) return B200SK_ERR_BAD_ARG;
+    if (p.mode == B200SK_MODE_KMER || p.mode == B200SK_MODE_PROTEIN) return B200SK_ERR_UNSUPPORTED;
+    if ((rc = ensure_meta(ctx))) return rc;
+    unsigned long long *meta = (unsigned long long *)ctx->meta.p;
+    CK(cudaMemsetAsync(meta, 0, 64, st));
+    if (n_reads == 0) {
+        uint64_t zero = out_base;
+        CK(cudaMemcpyAsync(d_ooff, &zero, 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    b200sk_params q = p;
+    // syncmer with s == k degenerates to "every k-mer" (sketch.go:160,328-331)
+    if (q.mode == B200SK_MODE_SYNCMER && q.s == q.k) { q.mode = B200SK_MODE_NTHASH; q.canonical = 1; }
+    if (q.mode == B200SK_MODE_MINIMIZER || q.mode == B200SK_MODE_SYNCMER) q.canonical = 1;
+
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bases = d_bases; a.off = d_off; a.off_orig = nullptr; a.n_reads = n_reads;
+    a.mode = q.mode; a.k = q.k; a.w = q.w; a.s = q.s; a.canonical = q.canonical; a.frame = q.frame;
+
+    if (q.circular) {
+        // seq2 = S + S[0:k-1] (iterator.go:642-646, sketch.go:106-110): materialise the extended
+        // batch once on the device; the kernels then see ordinary linear reads.
+        CK(ctx->circ_bases.reserve(n_bases + n_reads * (uint64_t)(q.k - 1) + 64));
+        CK(ctx->circ_off.reserve((n_reads + 1) * 8));
+        CK(ctx->scan_state.reserve(((n_reads + 1023) / 1024 + 1) * 8));
+        CK(cudaMemsetAsync(ctx->scan_state.p, 0, ((n_reads + 1023) / 1024 + 1) * 8, st));
+        CK(launch_circularize(d_bases, d_off, n_reads, q.k, (uint8_t *)ctx->circ_bases.p,
+                              (uint64_t *)ctx->circ_off.p, (uint64_t *)ctx->scan_state.p, meta + 4, st));
+        ctx->launches += 2;
+        a.off_orig = d_off;
+        a.bases = (const uint8_t *)ctx->circ_bases.p;
+        a.off = (const uint64_t *)ctx->circ_off.p;
+        n_bases += n_reads * (uint64_t)(q.k - 1);
+    }
+
+    uint64_t max_len = p.max_read_len;
+    Plan pl;
+    uint64_t n_items_host = n_reads;
+    bool have_items_host = true;
+    if (max_len == 0) {
+        // measure the longest read (and, with the chunked geometry, the item count)
+        a.C = kChunk;
+        CK(launch_prepass(a, meta + 2, st));
+        ctx->launches++;
+        unsigned long long hm[2];
+        CK(cudaMemcpyAsync(hm, meta + 2, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        max_len = hm[1] ? hm[1] : 1;
+        if (q.circular) max_len = max_len > (uint64_t)(q.k - 1) ? max_len - (q.k - 1) : 1; // plan re-adds it
+        if ((rc = make_plan(q, max_len, pl))) return rc;
+        if (pl.chunked) n_items_host = hm[0];
+    } else {
+        if ((rc = make_plan(q, max_len, pl))) return rc;
+        if (pl.chunked) {
+            a.C = pl.C;
+            CK(launch_prepass(a, meta + 2, st));
+            ctx->launches++;
+            have_items_host = false;
+        }
+    }
+    a.C = pl.C; a.span_max = pl.span_max; a.lcap = pl.lcap;
+    a.sm_tile = pl.sm_tile; a.sm_tile_bytes = pl.sm_tile_bytes; a.sm_ring = pl.sm_ring;
+    a.sm_ring_bytes = pl.sm_ring_bytes; a.sm_listv = pl.sm_listv; a.sm_listp = pl.sm_listp;
+    a.sm_total = pl.sm_total;
+
+    uint64_t items_bound = n_items_host;
+    if (pl.chunked) {
+        if (!have_items_host) items_bound = n_reads + n_bases / pl.C + 1;
+        CK(ctx->item_first.reserve((n_reads + 1) * 8));
+        const size_t sbytes = ((n_reads + 1023) / 1024 + 1) * 8;
+        CK(ctx->scan_state.reserve(sbytes));
+        CK(cudaMemsetAsync(ctx->scan_state.p, 0, sbytes, st));
+        CK(cudaMemsetAsync(meta + 4, 0, 8, st));
+        CK(launch_scan_items(a, (uint64_t *)ctx->item_first.p, (uint64_t *)ctx->scan_state.p, meta + 4, st));
+        ctx->launches++;
+        a.item_first = (const uint64_t *)ctx->item_first.p;
+        a.n_items_dev = (const uint64_t *)ctx->item_first.p + n_reads;
+        a.n_items = 0;
+    } else {
+        a.item_first = nullptr;
+        a.n_items_dev = nullptr;
+        a.n_items = n_reads;
+    }
+    const uint64_t n_tiles = (items_bound + pl.T - 1) / pl.T + 1;
+    CK(ctx->tile_state.reserve(n_tiles * 8));
+    CK(cudaMemsetAsync(ctx->tile_state.p, 0, n_tiles * 8, st));
+    a.out_val = d_val; a.out_pos = p.want_pos ? d_pos : nullptr; a.out_off = d_ooff; a.status = d_status;
+    a.capacity = d_val ? capacity : 0; a.out_base = out_base;
+    a.tile_state = (uint64_t *)ctx->tile_state.p;
+    a.ticket = meta + 0;
+    a.flags = d_flags ? d_flags : (uint32_t *)(meta + 1);
+    const int occ = main_kernel_occupancy(a, pl.T);
+    uint64_t blocks = (uint64_t)occ * ctx->sm_count;
+    if (blocks > n_tiles) blocks = n_tiles;
+    if (blocks < 1) blocks = 1;
+    CK(launch_main(a, pl.T, (int)blocks, st));
+    ctx->launches++;
+    return 0;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int b200sk_version(void) { return 100; }
+
+int b200sk_check_params(const b200sk_params *p) {
+    if (!p) return B200SK_ERR_BAD_ARG;
+    switch (p->mode) {
+    case B200SK_MODE_KMER:
+        if (p->k < 1) return B200SK_ERR_INVALID_K;       // iterator.go:669
+        if (p->k > 32) return B200SK_ERR_K_OVERFLOW;     // kmers.Encode, iterator.go:742
+        return 0;
+    case B200SK_MODE_NTHASH:
+        if (p->k < 1) return B200SK_ERR_INVALID_K;       // iterator.go:616
+        return 0;
+    case B200SK_MODE_MINIMIZER:
+        if (p->k < 1) return B200SK_ERR_INVALID_K;       // sketch.go:86
+        if (p->w < 1) return B200SK_ERR_INVALID_W;       // sketch.go:89 (w > 2^31-1 cannot be expressed in int32)
+        return 0;
+    case B200SK_MODE_SYNCMER:
+        if (p->k < 1) return B200SK_ERR_INVALID_K;       // sketch.go:143
+        if (p->s > p->k || p->s <= 0) return B200SK_ERR_INVALID_S; // sketch.go:146 (s<0: uint(s) overflows NewHasher)
+        return 0;
+    case B200SK_MODE_PROTEIN:
+        if (p->k < 1) return B200SK_ERR_INVALID_K;       // iterator-protein.go:47
+        if (p->frame < -3 || p->frame > 3 || p->frame == 0) return B200SK_ERR_INVALID_FRAME; // codon_tables.go:209
+        return 0;
+    default:
+        return B200SK_ERR_BAD_ARG;
+    }
+}
+
+const char *b200sk_strerror(int code) {
+    switch (code) {
+    case B200SK_OK: return "ok";
+    case B200SK_ERR_INVALID_K: return "sketches: invalid k-mer size";
+    case B200SK_ERR_SHORT_SEQ: return "sketches: sequence too short";
+    case B200SK_ERR_INVALID_W: return "kmers: invalid minimimzer window";
+    case B200SK_ERR_INVALID_S: return "kmers: invalid s-mer size";
+    case B200SK_ERR_ILLEGAL_BASE: return "sketches: illegal base";
+    case B200SK_ERR_K_OVERFLOW: return "unikmer: k-mer size (1-32) overflow";
+    case B200SK_ERR_INVALID_FRAME: return "seq: invalid frame. available: 1, 2, 3, -1, -2, -3";
+    case B200SK_ERR_CODON_TABLE: return "seq: invalid codon table";
+    case B200SK_ERR_TRANSLATE_SHORT: return "seq: sequence too short to translate";
+    case B200SK_ERR_INVALID_CODON: return "seq: invalid DNA base";
+    case B200SK_ERR_CUDA: return "b200sketch: CUDA error";
+    case B200SK_ERR_NO_DEVICE: return "b200sketch: no CUDA device (there is no CPU fallback)";
+    case B200SK_ERR_UNSUPPORTED: return "b200sketch: parameters outside the implemented range";
+    case B200SK_ERR_CAPACITY: return "b200sketch: output capacity too small";
+    case B200SK_ERR_BAD_ARG: return "b200sketch: bad argument";
+    case B200SK_ERR_NOMEM: return "b200sketch: out of memory";
+    default: return "b200sketch: unknown error";
+    }
+}
+
+int b200sk_create(b200sk_ctx **out, int device) {
+    if (!out) return B200SK_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return B200SK_ERR_NO_DEVICE;
+    }
+    b200sk_ctx *ctx = new b200sk_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B200SK_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return B200SK_ERR_CUDA;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void b200sk_destroy(b200sk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->circ_bases,
+                      &ctx->circ_off, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
+                      &ctx->d_status})
+        b->release();
+    for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+}
+
+void *b200sk_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void b200sk_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+const char *b200sk_last_error(const b200sk_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t b200sk_kernel_launches(const b200sk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t b200sk_output_bound(const b200sk_params *p, uint64_t n_bases, uint64_t n_reads, int exact) {
+    if (!p) return 0;
+    const uint64_t ext = p->circular ? n_reads * (uint64_t)(p->k > 0 ? p->k - 1 : 0) : 0;
+    const uint64_t nb = n_bases + ext;
+    switch (p->mode) {
+    case B200SK_MODE_KMER: return (p->canonical ? 1 : 2) * nb;
+    case B200SK_MODE_NTHASH: return nb;
+    case B200SK_MODE_PROTEIN: return nb / 3 + n_reads;
+    case B200SK_MODE_MINIMIZER:
+        if (exact || p->w <= 1) return nb;
+        return (uint64_t)(nb * (2.0 / (p->w + 1.0)) * 1.25) + n_reads + 1024;
+    case B200SK_MODE_SYNCMER: {
+        const int d = p->k - p->s;
+        if (exact || d <= 0) return nb;
+        return (uint64_t)(nb * (2.0 / (d + 1.0)) * 1.25) + n_reads + 1024;
+    }
+    default: return 0;
+    }
+}
+
+int b200sk_enqueue_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,
+                          const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, uint64_t *d_out_val,
+                          uint32_t *d_out_pos, uint64_t *d_out_off, int32_t *d_read_status, uint64_t capacity,
+                          void *stream, uint32_t *d_flags) {
+    if (!ctx || !p) return B200SK_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (d_flags) CK(cudaMemsetAsync(d_flags, 0, 4, (cudaStream_t)stream));
+    return enqueue(ctx, *p, d_bases, d_read_off, n_reads, n_bases, d_out_val, d_out_pos, d_out_off,
+                   d_read_status, capacity, 0, (cudaStream_t)stream, d_flags);
+}
+
+int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,
+                      const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, uint64_t *d_out_val,
+                      uint32_t *d_out_pos, uint64_t *d_out_off, int32_t *d_read_status, uint64_t capacity,
+                      void *stream, uint64_t *n_out) {
+    if (!ctx || !p) return B200SK_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = enqueue(ctx, *p, d_bases, d_read_off, n_reads, n_bases, d_out_val, d_out_pos, d_out_off,
+                     d_read_status, capacity, 0, st, nullptr);
+    if (rc) return rc;
+    uint64_t total = 0;
+    unsigned long long flags = 0;
+    CK(cudaMemcpyAsync(&total, d_out_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&flags, (unsigned long long *)ctx->meta.p + 1, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_out) *n_out = total;
+    if (flags & B200SK_FLAG_SPAN) return B200SK_ERR_BAD_ARG; // max_read_len hint smaller than a read
+    if (flags & B200SK_FLAG_CAPACITY) return B200SK_ERR_CAPACITY;
+    return 0;
+}
+
+// Host entry point.  Sub-batches of reads flow through three streams (H2D copy, kernels, D2H copy)
+// so the PCIe transfers of neighbouring sub-batches overlap the kernels.
+int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
+               uint64_t n_reads, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+               int32_t **read_status, uint64_t *n_out) {
+    if (!ctx || !p || !read_off) return B200SK_ERR_BAD_ARG;
+    int rc = b200sk_check_params(p);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    const uint64_t base0 = read_off[0];
+    const uint64_t n_bases = read_off[n_reads] - base0;
+    // v1: one sub-batch (the pipelined version splits here)
+    CK(ctx->d_bases.reserve(n_bases + 64));
+    CK(ctx->d_off.reserve((n_reads + 1) * 8));
+    CK(ctx->d_ooff.reserve((n_reads + 1) * 8));
+    CK(ctx->d_status.reserve((n_reads + 1) * 4));
+    CK(ctx->h_ooff.reserve((n_reads + 1) * 8));
+    CK(ctx->h_status.reserve((n_reads + 1) * 4));
+    if (n_bases) CK(cudaMemcpyAsync(ctx->d_bases.p, bases + base0, n_bases, cudaMemcpyHostToDevice, st));
+    std::vector<uint64_t> rel;
+    const uint64_t *off_src = read_off;
+    if (base0 != 0) {
+        rel.resize(n_reads + 1);
+        for (uint64_t i = 0; i <= n_reads; i++) rel[i] = read_off[i] - base0;
+        off_src = rel.data();
+    }
+    CK(cudaMemcpyAsync(ctx->d_off.p, off_src, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint64_t cap = b200sk_output_bound(p, n_bases, n_reads, 0);
+    uint64_t total = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->d_val.reserve(cap * 8 + 64));
+        if (p->want_pos) CK(ctx->d_pos.reserve(cap * 4 + 64));
+        rc = b200sk_run_device(ctx, p, (const uint8_t *)ctx->d_bases.p, (const uint64_t *)ctx->d_off.p, n_reads,
+                               n_bases, (uint64_t *)ctx->d_val.p, p->want_pos ? (uint32_t *)ctx->d_pos.p : nullptr,
+                               (uint64_t *)ctx->d_ooff.p, (int32_t *)ctx->d_status.p, cap, st, &total);
+        if (rc != B200SK_ERR_CAPACITY) break;
+        cap = total; // exact requirement reported by the first pass
+    }
+    if (rc) return rc;
+    CK(ctx->h_val.reserve(total * 8 + 8));
+    if (p->want_pos) CK(ctx->h_pos.reserve(total * 4 + 4));
+    if (total) {
+        CK(cudaMemcpyAsync(ctx->h_val.p, ctx->d_val.p, total * 8, cudaMemcpyDeviceToHost, st));
+        if (p->want_pos) CK(cudaMemcpyAsync(ctx->h_pos.p, ctx->d_pos.p, total * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(ctx->h_ooff.p, ctx->d_ooff.p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (n_reads) CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (out_val) *out_val = (uint64_t *)ctx->h_val.p;
+    if (out_pos) *out_pos = p->want_pos ? (uint32_t *)ctx->h_pos.p : nullptr;
+    if (out_off) *out_off = (uint64_t *)ctx->h_ooff.p;
+    if (read_status) *read_status = (int32_t *)ctx->h_status.p;
+    if (n_out) *n_out = total;
+    return 0;
+}
+
+} // extern "C"

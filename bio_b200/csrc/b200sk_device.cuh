@@ -1,0 +1,166 @@
+// Device-side building blocks shared by the sketching kernels (sm_100a only).
+//
+//  * ntHash-1 seeds / rotations (arithmetic of will-rowe/nthash v0.4.0 as used at
+//    sketches/iterator.go:649,659 and sketches/sketch.go:120,179,184,212,319,344,367)
+//  * 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) + mbarrier wrappers
+//  * single-pass ordered allocation of output ranges across tiles
+//    (decoupled look-back over a per-tile status word)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200sk {
+
+// ------------------------------------------------------------------ ntHash
+__device__ __host__ __forceinline__ uint64_t rol64(uint64_t v, unsigned n) {
+    n &= 63u;
+    return n ? (v << n) | (v >> (64u - n)) : v;
+}
+__device__ __host__ __forceinline__ uint64_t ror64(uint64_t v, unsigned n) {
+    n &= 63u;
+    return n ? (v >> n) | (v << (64u - n)) : v;
+}
+__device__ __forceinline__ uint64_t rol1(uint64_t v) { return (v << 1) | (v >> 63); }
+__device__ __forceinline__ uint64_t ror1(uint64_t v) { return (v >> 1) | (v << 63); }
+
+#define B200SK_SEED_A 0x3c8bfbb395c60474ULL
+#define B200SK_SEED_C 0x3193c18562a02b4cULL
+#define B200SK_SEED_G 0x20323ed082572324ULL
+#define B200SK_SEED_T 0x295549f54be24456ULL
+
+// seedTab[b] of the hasher: nonzero for A,C,G,T,U (either case) and for the
+// byte values 1,3,4,5,7 which the complement lookup seedTab[b & 7] lands on.
+__device__ __host__ __forceinline__ uint64_t seed_of_byte(unsigned b) {
+    switch (b) {
+    case 'A': case 'a': case 4: case 5: return B200SK_SEED_A;
+    case 'C': case 'c': case 7: return B200SK_SEED_C;
+    case 'G': case 'g': case 3: return B200SK_SEED_G;
+    case 'T': case 't': case 'U': case 'u': case 1: return B200SK_SEED_T;
+    default: return 0;
+    }
+}
+__device__ __host__ __forceinline__ uint64_t fwd_seed(unsigned b) { return seed_of_byte(b & 0xffu); }
+__device__ __host__ __forceinline__ uint64_t rev_seed(unsigned b) { return seed_of_byte(b & 7u); }
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk global->shared copy, completion counted in bytes on `bar`.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------ ordered allocation
+// status word per tile: [63:62] flag, [61:0] value.
+#define B200SK_FLAG_EMPTY 0ULL
+#define B200SK_FLAG_AGG 1ULL
+#define B200SK_FLAG_INC 2ULL
+#define B200SK_VAL_MASK ((1ULL << 62) - 1)
+
+__device__ __forceinline__ uint64_t ld_state(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by one full warp.  Publishes `total` for `tile` and returns the sum of
+// the totals of all tiles before it (exclusive prefix).  Tiles are handed out by
+// a ticket counter, so every predecessor is already running: no deadlock.
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint64_t tile, uint64_t total) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0) {
+        if (lane == 0) st_state(state, (B200SK_FLAG_INC << 62) | total);
+        return 0;
+    }
+    if (lane == 0) st_state(state + tile, (B200SK_FLAG_AGG << 62) | total);
+    uint64_t excl = 0;
+    int64_t idx = (int64_t)tile - 1 - (int64_t)lane;
+    while (true) {
+        uint64_t v = (B200SK_FLAG_INC << 62); // lanes before tile 0 read as "inclusive 0"
+        if (idx >= 0) {
+            do {
+                v = ld_state(state + idx);
+            } while ((v >> 62) == B200SK_FLAG_EMPTY);
+        }
+        const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
+        uint64_t contrib = v & B200SK_VAL_MASK;
+        if (inc) {
+            const unsigned first = __ffs(inc) - 1;
+            if (lane > first) contrib = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (inc) break;
+        idx -= 32;
+    }
+    if (lane == 0) st_state(state + tile, (B200SK_FLAG_INC << 62) | (excl + total));
+    return excl;
+}
+
+// Block-wide exclusive scan of one uint32 per thread (blockDim.x <= 1024, multiple of 32).
+// warp_sums: shared scratch of >= 33 uint32.  Returns exclusive prefix; *block_total = sum.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t *block_total) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < nw ? warp_sums[lane] : 0;
+        uint32_t si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= (unsigned)o) si += t;
+        }
+        if (lane < nw) warp_sums[lane] = si - s;
+        if (lane == 31) warp_sums[32] = si;
+    }
+    __syncthreads();
+    uint32_t excl = warp_sums[wid] + inc - v;
+    *block_total = warp_sums[32];
+    __syncthreads();
+    return excl;
+}
+
+} // namespace b200sk

@@ -1,0 +1,155 @@
+/*
+ * b200sketch.h -- C ABI of libb200sketch.so: the batch-shaped drop-in boundary
+ * for the sketching hot path of shenwei356/bio (reference @ 7b48836e).
+ *
+ * The reference has no FFI; its boundary for this path is the exported Go
+ * method set of package `sketches` (pull iterators, one uint64 per Next()).
+ * A per-element cgo call (~100 ns) would dwarf the 8 ns/base the Go loop
+ * needs, so the ABI is batch-shaped: the host side packs the records of a
+ * fastx chunk into one pinned byte buffer + offsets, one call sketches the
+ * whole batch on the GPU, and the Go shim (go/sketchesgpu)
+ * replays the per-read slices through Next()/Index().
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to the reference root).  Plain pointers and sizes only -- no torch types.
+ *
+ * Output contract (all modes): for read r the emitted elements are
+ * out_val[out_off[r] .. out_off[r+1]) in exactly the order the reference's
+ * Next() loop yields them; out_pos holds what Index() returns after each
+ * Next().  read_status[r] carries the error the reference constructor (or
+ * NextKmer) would have returned for that read (0 = ok); a read whose
+ * constructor fails emits nothing.
+ */
+#ifndef B200SKETCH_H
+#define B200SKETCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error / status codes ------------------------------------------------ */
+#define B200SK_OK 0
+#define B200SK_ERR_INVALID_K (-1)       /* sketches/iterator.go:35  ErrInvalidK    */
+#define B200SK_ERR_SHORT_SEQ (-2)       /* sketches/iterator.go:41  ErrShortSeq    */
+#define B200SK_ERR_INVALID_W (-3)       /* sketches/sketch.go:36    ErrInvalidW    */
+#define B200SK_ERR_INVALID_S (-4)       /* sketches/sketch.go:33    ErrInvalidS    */
+#define B200SK_ERR_ILLEGAL_BASE (-5)    /* sketches/iterator.go:44  ErrIllegalBase */
+#define B200SK_ERR_K_OVERFLOW (-6)      /* kmers.ErrKOverflow (k > 32), iterator.go:742 */
+#define B200SK_ERR_INVALID_FRAME (-7)   /* seq/codon_tables.go:209-211             */
+#define B200SK_ERR_CODON_TABLE (-8)     /* seq/seq.go:685 Translate: unknown table */
+#define B200SK_ERR_TRANSLATE_SHORT (-9) /* seq/codon_tables.go:206-208             */
+#define B200SK_ERR_INVALID_CODON (-10)  /* seq.ErrInvalidDNABase (not reachable: allowUnknownCodon=true) */
+/* library-level conditions (no reference counterpart) */
+#define B200SK_ERR_CUDA (-100)          /* a CUDA runtime call failed; see b200sk_last_error */
+#define B200SK_ERR_NO_DEVICE (-101)     /* no CUDA device: there is NO CPU fallback */
+#define B200SK_ERR_UNSUPPORTED (-102)   /* parameter outside what the kernels implement */
+#define B200SK_ERR_CAPACITY (-103)      /* caller-provided device output too small; *n_out = needed */
+#define B200SK_ERR_BAD_ARG (-104)
+#define B200SK_ERR_NOMEM (-105)
+
+/* ---- modes: which reference constructor the batch stands for ------------- */
+#define B200SK_MODE_KMER 0      /* NewKmerIterator      sketches/iterator.go:668 + NextKmer :708   */
+#define B200SK_MODE_NTHASH 1    /* NewHashIterator      sketches/iterator.go:615 + NextHash :658   */
+#define B200SK_MODE_MINIMIZER 2 /* NewMinimizerSketch   sketches/sketch.go:85    + NextMinimizer :205 */
+#define B200SK_MODE_SYNCMER 3   /* NewSyncmerSketch     sketches/sketch.go:142   + NextSyncmer :312   */
+#define B200SK_MODE_PROTEIN 4   /* NewProteinIterator   sketches/iterator-protein.go:46 + Next :76   */
+
+/* seq.Alphabet of the records (only NextKmer's non-canonical second strand
+ * depends on it: RevComInplace, sketches/iterator.go:719, seq/seq.go:350). */
+#define B200SK_ALPHABET_DNA_REDUNDANT 0 /* seq/alphabet.go:361 */
+#define B200SK_ALPHABET_DNA 1           /* seq/alphabet.go:353 */
+#define B200SK_ALPHABET_RNA_REDUNDANT 2 /* seq/alphabet.go:377 */
+#define B200SK_ALPHABET_RNA 3           /* seq/alphabet.go:369 */
+#define B200SK_ALPHABET_UNLIMIT 4       /* seq/alphabet.go:399: complement is a no-op */
+
+/* Constructor arguments, shared by every read of the batch. */
+typedef struct b200sk_params {
+    int32_t mode;        /* B200SK_MODE_*                                             */
+    int32_t k;           /* k-mer size (amino acids for MODE_PROTEIN)                 */
+    int32_t w;           /* minimizer window (MODE_MINIMIZER)                         */
+    int32_t s;           /* s-mer size (MODE_SYNCMER)                                 */
+    int32_t canonical;   /* KMER / NTHASH only; minimizer and syncmer are always canonical (sketch.go:212,319) */
+    int32_t circular;    /* append seq[0:k-1] (iterator.go:642-646, sketch.go:106-110,163-167)  */
+    int32_t codon_table; /* MODE_PROTEIN: NCBI transl_table id (seq/codon_tables.go:431-640)    */
+    int32_t frame;       /* MODE_PROTEIN: 1,2,3,-1,-2,-3 (seq/codon_tables.go:205)              */
+    int32_t alphabet;    /* B200SK_ALPHABET_*                                         */
+    int32_t want_pos;    /* 0: do not produce out_pos (dense modes: pos is just the running index) */
+    uint32_t max_read_len; /* optional hint: length of the longest read (0 = unknown; the library then
+                              measures it on the device, which costs one extra pass over read_off) */
+    int32_t reserved[5];
+} b200sk_params;
+
+typedef struct b200sk_ctx b200sk_ctx; /* one per caller thread and device; not thread-safe */
+
+/* Library / device lifetime.  device = CUDA ordinal.  There is no CPU
+ * fallback: without a usable device this returns B200SK_ERR_NO_DEVICE. */
+int b200sk_create(b200sk_ctx **ctx, int device);
+void b200sk_destroy(b200sk_ctx *ctx);
+
+/* C-owned pinned staging: the Go side packs record.Seq.Seq bytes straight into
+ * this buffer (cgo must not let C retain Go pointers across calls). */
+void *b200sk_alloc_pinned(size_t bytes);
+void b200sk_free_pinned(void *p);
+
+/* The constructor checks every New*() performs before looking at a sequence
+ * (iterator.go:616,669; sketch.go:86-91,143-148; iterator-protein.go:47;
+ * codon_tables.go:209).  Returns 0 or the B200SK_ERR_* the constructor returns. */
+int b200sk_check_params(const b200sk_params *p);
+
+/* Upper bound on the number of elements a batch can emit (for sizing device
+ * output in b200sk_run_device).  exact=0 returns the default (expected-density)
+ * capacity the host path starts with. */
+uint64_t b200sk_output_bound(const b200sk_params *p, uint64_t n_bases, uint64_t n_reads, int exact);
+
+/* Host entry point: replaces the per-record loop
+ *     it, err := sketches.NewXxx(record.Seq, ...); for { v, ok := it.Next(); i := it.Index() }
+ * over the n_reads records of a batch.  bases = concatenated record.Seq.Seq
+ * bytes (ASCII as delivered by seqio/fastx.Reader.Read, reader.go:233),
+ * read_off[n_reads+1] = byte offsets.  Host<->device copies are pipelined
+ * inside.  Outputs are library-owned pinned host arrays, valid until the next
+ * b200sk_run / b200sk_destroy on this ctx. */
+int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p,
+               const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+               uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+               int32_t **read_status, uint64_t *n_out);
+
+/* Device entry point: same contract with every buffer already resident in HBM
+ * (what a multi-stage GPU pipeline or the multi-GPU shard driver calls).
+ * d_bases must be readable up to the next 16-byte boundary past its end (TMA
+ * bulk copies move 16-byte units).  d_out_pos may be NULL.  capacity = elements
+ * available in d_out_val/d_out_pos.  Work is enqueued on `stream` (a
+ * cudaStream_t passed as void*); *n_out is valid after the call returns (the
+ * call synchronises the stream once to read it).  On B200SK_ERR_CAPACITY
+ * nothing was written to d_out_val/pos and *n_out holds the required capacity. */
+int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p,
+                      const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                      uint64_t n_bases,
+                      uint64_t *d_out_val, uint32_t *d_out_pos, uint64_t *d_out_off,
+                      int32_t *d_read_status, uint64_t capacity, void *stream, uint64_t *n_out);
+
+/* Same, but fully asynchronous: no host synchronisation; the element count is
+ * left in d_out_off[n_reads] and a capacity overflow is reported through
+ * *d_flags (bit 0) on the device.  Used inside timed regions. */
+int b200sk_enqueue_device(b200sk_ctx *ctx, const b200sk_params *p,
+                          const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                          uint64_t n_bases,
+                          uint64_t *d_out_val, uint32_t *d_out_pos, uint64_t *d_out_off,
+                          int32_t *d_read_status, uint64_t capacity, void *stream,
+                          uint32_t *d_flags);
+
+/* Error text: the reference's error strings for the codes that mirror them
+ * (iterator.go:34-53, sketch.go:32-42), library text otherwise. */
+const char *b200sk_strerror(int code);
+const char *b200sk_last_error(const b200sk_ctx *ctx); /* CUDA error detail */
+
+/* Introspection for the bench / tests. */
+uint64_t b200sk_kernel_launches(const b200sk_ctx *ctx); /* kernels launched so far on this ctx */
+int b200sk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SKETCH_H */
