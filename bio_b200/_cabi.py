@@ -39,7 +39,7 @@ EXPORTS = (
     "b200sk_create", "b200sk_destroy", "b200sk_alloc_pinned", "b200sk_free_pinned",
     "b200sk_check_params", "b200sk_output_bound", "b200sk_run", "b200sk_run_device",
     "b200sk_enqueue_device", "b200sk_strerror", "b200sk_last_error", "b200sk_kernel_launches",
-    "b200sk_version",
+    "b200sk_version", "b200sk_timing_enable", "b200sk_timing_collect",
 )
 
 
@@ -119,6 +119,10 @@ def lib():
     L.b200sk_last_error.argtypes = [vp]
     L.b200sk_kernel_launches.restype = C.c_uint64
     L.b200sk_kernel_launches.argtypes = [vp]
+    L.b200sk_timing_enable.restype = None
+    L.b200sk_timing_enable.argtypes = [vp, C.c_int]
+    L.b200sk_timing_collect.restype = C.c_int
+    L.b200sk_timing_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -165,6 +169,17 @@ class Context:
 
     def _raise(self, rc):
         raise SketchError(rc, lib().b200sk_last_error(self._h).decode() if rc == ERR_CUDA else "")
+
+    def timing_enable(self, on=True):
+        lib().b200sk_timing_enable(self._h, int(on))
+
+    def timing_collect(self):
+        """(sum of main-kernel durations in ms, number of kernels) since the last collect."""
+        s, n = C.c_double(0), C.c_uint64(0)
+        rc = lib().b200sk_timing_collect(self._h, C.byref(s), C.byref(n))
+        if rc != 0:
+            self._raise(rc)
+        return s.value, int(n.value)
 
     def kernel_launches(self):
         return int(lib().b200sk_kernel_launches(self._h))

@@ -102,6 +102,8 @@ struct b200sk_ctx {
     DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;
     HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
     uint64_t launches = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     std::string last_error;
 };
 
@@ -280,8 +282,18 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     uint64_t blocks = (uint64_t)occ * ctx->sm_count;
     if (blocks > n_tiles) blocks = n_tiles;
     if (blocks < 1) blocks = 1;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->timing) {
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaEventRecord(ev0, st));
+    }
     CK(launch_main(a, pl.T, (int)blocks, st));
     ctx->launches++;
+    if (ctx->timing) {
+        CK(cudaEventRecord(ev1, st));
+        ctx->timing_events.emplace_back(ev0, ev1);
+    }
     return 0;
 }
 
@@ -390,6 +402,28 @@ void *b200sk_alloc_pinned(size_t bytes) {
 }
 void b200sk_free_pinned(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+void b200sk_timing_enable(b200sk_ctx *ctx, int on) {
+    if (ctx) ctx->timing = on != 0;
+}
+int b200sk_timing_collect(b200sk_ctx *ctx, double *sum_ms, uint64_t *n) {
+    if (!ctx) return B200SK_ERR_BAD_ARG;
+    double sum = 0;
+    uint64_t cnt = 0;
+    for (auto &pr : ctx->timing_events) {
+        float ms = 0;
+        CK(cudaEventSynchronize(pr.second));
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        sum += ms;
+        cnt++;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->timing_events.clear();
+    if (sum_ms) *sum_ms = sum;
+    if (n) *n = cnt;
+    return 0;
 }
 
 const char *b200sk_last_error(const b200sk_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }

@@ -147,6 +147,11 @@ const char *b200sk_last_error(const b200sk_ctx *ctx); /* CUDA error detail */
 
 /* Introspection for the bench / tests. */
 uint64_t b200sk_kernel_launches(const b200sk_ctx *ctx); /* kernels launched so far on this ctx */
+/* Kernel timing: when enabled, every batch brackets its main sketching kernel with CUDA events on the
+ * stream it is launched on.  b200sk_timing_collect waits for the pending pairs, adds their durations
+ * (milliseconds) into *sum_ms, their number into *n, and forgets them. */
+void b200sk_timing_enable(b200sk_ctx *ctx, int on);
+int b200sk_timing_collect(b200sk_ctx *ctx, double *sum_ms, uint64_t *n);
 int b200sk_version(void);
 
 #ifdef __cplusplus

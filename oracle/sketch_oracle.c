@@ -882,6 +882,7 @@ static void *ora_worker(void *arg) {
     ora_job *j = (ora_job *)arg;
     const ora_params *p = j->p;
     size_t cap = 1024;
+    uint64_t sum = 0, ties = 0; /* thread-local: the job structs share cache lines */
     uint64_t *val = (uint64_t *)malloc(cap * sizeof(uint64_t));
     int64_t *idx = (int64_t *)malloc(cap * sizeof(int64_t));
     for (uint64_t r = j->r0; r < j->r1; r++) {
@@ -904,10 +905,10 @@ static void *ora_worker(void *arg) {
         case 4: n = ora_protein_iterator(s, len, p->k, p->codon_table, p->frame, val, &err); break;
         default: err = ORA_ERR_INVALID_K;
         }
-        j->ties += (uint64_t)tie;
+        ties += (uint64_t)tie;
         if (j->status) j->status[r] = err;
         if (j->counts) j->counts[r] = (uint64_t)n;
-        for (int64_t i = 0; i < n; i++) j->sum += val[i];
+        for (int64_t i = 0; i < n; i++) sum += val[i];
         if (j->out_val) {
             uint64_t o = j->out_off[r];
             memcpy(j->out_val + o, val, (size_t)n * sizeof(uint64_t));
@@ -925,6 +926,7 @@ static void *ora_worker(void *arg) {
         }
     }
     free(val); free(idx);
+    j->sum = sum; j->ties = ties;
     return 0;
 }
 

@@ -1,0 +1,147 @@
+"""The CPU oracle against every known-answer vector the reference's own tests hold for the path
+(tests/golden/reference_vectors.json, extracted from the reference test sources by
+tests/golden/make_golden.py), plus the derived KATs of SURVEY.md 8c and the property
+'literal Go state machine == closed form'."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def test_minimizer_golden_vector(golden):
+    # sketches/sketch_test.go:33-76 (TestMinimizer): the one known-answer test on the path
+    g = golden["sketch"]["minimizer"]
+    vals, idxs, err, tie = oracle.minimizer(g["seq"], g["k"], g["w"])
+    assert err == 0
+    assert [int(v) for v in vals] == g["values"]
+    assert list(idxs) == [0, 1, 4, 7, 8]
+
+
+def test_nthash_full_vector(golden):
+    # full k=5 canonical vector for "GGCAAGTTCGTCA" (includes the 5 golden values)
+    g = golden["sketch"]["minimizer"]
+    vals, err = oracle.hash_iterator(g["seq"], g["k"], canonical=True)
+    assert err == 0
+    expect = [973456138564179607, 2645801399420473919, 7385093395039290540, 10471074397186032936,
+              1099502864234245338, 11675079549201129366, 8106728639853938941, 6763474888237448943,
+              2737971715116251183]
+    assert [int(v) for v in vals] == expect
+    for gv in g["values"]:
+        assert gv in expect
+
+
+def test_syncmer_commented_values(golden):
+    # sketches/sketch_test.go:111-116: the commented-out expectations are ntHash values of k-mers 2 and 4
+    g = golden["sketch"]["syncmer"]
+    hv, _ = oracle.hash_iterator(g["seq"], g["k"], canonical=True)
+    assert int(hv[2]) == g["commented_values"][0]
+    assert int(hv[4]) == g["commented_values"][1]
+    vals, idxs, err, _ = oracle.syncmer(g["seq"], g["k"], g["s"])
+    assert err == 0
+    assert list(idxs) == [0, 3, 5, 8, 11]
+    assert int(vals[-1]) == 1955511966892880774
+    for v, i in zip(vals, idxs):
+        assert int(v) == int(hv[i])
+
+
+def test_iterator_counts(golden):
+    # sketches/iterator_test.go:63,100: count-only assertions
+    for name in ("TestKmerIterator", "TestHashIterator"):
+        g = golden["iterator"][name]
+        if name == "TestKmerIterator":
+            codes, err, _ = oracle.kmer_iterator(g["seq"], g["k"], canonical=True)
+        else:
+            codes, err = oracle.hash_iterator(g["seq"], g["k"], canonical=True)
+        assert err == 0 and len(codes) == g["expected_count"]
+
+
+def test_kmer_code_kats(golden):
+    # SURVEY.md 8c derived KATs on the 100-bp string of iterator_test.go:32
+    s = golden["iterator"]["TestKmerIterator"]["seq"]
+    c, err, _ = oracle.kmer_iterator(s, 10, canonical=True)
+    assert [int(x) for x in c[:3]] == [49027, 196109, 784436]
+    c, _, _ = oracle.kmer_iterator(s, 5, canonical=False)
+    assert [int(x) for x in c[:3]] == [47, 191, 766]
+    c, _, _ = oracle.kmer_iterator(s, 5, canonical=True)
+    assert [int(x) for x in c[:3]] == [31, 7, 257]
+    # 100-bp string, k=21: w=11 -> 15 minimizers, s=11 -> 9 syncmers
+    v, i, _, _ = oracle.minimizer(s, 21, 11)
+    assert len(v) == 15 and (int(i[0]), int(v[0])) == (10, 1056107554325543116)
+    assert (int(i[1]), int(v[1])) == (15, 936594548439088653)
+    v, i, _, _ = oracle.syncmer(s, 21, 11)
+    assert len(v) == 9 and (int(i[0]), int(v[0])) == (5, 9632232635579148968)
+    assert (int(i[1]), int(v[1])) == (12, 10120577261530545435)
+
+
+def test_translate_golden(golden):
+    # seq/codon_tables_test.go:26-152 (TestCodonTableStranslation)
+    assert len(golden["codon"]) == 6
+    for t in golden["codon"]:
+        aa, err = oracle.translate(t["nt"], t["table"], t["frame"], trim=t["trim"], clean=t["clean"],
+                                   allow_unknown=t["allow_unknown"])
+        assert err == 0
+        assert aa.decode() == t["aa"]
+
+
+def test_error_codes():
+    assert oracle.hash_iterator("ACGT", 0)[1] == oracle.ERR_INVALID_K
+    assert oracle.hash_iterator("ACGT", 5)[1] == oracle.ERR_SHORT_SEQ
+    assert oracle.minimizer("ACGTACGT", 5, 0)[2] == oracle.ERR_INVALID_W
+    assert oracle.minimizer("ACGTACGT", 5, 5)[2] == oracle.ERR_SHORT_SEQ
+    assert oracle.syncmer("ACGTACGT", 5, 6)[2] == oracle.ERR_INVALID_S
+    assert oracle.syncmer("ACGTACGT", 5, 0)[2] == oracle.ERR_INVALID_S
+    assert oracle.syncmer("ACGTAC", 5, 2)[2] == oracle.ERR_SHORT_SEQ
+    c, err, eidx = oracle.kmer_iterator("ACGTAC-GTACGT", 4)
+    assert err == oracle.ERR_ILLEGAL_BASE and len(c) == 3 and eidx == 3
+    assert oracle.kmer_iterator("ACGT" * 20, 33)[1] == oracle.ERR_K_OVERFLOW
+    assert oracle.protein_iterator("ACGTACGT", 3)[1] == oracle.ERR_SHORT_SEQ
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"AC", b"ACGTN", b"A"])
+def test_literal_equals_closed_form(alphabet):
+    # minimizer == leftmost window minimum de-duplicated by position; syncmer == closed form
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(alphabet, dtype=np.uint8)
+    for _ in range(300):
+        n = int(rng.integers(1, 200))
+        s = alpha[rng.integers(0, len(alpha), size=n)]
+        k = int(rng.integers(1, 25))
+        w = int(rng.integers(1, 20))
+        ss = int(rng.integers(1, k + 1))
+        circ = bool(rng.integers(0, 2))
+        a = oracle.minimizer(s, k, w, circular=circ)
+        b = oracle.minimizer_closed(s, k, w, circular=circ)
+        assert a[2] == b[2]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        a = oracle.syncmer(s, k, ss, circular=circ)
+        b = oracle.syncmer_closed(s, k, ss, circular=circ)
+        assert a[2] == b[2]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_protein_iterator_counts():
+    # sketches/iterator-protein_test.go:58 is count-only: len(aa) - k + 1 hashes
+    s = "ATGACTGCCATGGAGGAGTCACAGTCGGATATCAGCCTCGAGCTCCCTCTGAGCCAGGAG"
+    for frame in (1, 2, 3, -1, -2, -3):
+        aa, err = oracle.translate(s, 1, frame)
+        h, err2 = oracle.protein_iterator(s, 5, 1, frame)
+        assert err == 0 and err2 == 0
+        assert len(h) == len(aa) - 5 + 1
+        assert int(h[0]) == oracle.wyhash(aa[:5], 1)
+
+
+def test_oracle_regression_fixture():
+    # the committed oracle_vectors.npz still equals what the oracle computes today
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    z = np.load(os.path.join(here, "golden", "oracle_vectors.npz"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mov", os.path.join(here, "golden", "make_oracle_vectors.py"))
+    mov = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mov)
+    for name, (mode, kw) in mov.CASES.items():
+        r = oracle.run_batch(z["bases"], z["off"], mode, threads=2, **kw)
+        assert np.array_equal(r["val"], z[name + "/val"]), name
+        assert np.array_equal(r["pos"], z[name + "/pos"]), name
+        assert np.array_equal(r["off"], z[name + "/off"]), name
+        assert np.array_equal(r["status"], z[name + "/status"]), name

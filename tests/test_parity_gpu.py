@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact values, positions,
+offsets and per-read status.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from bio_b200 import _cabi as cabi
+from bio_b200 import synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+OMODE = {cabi.MODE_KMER: oracle.MODE_KMER, cabi.MODE_NTHASH: oracle.MODE_NTHASH,
+         cabi.MODE_MINIMIZER: oracle.MODE_MINIMIZER, cabi.MODE_SYNCMER: oracle.MODE_SYNCMER,
+         cabi.MODE_PROTEIN: oracle.MODE_PROTEIN}
+
+
+def assert_same(res, ref, label=""):
+    assert np.array_equal(res["status"], ref["status"]), label + " status"
+    assert np.array_equal(res["off"], ref["off"]), label + " offsets"
+    assert res["total"] == len(ref["val"]), label + " count"
+    assert np.array_equal(res["val"], ref["val"]), label + " values"
+    if res["pos"] is not None and ref["pos"] is not None:
+        assert np.array_equal(res["pos"], ref["pos"]), label + " positions"
+
+
+def run_both(ctx, mode, bases, off, hint=0, **kw):
+    p = cabi.make_params(mode, max_read_len=hint, **kw)
+    res = ctx.run(p, bases, off)
+    ref = oracle.run_batch(bases, off, OMODE[mode], threads=8, **kw)
+    return res, ref
+
+
+def test_reference_golden_minimizer_on_gpu(gpu_ctx, golden):
+    # sketches/sketch_test.go:67-72 through the CUDA path
+    g = golden["sketch"]["minimizer"]
+    s = np.frombuffer(g["seq"].encode(), dtype=np.uint8)
+    off = np.array([0, len(s)], dtype=np.uint64)
+    res = gpu_ctx.run(cabi.make_params(cabi.MODE_MINIMIZER, g["k"], w=g["w"]), s, off)
+    assert [int(v) for v in res["val"]] == g["values"]
+    assert list(res["pos"]) == [0, 1, 4, 7, 8]
+
+
+def test_reference_syncmer_input_on_gpu(gpu_ctx, golden):
+    g = golden["sketch"]["syncmer"]
+    s = np.frombuffer(g["seq"].encode(), dtype=np.uint8)
+    off = np.array([0, len(s)], dtype=np.uint64)
+    res = gpu_ctx.run(cabi.make_params(cabi.MODE_SYNCMER, g["k"], s=g["s"]), s, off)
+    assert list(res["pos"]) == [0, 3, 5, 8, 11]
+    assert int(res["val"][-1]) == 1955511966892880774
+
+
+FIXTURE_CASES = {
+    "nthash_k21": (cabi.MODE_NTHASH, dict(k=21)),
+    "nthash_k21_fwd": (cabi.MODE_NTHASH, dict(k=21, canonical=False)),
+    "minimizer_k21_w11": (cabi.MODE_MINIMIZER, dict(k=21, w=11)),
+    "minimizer_k5_w3": (cabi.MODE_MINIMIZER, dict(k=5, w=3)),
+    "syncmer_k21_s11": (cabi.MODE_SYNCMER, dict(k=21, s=11)),
+    "kmer_k21": (cabi.MODE_KMER, dict(k=21)),
+    "kmer_k5_both": (cabi.MODE_KMER, dict(k=5, canonical=False)),
+    "protein_k11_f1": (cabi.MODE_PROTEIN, dict(k=11, frame=1)),
+    "protein_k11_fm2": (cabi.MODE_PROTEIN, dict(k=11, frame=-2)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURE_CASES))
+def test_committed_fixture(gpu_ctx, name):
+    z = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+    mode, kw = FIXTURE_CASES[name]
+    res = gpu_ctx.run(cabi.make_params(mode, **kw), z["bases"], z["off"])
+    ref = dict(val=z[name + "/val"], pos=z[name + "/pos"], off=z[name + "/off"], status=z[name + "/status"])
+    assert_same(res, ref, name)
+
+
+@pytest.mark.parametrize("mode,kw", [
+    (cabi.MODE_NTHASH, dict(k=21)),
+    (cabi.MODE_NTHASH, dict(k=31, canonical=False)),
+    (cabi.MODE_MINIMIZER, dict(k=21, w=11)),
+    (cabi.MODE_MINIMIZER, dict(k=31, w=15)),
+    (cabi.MODE_MINIMIZER, dict(k=21, w=1)),
+    (cabi.MODE_SYNCMER, dict(k=21, s=11)),
+    (cabi.MODE_SYNCMER, dict(k=31, s=16)),
+    (cabi.MODE_SYNCMER, dict(k=21, s=21)),
+    (cabi.MODE_SYNCMER, dict(k=21, s=20)),
+    (cabi.MODE_KMER, dict(k=21)),
+    (cabi.MODE_KMER, dict(k=31, canonical=False)),
+    (cabi.MODE_PROTEIN, dict(k=11, frame=1)),
+    (cabi.MODE_PROTEIN, dict(k=11, frame=-3)),
+])
+def test_150bp_reads(gpu_ctx, mode, kw):
+    b, o = synth.uniform_reads(30000, 150, 42)
+    res, ref = run_both(gpu_ctx, mode, b, o, hint=150, **kw)
+    assert_same(res, ref)
+    res, ref = run_both(gpu_ctx, mode, b, o, hint=0, **kw)  # library measures the longest read itself
+    assert_same(res, ref)
+
+
+@pytest.mark.parametrize("mode,kw", [
+    (cabi.MODE_NTHASH, dict(k=21)),
+    (cabi.MODE_MINIMIZER, dict(k=21, w=11)),
+    (cabi.MODE_SYNCMER, dict(k=21, s=11)),
+    (cabi.MODE_KMER, dict(k=21)),
+    (cabi.MODE_KMER, dict(k=15, canonical=False)),
+    (cabi.MODE_PROTEIN, dict(k=11, frame=2)),
+    (cabi.MODE_PROTEIN, dict(k=11, frame=-1)),
+])
+def test_ont_like_long_reads(gpu_ctx, mode, kw):
+    L = synth.ont_like_lengths(400, 44)
+    b, o = synth.ragged_reads(L, 44)
+    res, ref = run_both(gpu_ctx, mode, b, o, **kw)
+    assert_same(res, ref)
+    res, ref = run_both(gpu_ctx, mode, b, o, hint=int(L.max()), **kw)
+    assert_same(res, ref)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_parameters_ragged_inputs(gpu_ctx, seed):
+    """Random k/w/s over ragged batches that include empty and too-short reads, lowercase, N, IUPAC
+    codes and arbitrary bytes (ntHash treats the forward strand by full byte and the reverse strand
+    by byte & 7 -- SURVEY.md 8c)."""
+    rng = np.random.default_rng(1000 + seed)
+    alphabets = [b"ACGT", b"ACGTN", b"ACGTacgtNn", b"ACGTRYKMSWBDHVN", bytes(range(256)), b"AC", b"A"]
+    lens = rng.integers(0, 700, size=300)
+    lens[rng.integers(0, 300, size=40)] = 0
+    b, o = synth.ragged_reads(lens, seed, alphabet=alphabets[seed % len(alphabets)])
+    k = int(rng.integers(1, 40))
+    w = int(rng.integers(1, 36))
+    s = int(rng.integers(1, k + 1))
+    for mode, kw in ((cabi.MODE_NTHASH, dict(k=k, canonical=bool(seed & 1))),
+                     (cabi.MODE_MINIMIZER, dict(k=k, w=w)),
+                     (cabi.MODE_SYNCMER, dict(k=k, s=s))):
+        res, ref = run_both(gpu_ctx, mode, b, o, **kw)
+        assert_same(res, ref, f"mode={mode} {kw}")
+
+
+@pytest.mark.parametrize("mode,kw", [
+    (cabi.MODE_NTHASH, dict(k=21)),
+    (cabi.MODE_MINIMIZER, dict(k=21, w=11)),
+    (cabi.MODE_SYNCMER, dict(k=21, s=11)),
+    (cabi.MODE_KMER, dict(k=21)),
+])
+def test_circular(gpu_ctx, mode, kw):
+    lens = [150] * 200 + [0, 10, 20, 21, 30, 31, 40, 41, 3000]
+    b, o = synth.ragged_reads(lens, 3)
+    res, ref = run_both(gpu_ctx, mode, b, o, circular=True, **kw)
+    assert_same(res, ref)
+
+
+def test_low_complexity_reads_overflow_staging(gpu_ctx):
+    """poly-A / dinucleotide reads: every window has a new leftmost minimum, so items emit far more
+    than the staged-list capacity and take the direct-write path."""
+    b, o = synth.ragged_reads([150] * 700 + [5000] * 10, 9, alphabet=b"A")
+    res, ref = run_both(gpu_ctx, cabi.MODE_MINIMIZER, b, o, k=21, w=11)
+    assert_same(res, ref)
+    assert ref["ties"] > 0
+    b, o = synth.ragged_reads([5000] * 40, 9, alphabet=b"AC")
+    res, ref = run_both(gpu_ctx, cabi.MODE_SYNCMER, b, o, k=21, s=11)
+    assert_same(res, ref)
+
+
+def test_empty_and_tiny_batches(gpu_ctx):
+    p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11)
+    res = gpu_ctx.run(p, np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert res["total"] == 0 and len(res["off"]) == 1
+    b, o = synth.ragged_reads([0, 0, 0], 1)
+    res = gpu_ctx.run(p, b, o)
+    assert res["total"] == 0 and list(res["status"]) == [cabi.ERR_SHORT_SEQ] * 3
+    b, o = synth.ragged_reads([31], 1)
+    res, ref = run_both(gpu_ctx, cabi.MODE_MINIMIZER, b, o, k=21, w=11)
+    assert_same(res, ref)
+    assert res["total"] == 1
+
+
+def test_kmer_illegal_base(gpu_ctx):
+    """NextKmer stops at the first k-mer holding an illegal base (iterator.go:730-748): the codes before
+    it are emitted, the read's status is ErrIllegalBase."""
+    b, o = synth.ragged_reads([150] * 64 + [3000] * 4, 5)
+    b = b.copy()
+    for r, p in ((3, 0), (7, 100), (10, 149), (20, 20), (21, 21), (64, 1500), (65, 2999), (66, 5)):
+        b[int(o[r]) + p] = ord("-")
+    for canonical in (True, False):
+        res, ref = run_both(gpu_ctx, cabi.MODE_KMER, b, o, k=21, canonical=canonical)
+        assert_same(res, ref)
+        assert (res["status"] == cabi.ERR_ILLEGAL_BASE).sum() == 8
+
+
+def test_device_capacity_and_hint_errors(gpu_ctx):
+    import torch
+    dev = torch.device("cuda:0")
+    b, o = synth.uniform_reads(5000, 150, 8)
+    db = torch.zeros(len(b) + 64, dtype=torch.uint8, device=dev)
+    db[:len(b)] = torch.from_numpy(b)
+    do = torch.from_numpy(o.astype(np.int64)).to(dev)
+    ooff = torch.empty(len(o), dtype=torch.int64, device=dev)
+    st = torch.empty(len(o) - 1, dtype=torch.int32, device=dev)
+    p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150)
+    small = torch.empty(1000, dtype=torch.int64, device=dev)
+    rc, need = gpu_ctx.run_device(p, db, do, len(b), small, None, ooff, st)
+    assert rc == cabi.ERR_CAPACITY and need > 1000
+    val = torch.empty(need, dtype=torch.int64, device=dev)
+    pos = torch.empty(need, dtype=torch.int32, device=dev)
+    rc, total = gpu_ctx.run_device(p, db, do, len(b), val, pos, ooff, st)
+    assert rc == 0 and total == need
+    ref = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=21, w=11, threads=4)
+    assert np.array_equal(val.cpu().numpy().view(np.uint64), ref["val"])
+    assert np.array_equal(pos.cpu().numpy().view(np.uint32), ref["pos"])
+    bad = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=100)  # hint below the real length
+    with pytest.raises(cabi.SketchError) as e:
+        gpu_ctx.run_device(bad, db, do, len(b), val, pos, ooff, st)
+    assert e.value.code == cabi.ERR_BAD_ARG
+
+
+def test_c2_c3_scale_properties(gpu_ctx):
+    """2M x 150 bp on the device (C2/C3 geometry): size-independent properties + a sampled oracle check."""
+    import torch
+    dev = torch.device("cuda:0")
+    n, L, k, w = 2_000_000, 150, 21, 11
+    db, do = synth.device_uniform_reads(n, L, 43, dev)
+    nb = n * L
+    ooff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    # dense: exactly L-k+1 hashes per read
+    ph = cabi.make_params(cabi.MODE_NTHASH, k, max_read_len=L, want_pos=False)
+    hv = torch.empty(n * (L - k + 1), dtype=torch.int64, device=dev)
+    rc, total = gpu_ctx.run_device(ph, db, do, nb, hv, None, ooff, st)
+    assert rc == 0 and total == n * (L - k + 1)
+    assert torch.equal(ooff, torch.arange(n + 1, device=dev, dtype=torch.int64) * (L - k + 1))
+    # minimizers: values are the hashes at their positions; positions strictly increase inside a read
+    # and consecutive ones are at most w apart; deterministic across runs
+    pm = cabi.make_params(cabi.MODE_MINIMIZER, k, w=w, max_read_len=L)
+    cap = int(cabi.lib().b200sk_output_bound(__import__("ctypes").byref(pm), nb, n, 0))
+    mv = torch.empty(cap, dtype=torch.int64, device=dev)
+    mp = torch.empty(cap, dtype=torch.int32, device=dev)
+    moff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    rc, mt = gpu_ctx.run_device(pm, db, do, nb, mv, mp, moff, st)
+    assert rc == 0 and int(st.abs().sum()) == 0
+    mv, mp = mv[:mt], mp[:mt].long()
+    read_of = torch.repeat_interleave(torch.arange(n, device=dev), moff[1:] - moff[:-1])
+    assert torch.equal(hv[read_of * (L - k + 1) + mp], mv)
+    same = read_of[1:] == read_of[:-1]
+    dpos = mp[1:] - mp[:-1]
+    assert bool((dpos[same] > 0).all()) and bool((dpos[same] <= w).all())
+    first = moff[:-1]
+    assert bool((mp[first] < w).all())  # the first window's minimum lies in the first w k-mers
+    chk1 = int(mv.sum().item())
+    mv2 = torch.empty(cap, dtype=torch.int64, device=dev)
+    rc, mt2 = gpu_ctx.run_device(pm, db, do, nb, mv2, None, moff, st)
+    assert mt2 == mt and int(mv2[:mt].sum().item()) == chk1
+    # sampled oracle check: 20k reads taken out of the big batch
+    idx = np.sort(np.random.default_rng(0).choice(n, 20000, replace=False))
+    hb = db[:nb].view(n, L)[torch.from_numpy(idx).to(dev)].cpu().numpy().reshape(-1)
+    ho = np.arange(len(idx) + 1, dtype=np.uint64) * np.uint64(L)
+    ref = oracle.run_batch(hb, ho, oracle.MODE_MINIMIZER, k=k, w=w, threads=8)
+    o_np = moff.cpu().numpy()
+    mv_np = mv.cpu().numpy().view(np.uint64)
+    got = np.concatenate([mv_np[o_np[i]:o_np[i + 1]] for i in idx])
+    assert np.array_equal(got, ref["val"])
