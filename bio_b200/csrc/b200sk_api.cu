@@ -19,6 +19,8 @@ cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *ti
                               unsigned long long *ticket, cudaStream_t st);
 cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st);
 int main_kernel_occupancy(const KArgs &a, int threads);
+cudaError_t launch_minimizer_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
+bool minimizer_reg_supported(int w);
 cudaError_t launch_circularize(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, int k,
                                uint8_t *bases2, uint64_t *off2, uint64_t *tile_state,
                                unsigned long long *ticket, cudaStream_t st);
@@ -74,6 +76,8 @@ struct HostBuf { // pinned
 struct Plan {
     int T = 128;
     bool chunked = false;
+    bool reg = false; // window state in registers (b200sk_sparse_reg.cu)
+    int ctas_per_sm = 1;
     uint32_t C = 0, span_max = 0, lcap = 0;
     uint32_t sm_tile = 0, sm_tile_bytes = 0, sm_ring = 0, sm_ring_bytes = 0, sm_listv = 0, sm_listp = 0,
              sm_total = 0;
@@ -151,9 +155,38 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     const bool sparse = mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER;
     pl.lcap = 0;
     if (sparse) {
-        double e = pl.C * density * 1.5 + 8.0;
+        // staged-list capacity: the first window always emits, later ones at the density; +45% (about four
+        // standard deviations on random reads) keeps the overflow path to ~1e-4 of the items
+        double e = (1.0 + (pl.C - 1) * density) * 1.45 + 2.0;
         pl.lcap = (uint32_t)std::min<double>(pl.C, e);
         if (pl.lcap < 1) pl.lcap = 1;
+    }
+    pl.reg = mode == B200SK_MODE_MINIMIZER && minimizer_reg_supported(w);
+    if (pl.reg) {
+        // tables 2 KB + control, tile, lists of (lcap+1) slots x (8 B value + 1 B position delta)
+        int best_warps = -1;
+        Plan best = pl;
+        for (int T : {128, 96, 64}) {
+            Plan c = pl;
+            c.T = T;
+            c.sm_tile = 2048 + 256;
+            c.sm_tile_bytes = up16((uint32_t)T * c.span_max + 32);
+            c.sm_ring = c.sm_tile + c.sm_tile_bytes;
+            c.sm_ring_bytes = 0;
+            c.sm_listv = c.sm_ring;
+            c.sm_listp = c.sm_listv + up16((c.lcap + 1) * T * 8);
+            c.sm_total = c.sm_listp + up16((c.lcap + 1) * T);
+            if (c.sm_total > kSmemLimit) continue;
+            int ctas = (int)(233472u / (c.sm_total + 1024u));
+            ctas = std::min(ctas, 65536 / (T * 128)); // registers: <= 128 per thread
+            ctas = std::min(ctas, 32);
+            if (ctas < 1) continue;
+            c.ctas_per_sm = ctas;
+            const int warps = ctas * T / 32;
+            if (warps > best_warps) { best_warps = warps; best = c; }
+        }
+        if (best_warps > 0) { pl = best; return 0; }
+        pl.reg = false;
     }
     for (int T : {128, 64, 32}) {
         pl.T = T;
@@ -200,6 +233,9 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     // syncmer with s == k degenerates to "every k-mer" (sketch.go:160,328-331)
     if (q.mode == B200SK_MODE_SYNCMER && q.s == q.k) { q.mode = B200SK_MODE_NTHASH; q.canonical = 1; }
     if (q.mode == B200SK_MODE_MINIMIZER || q.mode == B200SK_MODE_SYNCMER) q.canonical = 1;
+    // minimizer with w == 1 is "every k-mer" as well (sketch.go:103,218-222)
+    const bool min_w1 = q.mode == B200SK_MODE_MINIMIZER && q.w == 1;
+    if (min_w1) q.mode = B200SK_MODE_NTHASH;
 
     KArgs a;
     memset(&a, 0, sizeof(a));
@@ -278,7 +314,9 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     a.tile_state = (uint64_t *)ctx->tile_state.p;
     a.ticket = meta + 0;
     a.flags = d_flags ? d_flags : (uint32_t *)(meta + 1);
-    const int occ = main_kernel_occupancy(a, pl.T);
+    int occ = 1;
+    if (pl.reg) CK(launch_minimizer_reg(a, pl.T, 0, st, &occ));
+    else occ = main_kernel_occupancy(a, pl.T);
     uint64_t blocks = (uint64_t)occ * ctx->sm_count;
     if (blocks > n_tiles) blocks = n_tiles;
     if (blocks < 1) blocks = 1;
@@ -288,7 +326,8 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(cudaEventCreate(&ev1));
         CK(cudaEventRecord(ev0, st));
     }
-    CK(launch_main(a, pl.T, (int)blocks, st));
+    if (pl.reg) CK(launch_minimizer_reg(a, pl.T, (int)blocks, st, nullptr));
+    else CK(launch_main(a, pl.T, (int)blocks, st));
     ctx->launches++;
     if (ctx->timing) {
         CK(cudaEventRecord(ev1, st));
