@@ -21,6 +21,11 @@ cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st
 int main_kernel_occupancy(const KArgs &a, int threads);
 cudaError_t launch_minimizer_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
 bool minimizer_reg_supported(int w);
+cudaError_t launch_scan_counts(const KArgs &a, uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st);
+cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *ill,
+                                 cudaStream_t st);
+cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
+bool build_codon_aux(int id, uint8_t *aux);
 cudaError_t launch_circularize(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, int k,
                                uint8_t *bases2, uint64_t *off2, uint64_t *tile_state,
                                unsigned long long *ticket, cudaStream_t st);
@@ -76,7 +81,8 @@ struct HostBuf { // pinned
 struct Plan {
     int T = 128;
     bool chunked = false;
-    bool reg = false; // window state in registers (b200sk_sparse_reg.cu)
+    bool reg = false;   // window state in registers (b200sk_sparse_reg.cu)
+    bool dense = false; // b200sk_dense.cu
     int ctas_per_sm = 1;
     uint32_t C = 0, span_max = 0, lcap = 0;
     uint32_t sm_tile = 0, sm_tile_bytes = 0, sm_ring = 0, sm_ring_bytes = 0, sm_listv = 0, sm_listp = 0,
@@ -102,6 +108,9 @@ struct b200sk_ctx {
     DevBuf scan_state; // item scan look-back words
     DevBuf item_first;
     DevBuf circ_bases, circ_off;
+    DevBuf ill, aux;
+    int aux_table = -1;
+    std::vector<uint8_t> aux_host;
     // host path device buffers
     DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;
     HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
@@ -136,6 +145,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     switch (mode) {
     case B200SK_MODE_MINIMIZER: halo = (uint64_t)w + k - 1; density = 2.0 / (w + 1.0); break;
     case B200SK_MODE_SYNCMER: halo = 2ull * d + s - 1; density = 2.0 / (d + 1.0); break;
+    case B200SK_MODE_PROTEIN: halo = (uint64_t)k - 1; density = 1.0; break;
     default: halo = (uint64_t)k - 1; density = 1.0; break;
     }
     const uint64_t ext = p.circular ? (uint64_t)(k - 1) : 0;
@@ -143,17 +153,45 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     pl.chunked = !(max_len && max_len <= kSingleMaxLen);
     if (!pl.chunked) {
         int32_t st;
-        uint32_t np = read_positions(mode, max_len, max_len, k, w, s, &st);
+        ReadGeom g;
+        g.mode = mode; g.k = k; g.w = w; g.s = s; g.frame = 1; g.canonical = p.canonical;
+        g.protein_input = p.alphabet == B200SK_ALPHABET_PROTEIN; g.ill = nullptr;
+        uint32_t np = read_positions(g, 0, max_len, max_len, &st);
         pl.C = np ? np : 1;
         pl.span_max = (uint32_t)max_len;
     } else {
         pl.C = kChunk;
-        if ((uint64_t)pl.C + halo > 60000) return B200SK_ERR_UNSUPPORTED;
+        if ((uint64_t)pl.C + halo > 20000) return B200SK_ERR_UNSUPPORTED;
         pl.span_max = (uint32_t)(pl.C + halo);
+        if (mode == B200SK_MODE_PROTEIN && p.alphabet != B200SK_ALPHABET_PROTEIN) pl.span_max *= 3; // codons
     }
     if (pl.span_max < 16) pl.span_max = 16;
     const bool sparse = mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER;
     pl.lcap = 0;
+    pl.dense = !sparse;
+    if (pl.dense) {
+        // tables 8 KB + control, per-warp output staging (two areas for both-strand k-mers), tile,
+        // per-thread amino-acid buffers (protein)
+        const uint32_t stage_w = (mode == B200SK_MODE_KMER ? 2u : 1u) * 32u * (16u * 8u + 8u);
+        uint32_t aa_stride = 0;
+        if (mode == B200SK_MODE_PROTEIN) {
+            aa_stride = ((pl.C + (uint32_t)k - 1 + 3) / 4) | 1u; // odd number of words: conflict-free columns
+            aa_stride *= 4;
+        }
+        pl.lcap = aa_stride;
+        for (int T : {128, 64, 32}) {
+            pl.T = T;
+            pl.sm_ring = 8192 + 256;
+            pl.sm_ring_bytes = (uint32_t)(T / 32) * stage_w;
+            pl.sm_tile = pl.sm_ring + pl.sm_ring_bytes;
+            pl.sm_tile_bytes = up16((uint32_t)T * pl.span_max + 32);
+            pl.sm_listv = pl.sm_tile + pl.sm_tile_bytes;
+            pl.sm_listp = pl.sm_listv + up16((uint32_t)T * aa_stride);
+            pl.sm_total = pl.sm_listp;
+            if (pl.sm_total <= 112 * 1024) return 0;
+        }
+        return pl.sm_total <= kSmemLimit ? 0 : B200SK_ERR_UNSUPPORTED;
+    }
     if (sparse) {
         // staged-list capacity: the first window always emits, later ones at the density; +45% (about four
         // standard deviations on random reads) keeps the overflow path to ~1e-4 of the items
@@ -219,7 +257,6 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     if (rc) return rc;
     if (!d_off || !d_ooff || (n_bases && !d_bases)) return B200SK_ERR_BAD_ARG;
     if (((uintptr_t)d_bases & 15u) != 0) return B200SK_ERR_BAD_ARG;
-    if (p.mode == B200SK_MODE_KMER || p.mode == B200SK_MODE_PROTEIN) return B200SK_ERR_UNSUPPORTED;
     if ((rc = ensure_meta(ctx))) return rc;
     unsigned long long *meta = (unsigned long long *)ctx->meta.p;
     CK(cudaMemsetAsync(meta, 0, 64, st));
@@ -230,17 +267,40 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         return 0;
     }
     b200sk_params q = p;
-    // syncmer with s == k degenerates to "every k-mer" (sketch.go:160,328-331)
+    // "every k-mer" degenerations: syncmer with s == k (sketch.go:160,328-331), minimizer with w == 1
+    // (sketch.go:103,218-222) -- both are the canonical hash stream with Index() = k-mer position
     if (q.mode == B200SK_MODE_SYNCMER && q.s == q.k) { q.mode = B200SK_MODE_NTHASH; q.canonical = 1; }
+    if (q.mode == B200SK_MODE_MINIMIZER && q.w == 1) { q.mode = B200SK_MODE_NTHASH; q.canonical = 1; }
     if (q.mode == B200SK_MODE_MINIMIZER || q.mode == B200SK_MODE_SYNCMER) q.canonical = 1;
-    // minimizer with w == 1 is "every k-mer" as well (sketch.go:103,218-222)
-    const bool min_w1 = q.mode == B200SK_MODE_MINIMIZER && q.w == 1;
-    if (min_w1) q.mode = B200SK_MODE_NTHASH;
+    if (q.mode == B200SK_MODE_PROTEIN) q.circular = 0; // the reference's protein iterator has no circular option
 
     KArgs a;
     memset(&a, 0, sizeof(a));
     a.bases = d_bases; a.off = d_off; a.off_orig = nullptr; a.n_reads = n_reads;
     a.mode = q.mode; a.k = q.k; a.w = q.w; a.s = q.s; a.canonical = q.canonical; a.frame = q.frame;
+    a.alphabet = q.alphabet;
+
+    if (q.mode == B200SK_MODE_KMER) {
+        // NextKmer stops at the first illegal base (iterator.go:730-748): find it once per read
+        CK(ctx->ill.reserve(n_reads * 4));
+        CK(launch_first_illegal(d_bases, d_off, n_reads, (uint32_t *)ctx->ill.p, st));
+        ctx->launches++;
+        a.ill = (const uint32_t *)ctx->ill.p;
+    }
+    if (q.mode == B200SK_MODE_PROTEIN && q.alphabet != B200SK_ALPHABET_PROTEIN) {
+        if (ctx->aux_table != q.codon_table) {
+            ctx->aux_host.resize(4608);
+            if (!build_codon_aux(q.codon_table, ctx->aux_host.data())) return B200SK_ERR_CODON_TABLE;
+            CK(ctx->aux.reserve(4608));
+            CK(cudaMemcpyAsync(ctx->aux.p, ctx->aux_host.data(), 4608, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st)); // aux_host may be rebuilt by a later call
+            ctx->aux_table = q.codon_table;
+        }
+        a.aux = (const uint8_t *)ctx->aux.p;
+    } else if (q.mode == B200SK_MODE_PROTEIN) {
+        CK(ctx->aux.reserve(4608));
+        a.aux = (const uint8_t *)ctx->aux.p; // unused for amino-acid input, but the kernel copies the area
+    }
 
     if (q.circular) {
         // seq2 = S + S[0:k-1] (iterator.go:642-646, sketch.go:106-110): materialise the extended
@@ -287,12 +347,27 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     a.sm_tile = pl.sm_tile; a.sm_tile_bytes = pl.sm_tile_bytes; a.sm_ring = pl.sm_ring;
     a.sm_ring_bytes = pl.sm_ring_bytes; a.sm_listv = pl.sm_listv; a.sm_listp = pl.sm_listp;
     a.sm_total = pl.sm_total;
+    a.out_val = d_val; a.out_pos = p.want_pos ? d_pos : nullptr; a.out_off = d_ooff; a.status = d_status;
+    a.capacity = d_val ? capacity : 0; a.out_base = out_base;
+    a.flags = d_flags ? d_flags : (uint32_t *)(meta + 1);
 
+    const size_t sbytes = ((n_reads + 1023) / 1024 + 1) * 8;
+    if (pl.dense) {
+        // dense modes: output offsets and statuses follow from the lengths
+        CK(ctx->scan_state.reserve(sbytes));
+        CK(cudaMemsetAsync(ctx->scan_state.p, 0, sbytes, st));
+        CK(cudaMemsetAsync(meta + 4, 0, 8, st));
+        CK(launch_scan_counts(a, (uint64_t *)ctx->scan_state.p, meta + 4, st));
+        ctx->launches++;
+    }
     uint64_t items_bound = n_items_host;
     if (pl.chunked) {
-        if (!have_items_host) items_bound = n_reads + n_bases / pl.C + 1;
+        if (!have_items_host) {
+            uint64_t unit = pl.C;
+            if (q.mode == B200SK_MODE_PROTEIN && q.alphabet != B200SK_ALPHABET_PROTEIN) unit *= 3;
+            items_bound = n_reads + n_bases / unit + 1;
+        }
         CK(ctx->item_first.reserve((n_reads + 1) * 8));
-        const size_t sbytes = ((n_reads + 1023) / 1024 + 1) * 8;
         CK(ctx->scan_state.reserve(sbytes));
         CK(cudaMemsetAsync(ctx->scan_state.p, 0, sbytes, st));
         CK(cudaMemsetAsync(meta + 4, 0, 8, st));
@@ -307,15 +382,15 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         a.n_items = n_reads;
     }
     const uint64_t n_tiles = (items_bound + pl.T - 1) / pl.T + 1;
-    CK(ctx->tile_state.reserve(n_tiles * 8));
-    CK(cudaMemsetAsync(ctx->tile_state.p, 0, n_tiles * 8, st));
-    a.out_val = d_val; a.out_pos = p.want_pos ? d_pos : nullptr; a.out_off = d_ooff; a.status = d_status;
-    a.capacity = d_val ? capacity : 0; a.out_base = out_base;
+    if (!pl.dense) {
+        CK(ctx->tile_state.reserve(n_tiles * 8));
+        CK(cudaMemsetAsync(ctx->tile_state.p, 0, n_tiles * 8, st));
+    }
     a.tile_state = (uint64_t *)ctx->tile_state.p;
     a.ticket = meta + 0;
-    a.flags = d_flags ? d_flags : (uint32_t *)(meta + 1);
     int occ = 1;
-    if (pl.reg) CK(launch_minimizer_reg(a, pl.T, 0, st, &occ));
+    if (pl.dense) CK(launch_dense(a, pl.T, 0, st, &occ));
+    else if (pl.reg) CK(launch_minimizer_reg(a, pl.T, 0, st, &occ));
     else occ = main_kernel_occupancy(a, pl.T);
     uint64_t blocks = (uint64_t)occ * ctx->sm_count;
     if (blocks > n_tiles) blocks = n_tiles;
@@ -326,7 +401,8 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(cudaEventCreate(&ev1));
         CK(cudaEventRecord(ev0, st));
     }
-    if (pl.reg) CK(launch_minimizer_reg(a, pl.T, (int)blocks, st, nullptr));
+    if (pl.dense) CK(launch_dense(a, pl.T, (int)blocks, st, nullptr));
+    else if (pl.reg) CK(launch_minimizer_reg(a, pl.T, (int)blocks, st, nullptr));
     else CK(launch_main(a, pl.T, (int)blocks, st));
     ctx->launches++;
     if (ctx->timing) {
@@ -361,10 +437,15 @@ int b200sk_check_params(const b200sk_params *p) {
         if (p->k < 1) return B200SK_ERR_INVALID_K;       // sketch.go:143
         if (p->s > p->k || p->s <= 0) return B200SK_ERR_INVALID_S; // sketch.go:146 (s<0: uint(s) overflows NewHasher)
         return 0;
-    case B200SK_MODE_PROTEIN:
+    case B200SK_MODE_PROTEIN: {
         if (p->k < 1) return B200SK_ERR_INVALID_K;       // iterator-protein.go:47
-        if (p->frame < -3 || p->frame > 3 || p->frame == 0) return B200SK_ERR_INVALID_FRAME; // codon_tables.go:209
+        if (p->alphabet == B200SK_ALPHABET_PROTEIN) return 0; // already amino acids (iterator-protein.go:68)
+        if (p->alphabet == B200SK_ALPHABET_UNLIMIT) return B200SK_ERR_BAD_ARG; // seq.go:686: only DNA/RNA translate
+        uint8_t tmp[4608];
+        if (!build_codon_aux(p->codon_table, tmp)) return B200SK_ERR_CODON_TABLE;      // seq.go:691
+        if (p->frame < -3 || p->frame > 3 || p->frame == 0) return B200SK_ERR_INVALID_FRAME; // seq.go:694
         return 0;
+    }
     default:
         return B200SK_ERR_BAD_ARG;
     }
@@ -421,7 +502,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->circ_bases,
-                      &ctx->circ_off, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
+                      &ctx->circ_off, &ctx->ill, &ctx->aux, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
                       &ctx->d_status})
         b->release();
     for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();

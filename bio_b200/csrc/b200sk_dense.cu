@@ -1,0 +1,491 @@
+// Dense modes: every position of a read emits exactly one element, so the output offsets follow from
+// the read lengths alone (k_scan_reads<true> writes out_off[] and read_status[] before this kernel runs).
+//
+//   MODE_NTHASH   NextHash        sketches/iterator.go:658-665   (also minimizer w==1 / syncmer s==k)
+//   MODE_KMER     NextKmer        sketches/iterator.go:708-759   2-bit codes, canonical or both strands
+//   MODE_PROTEIN  ProteinIterator sketches/iterator-protein.go:46-90  translate one frame + wyhash(seed 1)
+//
+// Same tiling as the sparse kernels (tile of blockDim.x items, one TMA bulk copy per tile, one thread walks
+// one item).  Each thread produces 8 bytes per step; a warp collects 16 steps per lane in shared memory and
+// then writes every lane's 128-byte run with coalesced stores.
+#include "../../include/b200sk_codon_data.h"
+#include "b200sk_tile.cuh"
+
+namespace b200sk {
+
+#define DENSE_S 16                          /* steps staged per lane between flushes */
+#define DENSE_ROW (DENSE_S * 8 + 8)         /* bytes per lane row (+8: rows land on different banks) */
+#define DENSE_WARP_STAGE (32 * DENSE_ROW)   /* one staging area per warp (two for both-strand k-mers) */
+
+// ------------------------------------------------------------------ 2-bit base code, pair letters
+// sketches/kmers.go:23-40 (IUPAC codes map to their first base; 4 = illegal)
+__device__ __host__ inline uint32_t base2bit_of(uint32_t b) {
+    switch (b) {
+    case 'A': case 'a': case 'D': case 'd': case 'H': case 'h': case 'M': case 'm':
+    case 'N': case 'n': case 'R': case 'r': case 'V': case 'v': case 'W': case 'w': return 0;
+    case 'B': case 'b': case 'C': case 'c': case 'S': case 's': case 'Y': case 'y': return 1;
+    case 'G': case 'g': case 'K': case 'k': return 2;
+    case 'T': case 't': case 'U': case 'u': return 3;
+    default: return 4;
+    }
+}
+// seq.Alphabet.PairLetter (seq/alphabet.go:313-325, letters/pairs :353-399); letters outside the
+// alphabet come back unchanged (seq/seq.go:389-391)
+__device__ __host__ inline uint32_t pair_letter(int alphabet, uint32_t b) {
+    const char *l, *p;
+    switch (alphabet) {
+    case B200SK_ALPHABET_DNA_REDUNDANT: l = "acgtryswkmbdhvACGTRYSWKMBDHV"; p = "tgcayrswmkvhdbTGCAYRSWMKVHDB"; break;
+    case B200SK_ALPHABET_DNA: l = "acgtACGT"; p = "tgcaTGCA"; break;
+    case B200SK_ALPHABET_RNA_REDUNDANT: l = "acguryswkmbdhvACGURYSWKMBDHV"; p = "ugcayrswmkvhdbUGCAYRSWMKVHDB"; break;
+    case B200SK_ALPHABET_RNA: l = "acguACGU"; p = "ugcaUGCA"; break;
+    default: return b;
+    }
+    for (int i = 0; l[i]; i++)
+        if ((uint32_t)(uint8_t)l[i] == b) return (uint32_t)(uint8_t)p[i];
+    return b;
+}
+
+// first illegal base of every read (0xffffffff: none) -- one warp per read
+__global__ void k_first_illegal(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
+                                uint64_t n_reads, uint32_t *ill) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_reads; r += nwarps) {
+        const uint64_t s0 = off[r], L = off[r + 1] - s0;
+        uint32_t best = 0xffffffffu;
+        for (uint64_t i0 = 0; i0 < L && best == 0xffffffffu; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            const bool bad = i < L && base2bit_of(bases[s0 + i]) == 4;
+            const unsigned m = __ballot_sync(0xffffffffu, bad);
+            if (m) best = (uint32_t)(i0 + (uint64_t)(__ffs(m) - 1));
+        }
+        if (lane == 0) ill[r] = best;
+    }
+}
+
+// ------------------------------------------------------------------ wyhash (zeebo/wyhash v0.0.1 Hash(b, seed))
+// Published wyhash v1 layout: 32-byte blocks, tail by len & 31, final mum(seed, len ^ p5).  The tail
+// reads 8 bytes as two 32-bit halves with the first half high.  Reference parity of this function is
+// unpinned (no reference test checks a protein hash value); it is bit-exact against oracle/.
+#define WYP0 0xa0761d6478bd642fULL
+#define WYP1 0xe7037ed1a0b428dbULL
+#define WYP2 0x8ebc6af09c88c6e3ULL
+#define WYP3 0x589965cc75374cc3ULL
+#define WYP4 0x1d8e4e27c47d124fULL
+#define WYP5 0xeb44accab455d165ULL
+__device__ __forceinline__ uint64_t wymum(uint64_t a, uint64_t b) { return __umul64hi(a, b) ^ (a * b); }
+
+struct ByteSrc { // little-endian reads of an unaligned byte string in shared memory
+    const uint8_t *p;
+    __device__ __forceinline__ uint64_t r8(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ uint64_t r16(uint32_t i) const { return r8(i) | (r8(i + 1) << 8); }
+    __device__ __forceinline__ uint64_t r32(uint32_t i) const { return r16(i) | (r16(i + 2) << 16); }
+    __device__ __forceinline__ uint64_t r64(uint32_t i) const { return r32(i) | (r32(i + 4) << 32); }
+    __device__ __forceinline__ uint64_t r64s(uint32_t i) const { return (r32(i) << 32) | r32(i + 4); }
+};
+
+__device__ __forceinline__ uint64_t wy_tail_word(const ByteSrc &s, uint32_t o, uint32_t n) { // n in 1..8
+    switch (n) {
+    case 1: return s.r8(o);
+    case 2: return s.r16(o);
+    case 3: return (s.r16(o) << 8) | s.r8(o + 2);
+    case 4: return s.r32(o);
+    case 5: return (s.r32(o) << 8) | s.r8(o + 4);
+    case 6: return (s.r32(o) << 16) | s.r16(o + 4);
+    case 7: return (s.r32(o) << 24) | (s.r16(o + 4) << 8) | s.r8(o + 6);
+    default: return s.r64s(o);
+    }
+}
+
+__device__ __forceinline__ uint64_t wyhash_dev(const ByteSrc &s, uint32_t len, uint64_t seed) {
+    uint32_t o = 0;
+    for (uint32_t i = 0; i + 32 <= len; i += 32, o += 32)
+        seed = wymum(seed ^ WYP0, wymum(s.r64(o) ^ WYP1, s.r64(o + 8) ^ WYP2) ^
+                                      wymum(s.r64(o + 16) ^ WYP3, s.r64(o + 24) ^ WYP4));
+    seed ^= WYP0;
+    const uint32_t t = len & 31u;
+    if (t == 0) {
+    } else if (t <= 8) {
+        seed = wymum(seed, wy_tail_word(s, o, t) ^ WYP1);
+    } else if (t <= 16) {
+        seed = wymum(s.r64s(o) ^ seed, wy_tail_word(s, o + 8, t - 8) ^ WYP2);
+    } else if (t <= 24) {
+        seed = wymum(s.r64s(o) ^ seed, s.r64s(o + 8) ^ WYP2) ^ wymum(seed, wy_tail_word(s, o + 16, t - 16) ^ WYP3);
+    } else {
+        seed = wymum(s.r64s(o) ^ seed, s.r64s(o + 8) ^ WYP2) ^
+               wymum(s.r64s(o + 16) ^ seed, wy_tail_word(s, o + 24, t - 24) ^ WYP4);
+    }
+    return wymum(seed, (uint64_t)len ^ WYP5);
+}
+
+// ------------------------------------------------------------------ codon lookup
+// aux layout: [0,4096) matrix[i][j][k] over 4-bit IUPAC codes, [4096,4352) base2code (0xff = invalid),
+// [4352,4608) DNA pair letters.  CodonTable.Get: seq/codon_tables.go:152-170 with allowUnknownCodon=true.
+__device__ __forceinline__ uint32_t codon_aa(const uint8_t *tab, uint32_t b0, uint32_t b1, uint32_t b2) {
+    const uint32_t c0 = tab[4096 + b0], c1 = tab[4096 + b1], c2 = tab[4096 + b2];
+    if ((c0 | c1 | c2) & 0x80u) return 'X'; // invalid base, unknown codons allowed
+    if (b0 == '-' && b1 == '-' && b2 == '-') return '-';
+    const uint32_t aa = tab[(c0 << 8) | (c1 << 4) | c2];
+    return aa ? aa : 'X';
+}
+
+// ------------------------------------------------------------------ staged, coalesced output
+// Each lane filled `n` (<= 16) entries of its row; entry e goes to out[b + d*e] (d = +1, or -1 for the
+// second strand of both-strand k-mers), position p0 + d*e.  Two lanes' rows leave per iteration.
+__device__ __forceinline__ void flush_rows(const uint8_t *stage, uint64_t *out_val, uint32_t *out_pos, uint64_t b,
+                                           uint32_t n, int d, uint32_t p0, unsigned lane) {
+    __syncwarp();
+#pragma unroll 4
+    for (int j = 0; j < 32; j += 2) {
+        const int src = j + (int)(lane >> 4);
+        const uint32_t e = lane & 15u;
+        const uint64_t bb = __shfl_sync(0xffffffffu, b, src);
+        const uint32_t nn = __shfl_sync(0xffffffffu, n, src);
+        const int dd = __shfl_sync(0xffffffffu, d, src);
+        const uint32_t pp = __shfl_sync(0xffffffffu, p0, src);
+        if (e < nn) {
+            const uint64_t v = *reinterpret_cast<const uint64_t *>(stage + src * DENSE_ROW + e * 8);
+            const uint64_t idx = bb + (uint64_t)((int64_t)dd * (int64_t)e);
+            out_val[idx] = v;
+            if (out_pos) out_pos[idx] = pp + (uint32_t)(dd * (int)e);
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ kernel
+struct DItem {
+    uint64_t r, gb0, obase; // obase: global element index of the item's first element
+    uint32_t nb, nstep, p0, np;
+    uint64_t L;
+    bool valid, both; // both: k-mer second strand is emitted too
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_dense(const KArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, wid = tid >> 5;
+    uint8_t *tab = smem; // 8 KB: ntHash tables by byte / k-mer LUT / codon tables
+    TileCtl *ctl = reinterpret_cast<TileCtl *>(smem + 8192);
+    uint8_t *tilebuf = smem + a.sm_tile;
+    uint8_t *stage = smem + a.sm_ring + wid * (MODE == B200SK_MODE_KMER ? 2 : 1) * DENSE_WARP_STAGE;
+    uint8_t *row = stage + lane * DENSE_ROW;
+    const int k = a.k;
+    if (MODE == B200SK_MODE_NTHASH) {
+        ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(tab), *tOut = tIn + 256;
+        for (uint32_t b = tid; b < 256; b += T) {
+            const uint64_t f = fwd_seed(b), r = rev_seed(b);
+            tIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(k - 1)));
+            tOut[b] = make_ulonglong2(rol64(f, (unsigned)k), ror64(r, 1));
+        }
+    } else if (MODE == B200SK_MODE_KMER) {
+        for (uint32_t b = tid; b < 256; b += T) {
+            const uint32_t bit = base2bit_of(b);
+            const uint32_t cb = base2bit_of(pair_letter(a.alphabet, b));
+            tab[b] = (uint8_t)((bit & 3u) | ((cb & 3u) << 2) | (bit == 4 ? 0x10u : 0u));
+        }
+    } else {
+        for (uint32_t i = tid; i < 4608; i += T) tab[i] = a.aux[i];
+    }
+    if (tid == 0) {
+        mbar_init(&ctl->mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
+    const uint64_t total = a.out_off[a.n_reads] - a.out_base;
+    const bool fits = total <= a.capacity;
+    if (!fits) {
+        if (blockIdx.x == 0 && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
+        return;
+    }
+    const ReadGeom g = a.geom();
+    uint32_t parity = 0;
+    for (;;) {
+        if (tid == 0) ctl->tile = atomicAdd(a.ticket, 1ULL);
+        __syncthreads();
+        const uint64_t tile = ctl->tile;
+        const uint64_t item0 = tile * T;
+        if (item0 >= n_items) break;
+        // ---- geometry
+        DItem it;
+        it.valid = item0 + tid < n_items;
+        it.r = 0; it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0; it.p0 = 0; it.np = 0; it.L = 0; it.both = false;
+        if (it.valid) {
+            const uint64_t item = item0 + tid;
+            uint64_t r = item;
+            uint32_t c = 0;
+            if (a.item_first) {
+                uint64_t lo = 0, hi = a.n_reads;
+                while (hi - lo > 1) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (a.item_first[mid] <= item) lo = mid; else hi = mid;
+                }
+                r = lo;
+                c = (uint32_t)(item - a.item_first[r]);
+            }
+            it.r = r;
+            const uint64_t o0 = a.off[r];
+            it.L = a.off[r + 1] - o0;
+            const uint64_t orig = a.off_orig ? a.off_orig[r + 1] - a.off_orig[r] : it.L;
+            int32_t st;
+            it.np = read_positions(g, r, it.L, orig, &st);
+            it.gb0 = o0;
+            if (it.np) {
+                // reverse frames read the sequence downwards: hand the chunks out last-first so that item
+                // order is still address order and a tile stays one compact byte range
+                if (MODE == B200SK_MODE_PROTEIN && a.frame < 0 && !g.protein_input) c = chunks_of(it.np, a.C) - 1 - c;
+                it.p0 = c * a.C;
+                it.nstep = min(it.np, it.p0 + a.C) - it.p0;
+                it.obase = a.out_off[r] - a.out_base + it.p0;
+                if (MODE == B200SK_MODE_PROTEIN) {
+                    const uint32_t naa = it.nstep + (uint32_t)k - 1; // amino acids the item reads
+                    if (g.protein_input) {
+                        it.gb0 = o0 + it.p0;
+                        it.nb = naa;
+                    } else if (a.frame > 0) {
+                        it.gb0 = o0 + (uint32_t)(a.frame - 1) + 3ull * it.p0;
+                        it.nb = 3 * naa;
+                    } else { // reverse frames walk down from base L-|f|
+                        const uint64_t top = it.L - (uint64_t)(-a.frame) - 3ull * it.p0; // first codon's base i
+                        it.nb = 3 * naa;
+                        it.gb0 = o0 + top + 1 - it.nb;
+                    }
+                } else {
+                    it.nb = it.nstep + (uint32_t)k - 1;
+                    it.gb0 = o0 + it.p0;
+                    it.both = MODE == B200SK_MODE_KMER && !a.canonical && st == B200SK_OK;
+                }
+            }
+        }
+        // tile byte range = [min gb0, max gb0+nb) over the items (reverse frames walk a read downwards, so
+        // item order is not address order here)
+        if (tid == 0) { ctl->lo = ~0ULL; ctl->hi = 0; }
+        __syncthreads();
+        {
+            unsigned long long lo = it.nb ? it.gb0 : ~0ULL, hi = it.nb ? it.gb0 + it.nb : 0ULL;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) {
+                atomicMin(reinterpret_cast<unsigned long long *>(&ctl->lo), lo);
+                atomicMax(reinterpret_cast<unsigned long long *>(&ctl->hi), hi);
+            }
+        }
+        __syncthreads();
+        const uint64_t lo_al = ctl->hi ? ctl->lo & ~15ULL : 0;
+        const uint64_t span = ctl->hi > lo_al ? ctl->hi - lo_al : 0;
+        const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
+        const bool span_ok = bytes <= a.sm_tile_bytes;
+        if (tid == 0 && bytes && span_ok) {
+            mbar_expect_tx(&ctl->mbar, bytes);
+            tma_load_1d(tilebuf, a.bases + lo_al, bytes, &ctl->mbar);
+        }
+        if (!span_ok && tid == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
+        if (bytes && span_ok) {
+            mbar_wait(&ctl->mbar, parity);
+            parity ^= 1u;
+        }
+        const uint32_t nstep = span_ok ? it.nstep : 0u;
+        const uint8_t *sb = tilebuf + (uint32_t)(it.gb0 - lo_al);
+        // warp-uniform trip count
+        uint32_t maxn = nstep;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+
+        if (MODE == B200SK_MODE_NTHASH) {
+            const ulonglong2 *tIn = reinterpret_cast<const ulonglong2 *>(tab), *tOut = tIn + 256;
+            const bool canonical = a.canonical != 0;
+            uint64_t fh = 0, rh = 0;
+            if (nstep)
+                for (int j = 0; j < k - 1; j++) {
+                    const ulonglong2 e = tIn[sb[j]];
+                    fh = rol1(fh) ^ e.x;
+                    rh = ror1(rh) ^ e.y;
+                }
+            for (uint32_t u0 = 0; u0 < maxn; u0 += DENSE_S) {
+#pragma unroll 4
+                for (uint32_t e = 0; e < DENSE_S; e++) {
+                    const uint32_t u = u0 + e;
+                    if (u < nstep) {
+                        const ulonglong2 in = tIn[sb[u + k - 1]];
+                        ulonglong2 o = make_ulonglong2(0, 0);
+                        if (u) o = tOut[sb[u - 1]];
+                        fh = rol1(fh) ^ o.x ^ in.x;
+                        rh = ror1(rh) ^ o.y ^ in.y;
+                        *reinterpret_cast<uint64_t *>(row + e * 8) = (canonical && rh < fh) ? rh : fh; // iterator.go:659
+                    }
+                }
+                const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
+                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, n, 1, it.p0 + u0, lane);
+            }
+        } else if (MODE == B200SK_MODE_KMER) {
+            // iterator.go:736,740,754: code = (pre & mask1) << 2 | bit; rc = (bit ^ 3) << 2(k-1) | preRC >> 2.
+            // Second strand (non-canonical, :713-723): the codes of RevComInplace(seq), i.e. for k-mer i the
+            // pair-letter reverse complement, emitted at index np-1-i after the np forward codes.
+            const int sh = 2 * (k - 1);
+            const uint64_t mask1 = (1ull << sh) - 1ull; // iterator.go:699 (sh <= 62)
+            uint64_t code = 0, rc3 = 0, rcq = 0;
+            const bool canonical = a.canonical != 0;
+            uint8_t *row2 = row + DENSE_WARP_STAGE;
+            if (nstep)
+                for (int j = 0; j < k - 1; j++) {
+                    const uint32_t v = tab[sb[j]];
+                    code = (code << 2) | (v & 3u);
+                    rc3 = (rc3 >> 2) | ((uint64_t)((v & 3u) ^ 3u) << sh);
+                    rcq = (rcq >> 2) | ((uint64_t)((v >> 2) & 3u) << sh);
+                }
+            for (uint32_t u0 = 0; u0 < maxn; u0 += DENSE_S) {
+#pragma unroll 4
+                for (uint32_t e = 0; e < DENSE_S; e++) {
+                    const uint32_t u = u0 + e;
+                    if (u < nstep) {
+                        const uint32_t v = tab[sb[u + k - 1]];
+                        code = ((code & mask1) << 2) | (v & 3u);
+                        rc3 = (rc3 >> 2) | ((uint64_t)((v & 3u) ^ 3u) << sh);
+                        rcq = (rcq >> 2) | ((uint64_t)((v >> 2) & 3u) << sh);
+                        *reinterpret_cast<uint64_t *>(row + e * 8) = (canonical && rc3 < code) ? rc3 : code;
+                        *reinterpret_cast<uint64_t *>(row2 + e * 8) = rcq;
+                    }
+                }
+                const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
+                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, n, 1, it.p0 + u0, lane);
+                // strand 2: k-mer i = p0+u0+e lands at out_off[r] + np + (np-1-i), position np-1-i
+                const uint32_t i0 = it.p0 + u0;
+                const uint64_t b2 = it.obase - it.p0 + 2ull * it.np - 1 - i0;
+                flush_rows(stage + DENSE_WARP_STAGE, a.out_val, a.out_pos, b2, it.both ? n : 0u, -1,
+                           it.np - 1 - i0, lane);
+            }
+        } else { // PROTEIN
+            uint8_t *aab = smem + a.sm_listv + tid * a.lcap; // lcap = per-thread amino-acid buffer stride
+            const uint32_t naa = nstep ? nstep + (uint32_t)k - 1 : 0u;
+            ByteSrc src;
+            if (g.protein_input) {
+                src.p = sb;
+            } else {
+                src.p = aab;
+                if (a.frame > 0) {
+                    for (uint32_t t = 0; t < naa; t++)
+                        aab[t] = (uint8_t)codon_aa(tab, sb[3 * t], sb[3 * t + 1], sb[3 * t + 2]);
+                } else {
+                    const uint8_t *pl = tab + 4352;
+                    const uint32_t top = it.nb - 1; // the item's bases end at the first codon's base i
+                    for (uint32_t t = 0; t < naa; t++) {
+                        const uint32_t i = top - 3 * t;
+                        aab[t] = (uint8_t)codon_aa(tab, pl[sb[i]], pl[sb[i - 1]], pl[sb[i - 2]]); // codon_tables.go:222-226
+                    }
+                }
+            }
+            for (uint32_t u0 = 0; u0 < maxn; u0 += DENSE_S) {
+                for (uint32_t e = 0; e < DENSE_S; e++) {
+                    const uint32_t u = u0 + e;
+                    if (u < nstep) {
+                        ByteSrc s2;
+                        s2.p = src.p + u;
+                        *reinterpret_cast<uint64_t *>(row + e * 8) = wyhash_dev(s2, (uint32_t)k, 1ull); // iterator-protein.go:87
+                    }
+                }
+                const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
+                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, n, 1, it.p0 + u0, lane);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ host: codon tables
+// codonTableFromText (seq/codon_tables.go:316-427): the 64 standard codons, then every ambiguous codon
+// whose expansions agree on one amino acid, axis by axis (third base, second, first).
+static int base2code_host(int b) { // seq/ambiguous_bases.go:28-67; -1 invalid
+    switch (b) {
+    case 'A': case 'a': return 1;  case 'C': case 'c': return 2;  case 'G': case 'g': return 4;
+    case 'T': case 't': case 'U': case 'u': return 8;  case 'N': case 'n': return 15;
+    case 'M': case 'm': return 3;  case 'R': case 'r': return 5;  case 'W': case 'w': return 9;
+    case 'S': case 's': return 6;  case 'Y': case 'y': return 10; case 'K': case 'k': return 12;
+    case 'V': case 'v': return 7;  case 'H': case 'h': return 11; case 'D': case 'd': return 13;
+    case 'B': case 'b': return 14; case ' ': case '*': case '-': return 0;
+    default: return -1;
+    }
+}
+
+static void merge_axis(uint8_t (*t)[16][16], int axis) {
+    for (int i = 1; i < 16; i++)
+        for (int j = 1; j < 16; j++) {
+            int mask_of[256] = {0};
+            for (int c = 1; c < 16; c++) {
+                const uint8_t aa = axis == 3 ? t[i][j][c] : axis == 2 ? t[i][c][j] : t[c][i][j];
+                if (aa) mask_of[aa] |= c;
+            }
+            for (int aa = 1; aa < 256; aa++) {
+                const int amb = mask_of[aa];
+                if (!amb) continue;
+                for (int c = 1; c < 16; c++) {
+                    if ((c & amb) != c) continue;
+                    if (axis == 3) t[i][j][c] = (uint8_t)aa;
+                    else if (axis == 2) t[i][c][j] = (uint8_t)aa;
+                    else t[c][i][j] = (uint8_t)aa;
+                }
+            }
+        }
+}
+
+// Fills aux[4608] for transl_table `id`; false if the reference does not register that table.
+bool build_codon_aux(int id, uint8_t *aux) {
+    const char *aas = nullptr;
+    for (int i = 0; i < B200SK_N_CODON_ROWS; i++)
+        if (B200SK_CODON_ROWS[i].id == id) aas = B200SK_CODON_ROWS[i].aas;
+    if (!aas) return false;
+    static const char order[4] = {'T', 'C', 'A', 'G'};
+    uint8_t(*t)[16][16] = reinterpret_cast<uint8_t(*)[16][16]>(aux);
+    memset(aux, 0, 4608);
+    for (int c = 0; c < 64; c++)
+        t[base2code_host(order[c >> 4])][base2code_host(order[(c >> 2) & 3])][base2code_host(order[c & 3])] =
+            (uint8_t)aas[c];
+    merge_axis(t, 3);
+    merge_axis(t, 2);
+    merge_axis(t, 1);
+    for (int b = 0; b < 256; b++) {
+        const int c = base2code_host(b);
+        aux[4096 + b] = c < 0 ? 0xff : (uint8_t)c;
+        aux[4352 + b] = (uint8_t)pair_letter(B200SK_ALPHABET_DNA, (uint32_t)b);
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ launch
+cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *ill,
+                                 cudaStream_t st) {
+    uint64_t cb = (n_reads + 7) / 8;
+    if (cb > 148 * 16) cb = 148 * 16;
+    if (cb == 0) cb = 1;
+    k_first_illegal<<<(unsigned)cb, 256, 0, st>>>(bases, off, n_reads, ill);
+    return cudaGetLastError();
+}
+
+template <int MODE> static cudaError_t launch_dense_mode(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
+    const void *fn = (const void *)k_dense<MODE>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.sm_total);
+    if (e != cudaSuccess) return e;
+    if (occ) {
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, a.sm_total);
+        *occ = nb < 1 ? 1 : nb;
+        return e;
+    }
+    k_dense<MODE><<<blocks, threads, a.sm_total, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
+    switch (a.mode) {
+    case B200SK_MODE_NTHASH: return launch_dense_mode<B200SK_MODE_NTHASH>(a, threads, blocks, st, occ);
+    case B200SK_MODE_KMER: return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
+    case B200SK_MODE_PROTEIN: return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+} // namespace b200sk

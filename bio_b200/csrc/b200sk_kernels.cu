@@ -26,15 +26,14 @@ namespace b200sk {
 // Per-read chunk count, total number of items and the longest read.
 // meta[0] += items, meta[1] = max(meta[1], L)
 __global__ void k_prepass(const uint64_t *__restrict__ off, const uint64_t *__restrict__ off_orig,
-                          uint64_t n_reads, int mode, int k, int w, int s, uint32_t C,
-                          unsigned long long *meta) {
+                          uint64_t n_reads, const ReadGeom g, uint32_t C, unsigned long long *meta) {
     unsigned long long items = 0, maxlen = 0;
     for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads;
          r += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t L = off[r + 1] - off[r];
         const uint64_t orig = off_orig ? off_orig[r + 1] - off_orig[r] : L;
         int32_t st;
-        const uint32_t np = read_positions(mode, L, orig, k, w, s, &st);
+        const uint32_t np = read_positions(g, r, L, orig, &st);
         items += chunks_of(np, C);
         maxlen = L > maxlen ? L : maxlen;
     }
@@ -50,13 +49,15 @@ __global__ void k_prepass(const uint64_t *__restrict__ off, const uint64_t *__re
     }
 }
 
-// Exclusive scan of chunks-per-read -> item_first[0..n_reads]; single pass with
-// look-back.  1024 reads per tile (256 threads x 4).
-__global__ void __launch_bounds__(256) k_scan_items(const uint64_t *__restrict__ off,
+// Exclusive scan over reads, single pass with look-back, 1024 reads per tile (256 threads x 4).
+//   COUNTS == false: chunks per read  -> item_first[0..n_reads]
+//   COUNTS == true : elements per read (dense modes) -> out[0..n_reads] (+ base), and the per-read status
+template <bool COUNTS>
+__global__ void __launch_bounds__(256) k_scan_reads(const uint64_t *__restrict__ off,
                                                     const uint64_t *__restrict__ off_orig, uint64_t n_reads,
-                                                    int mode, int k, int w, int s, uint32_t C,
-                                                    uint64_t *item_first, uint64_t *tile_state,
-                                                    unsigned long long *ticket) {
+                                                    const ReadGeom g, uint32_t C, uint64_t base,
+                                                    uint64_t *item_first, int32_t *status_out,
+                                                    uint64_t *tile_state, unsigned long long *ticket) {
     __shared__ uint32_t warp_sums[34];
     __shared__ uint64_t sh_tile, sh_base;
     for (;;) {
@@ -74,7 +75,13 @@ __global__ void __launch_bounds__(256) k_scan_items(const uint64_t *__restrict__
                 const uint64_t L = off[r + 1] - off[r];
                 const uint64_t orig = off_orig ? off_orig[r + 1] - off_orig[r] : L;
                 int32_t st;
-                c[i] = chunks_of(read_positions(mode, L, orig, k, w, s, &st), C);
+                const uint32_t np = read_positions(g, r, L, orig, &st);
+                if (COUNTS) {
+                    c[i] = (uint32_t)dense_count(g, np, st);
+                    if (status_out) status_out[r] = st;
+                } else {
+                    c[i] = chunks_of(np, C);
+                }
             }
             sum += c[i];
         }
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(256) k_scan_items(const uint64_t *__restrict__
             if (threadIdx.x == 0) sh_base = b;
         }
         __syncthreads();
-        uint64_t run = sh_base + excl;
+        uint64_t run = base + sh_base + excl;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const uint64_t r = r0 + i;
@@ -444,129 +451,13 @@ __global__ void __launch_bounds__(128) k_sparse(const KArgs a) {
     }
 }
 
-// ------------------------------------------------------------------ dense ntHash kernel
-// NextHash (iterator.go:658-665): every k-mer's hash, canonical or forward.
-// Output ranges are known from the lengths alone; the tile look-back hands out
-// the offsets, the values are written as they are produced.
-__global__ void __launch_bounds__(128) k_dense_hash(const KArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, T = blockDim.x;
-    ulonglong2 *tabIn = reinterpret_cast<ulonglong2 *>(smem);
-    ulonglong2 *tabOut = tabIn + 256;
-    TileCtl *ctl = reinterpret_cast<TileCtl *>(smem + 14336);
-    uint8_t *tilebuf = smem + a.sm_tile;
-    for (uint32_t b = tid; b < 256; b += T) {
-        const uint64_t f = fwd_seed(b), r = rev_seed(b);
-        tabIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(a.k - 1)));
-        tabOut[b] = make_ulonglong2(rol64(f, (unsigned)a.k), ror64(r, 1));
-    }
-    if (tid == 0) {
-        mbar_init(&ctl->mbar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
-    const int k = a.k;
-    const bool canonical = a.canonical != 0;
-    uint32_t parity = 0;
-    for (;;) {
-        if (tid == 0) ctl->tile = atomicAdd(a.ticket, 1ULL);
-        __syncthreads();
-        const uint64_t tile = ctl->tile;
-        const uint64_t item0 = tile * T;
-        if (item0 >= n_items) break;
-        const uint32_t nvalid = (uint32_t)min((uint64_t)T, n_items - item0);
-        // geometry (dense: chunk c owns k-mers [cC, min(np,(c+1)C)); no halo besides the k-1 bases)
-        const uint64_t item = item0 + tid;
-        const bool valid = item < n_items;
-        uint64_t r = item, gb0 = 0;
-        uint32_t c = 0, nstep = 0, nb = 0, p0 = 0;
-        int32_t status = 0;
-        bool first_chunk = false, last_item = false;
-        if (valid) {
-            if (a.item_first) {
-                uint64_t lo = 0, hi = a.n_reads;
-                while (hi - lo > 1) {
-                    const uint64_t mid = (lo + hi) >> 1;
-                    if (a.item_first[mid] <= item) lo = mid; else hi = mid;
-                }
-                r = lo;
-                c = (uint32_t)(item - a.item_first[r]);
-            }
-            first_chunk = c == 0;
-            last_item = item + 1 == n_items;
-            const uint64_t o0 = a.off[r], L = a.off[r + 1] - o0;
-            const uint64_t orig = a.off_orig ? a.off_orig[r + 1] - a.off_orig[r] : L;
-            const uint32_t np = read_positions(B200SK_MODE_NTHASH, L, orig, k, 0, 0, &status);
-            gb0 = o0;
-            if (np) {
-                p0 = c * a.C;
-                nstep = min(np, p0 + a.C) - p0;
-                nb = nstep + (uint32_t)k - 1;
-                gb0 = o0 + p0;
-            }
-        }
-        if (tid == 0) ctl->lo = gb0;
-        if (tid == nvalid - 1) ctl->hi = gb0 + nb;
-        __syncthreads();
-        const uint64_t lo_al = ctl->lo & ~15ULL;
-        const uint64_t span = ctl->hi > lo_al ? ctl->hi - lo_al : 0;
-        const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
-        const bool span_ok = bytes <= a.sm_tile_bytes;
-        if (tid == 0 && bytes && span_ok) {
-            mbar_expect_tx(&ctl->mbar, bytes);
-            tma_load_1d(tilebuf, a.bases + lo_al, bytes, &ctl->mbar);
-        }
-        if (!span_ok && tid == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
-        if (valid && first_chunk && a.status) a.status[r] = status;
-        uint32_t total;
-        const uint32_t excl = block_excl_scan(span_ok ? nstep : 0u, ctl->warp_sums, &total);
-        if (tid < 32) {
-            const uint64_t b = lookback_exclusive(a.tile_state, tile, total);
-            if (tid == 0) ctl->base = b;
-        }
-        __syncthreads();
-        const uint64_t tb = ctl->base;
-        const uint64_t mine = tb + excl;
-        if (valid && first_chunk) a.out_off[r] = a.out_base + mine;
-        if (valid && last_item) a.out_off[a.n_reads] = a.out_base + mine + (span_ok ? nstep : 0u);
-        const bool fits = tb + total <= a.capacity;
-        if (!fits && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
-        if (bytes && span_ok) {
-            mbar_wait(&ctl->mbar, parity);
-            parity ^= 1u;
-        }
-        if (fits && span_ok && nstep) {
-            const uint8_t *sb = tilebuf + (uint32_t)(gb0 - lo_al);
-            uint64_t *gv = a.out_val + mine;
-            uint32_t *gp = a.out_pos ? a.out_pos + mine : nullptr;
-            uint64_t fh = 0, rh = 0;
-            for (int j = 0; j < k - 1; j++) {
-                const ulonglong2 e = tabIn[sb[j]];
-                fh = rol1(fh) ^ e.x;
-                rh = ror1(rh) ^ e.y;
-            }
-            for (uint32_t u = 0; u < nstep; u++) {
-                const ulonglong2 e = tabIn[sb[u + k - 1]];
-                ulonglong2 o = make_ulonglong2(0, 0);
-                if (u) o = tabOut[sb[u - 1]];
-                fh = rol1(fh) ^ o.x ^ e.x;
-                rh = ror1(rh) ^ o.y ^ e.y;
-                gv[u] = (canonical && rh < fh) ? rh : fh; // iterator.go:659
-                if (gp) gp[u] = p0 + u;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ------------------------------------------------------------------ launch helpers (host)
 cudaError_t launch_prepass(const KArgs &a, unsigned long long *meta, cudaStream_t st) {
     const int threads = 256;
     uint64_t blocks = (a.n_reads + threads - 1) / threads;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks == 0) blocks = 1;
-    k_prepass<<<(unsigned)blocks, threads, 0, st>>>(a.off, a.off_orig, a.n_reads, a.mode, a.k, a.w, a.s, a.C, meta);
+    k_prepass<<<(unsigned)blocks, threads, 0, st>>>(a.off, a.off_orig, a.n_reads, a.geom(), a.C, meta);
     return cudaGetLastError();
 }
 
@@ -575,8 +466,18 @@ cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *ti
     uint64_t tiles = (a.n_reads + 1023) / 1024;
     uint64_t blocks = tiles < 148 * 8 ? tiles : 148 * 8;
     if (blocks == 0) blocks = 1;
-    k_scan_items<<<(unsigned)blocks, 256, 0, st>>>(a.off, a.off_orig, a.n_reads, a.mode, a.k, a.w, a.s, a.C,
-                                                  item_first, tile_state, ticket);
+    k_scan_reads<false><<<(unsigned)blocks, 256, 0, st>>>(a.off, a.off_orig, a.n_reads, a.geom(), a.C, 0, item_first,
+                                                         nullptr, tile_state, ticket);
+    return cudaGetLastError();
+}
+
+// dense modes: out_off[0..n_reads] (+ out_base) and read_status straight from the lengths
+cudaError_t launch_scan_counts(const KArgs &a, uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st) {
+    uint64_t tiles = (a.n_reads + 1023) / 1024;
+    uint64_t blocks = tiles < 148 * 8 ? tiles : 148 * 8;
+    if (blocks == 0) blocks = 1;
+    k_scan_reads<true><<<(unsigned)blocks, 256, 0, st>>>(a.off, a.off_orig, a.n_reads, a.geom(), a.C, a.out_base,
+                                                        a.out_off, a.status, tile_state, ticket);
     return cudaGetLastError();
 }
 
@@ -611,10 +512,6 @@ cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st
         if ((e = set_smem((const void *)k_sparse<B200SK_MODE_SYNCMER>, a.sm_total)) != cudaSuccess) return e;
         k_sparse<B200SK_MODE_SYNCMER><<<blocks, threads, a.sm_total, st>>>(a);
         break;
-    case B200SK_MODE_NTHASH:
-        if ((e = set_smem((const void *)k_dense_hash, a.sm_total)) != cudaSuccess) return e;
-        k_dense_hash<<<blocks, threads, a.sm_total, st>>>(a);
-        break;
     default:
         return cudaErrorInvalidValue;
     }
@@ -624,8 +521,7 @@ cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st
 int main_kernel_occupancy(const KArgs &a, int threads) {
     int nb = 0;
     const void *fn = a.mode == B200SK_MODE_MINIMIZER ? (const void *)k_sparse<B200SK_MODE_MINIMIZER>
-                     : a.mode == B200SK_MODE_SYNCMER ? (const void *)k_sparse<B200SK_MODE_SYNCMER>
-                                                     : (const void *)k_dense_hash;
+                                                     : (const void *)k_sparse<B200SK_MODE_SYNCMER>;
     set_smem(fn, a.sm_total);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, a.sm_total) != cudaSuccess) return 1;
     return nb < 1 ? 1 : nb;

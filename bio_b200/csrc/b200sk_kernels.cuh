@@ -10,6 +10,12 @@ namespace b200sk {
 #define B200SK_FLAG_CAPACITY 1u /* output capacity exceeded: values not written       */
 #define B200SK_FLAG_SPAN 2u     /* a read was longer than the max_read_len hint        */
 
+// What the per-read geometry depends on (a slice of KArgs, also used by the small pre-pass kernels).
+struct ReadGeom {
+    int32_t mode, k, w, s, frame, canonical, protein_input;
+    const uint32_t *ill; // MODE_KMER: first illegal base per read (>= length: none); may be null on the host
+};
+
 struct KArgs {
     const uint8_t *bases;
     const uint64_t *off;      // n_reads+1 (circular: offsets into the extended copy)
@@ -29,7 +35,13 @@ struct KArgs {
     uint32_t *flags;
     const uint32_t *ill; // MODE_KMER: first illegal base per read (0xffffffff = none)
     const uint8_t *aux;  // MODE_PROTEIN: codon matrix (4096) + base2code (256) + pair LUT (256); KMER: luts
-    int32_t mode, k, w, s, canonical, frame;
+    int32_t mode, k, w, s, canonical, frame, alphabet;
+    __host__ __device__ ReadGeom geom() const {
+        ReadGeom g;
+        g.mode = mode; g.k = k; g.w = w; g.s = s; g.frame = frame; g.canonical = canonical;
+        g.protein_input = alphabet == 5; g.ill = ill;
+        return g;
+    }
     uint32_t C;        // positions per chunk
     uint32_t span_max; // max bases one item touches
     uint32_t lcap;     // staged outputs per item (sparse modes)
@@ -37,30 +49,60 @@ struct KArgs {
     uint32_t sm_tile, sm_tile_bytes, sm_ring, sm_ring_bytes, sm_listv, sm_listp, sm_total;
 };
 
-// Number of output-candidate positions of a read of (extended) length L, and the
-// status the reference constructor returns for it.  orig = un-extended length.
-//   NTHASH  : k-mers                      iterator.go:616-621
-//   KMER    : k-mers                      iterator.go:669-674
-//   MINIMIZER: windows = L-k-w+2          sketch.go:86-94 (length check on the un-extended length)
-//   SYNCMER : idx in [0, end], end=L-2k+s+1   sketch.go:143-151,173
-__host__ __device__ inline uint32_t read_positions(int mode, uint64_t L, uint64_t orig, int k, int w, int s,
+// amino acids a frame of a read of length L translates to (seq/codon_tables.go:219,255)
+__host__ __device__ inline uint32_t frame_aa_count(uint64_t L, int frame) {
+    const uint64_t f = (uint64_t)(frame < 0 ? -frame : frame);
+    return L >= f + 2 ? (uint32_t)((L - f - 2) / 3 + 1) : 0u;
+}
+
+// Number of output-candidate positions of a read of (extended) length L, and the status the reference
+// returns for it.  orig = un-extended length, r = read index (for ill[]).
+//   NTHASH   : k-mers                         iterator.go:616-621
+//   KMER     : k-mers before the first one holding an illegal base      iterator.go:669-674,730-748
+//   MINIMIZER: windows = L-k-w+2              sketch.go:86-94 (length check on the un-extended length)
+//   SYNCMER  : idx in [0, end], end=L-2k+s+1  sketch.go:143-151,173
+//   PROTEIN  : amino-acid k-mers of the frame iterator-protein.go:47-52,70
+__host__ __device__ inline uint32_t read_positions(const ReadGeom &g, uint64_t r, uint64_t L, uint64_t orig,
                                                    int32_t *status) {
     *status = B200SK_OK;
-    switch (mode) {
-    case B200SK_MODE_KMER:
+    const int k = g.k;
+    switch (g.mode) {
     case B200SK_MODE_NTHASH:
         if (orig < (uint64_t)k) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
         return (uint32_t)(L - (uint64_t)k + 1);
+    case B200SK_MODE_KMER: {
+        if (orig < (uint64_t)k) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
+        const uint32_t np = (uint32_t)(L - (uint64_t)k + 1);
+        if (g.ill) {
+            const uint32_t bad = g.ill[r];
+            if ((uint64_t)bad < orig) {
+                *status = B200SK_ERR_ILLEGAL_BASE;
+                return bad >= (uint32_t)k - 1 ? bad - ((uint32_t)k - 1) : 0u;
+            }
+        }
+        return np;
+    }
     case B200SK_MODE_MINIMIZER:
-        if (orig < (uint64_t)k + (uint64_t)w - 1) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
-        return (uint32_t)(L - (uint64_t)k - (uint64_t)w + 2);
+        if (orig < (uint64_t)k + (uint64_t)g.w - 1) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
+        return (uint32_t)(L - (uint64_t)k - (uint64_t)g.w + 2);
     case B200SK_MODE_SYNCMER: {
-        const int64_t need = 2 * (int64_t)k - s - 1;
+        const int64_t need = 2 * (int64_t)k - g.s - 1;
         if ((int64_t)orig < need || L < (uint64_t)k) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
-        return (uint32_t)(L - 2 * (uint64_t)k + (uint64_t)s + 2);
+        return (uint32_t)(L - 2 * (uint64_t)k + (uint64_t)g.s + 2);
+    }
+    case B200SK_MODE_PROTEIN: {
+        if (orig < 3ull * (uint64_t)k) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
+        const uint32_t naa = g.protein_input ? (uint32_t)L : frame_aa_count(L, g.frame);
+        return naa >= (uint32_t)k ? naa - (uint32_t)k + 1 : 0u;
     }
     default: return 0;
     }
+}
+
+// elements the read emits in a dense mode
+__host__ __device__ inline uint64_t dense_count(const ReadGeom &g, uint32_t np, int32_t status) {
+    if (g.mode == B200SK_MODE_KMER && !g.canonical && status == B200SK_OK) return 2ull * np;
+    return np;
 }
 
 __host__ __device__ inline uint32_t chunks_of(uint32_t npos, uint32_t C) {

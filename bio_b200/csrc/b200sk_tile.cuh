@@ -50,7 +50,7 @@ __device__ __forceinline__ void item_geometry(const KArgs &a, uint64_t item, uin
     const uint64_t o0 = a.off[r], o1 = a.off[r + 1];
     const uint64_t L = o1 - o0;
     const uint64_t orig = a.off_orig ? a.off_orig[r + 1] - a.off_orig[r] : L;
-    const uint32_t np = read_positions(MODE, L, orig, a.k, a.w, a.s, &it.status);
+    const uint32_t np = read_positions(a.geom(), r, L, orig, &it.status);
     it.gb0 = o0;
     if (np == 0) return;
     const uint32_t p0 = c * a.C;

@@ -64,6 +64,7 @@ extern "C" {
 #define B200SK_ALPHABET_RNA_REDUNDANT 2 /* seq/alphabet.go:377 */
 #define B200SK_ALPHABET_RNA 3           /* seq/alphabet.go:369 */
 #define B200SK_ALPHABET_UNLIMIT 4       /* seq/alphabet.go:399: complement is a no-op */
+#define B200SK_ALPHABET_PROTEIN 5       /* MODE_PROTEIN only: records are amino acids already (iterator-protein.go:68) */
 
 /* Constructor arguments, shared by every read of the batch. */
 typedef struct b200sk_params {

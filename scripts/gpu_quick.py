@@ -58,6 +58,19 @@ b4, o4 = synth.ragged_reads([150] * 500, 9, alphabet=b"A")
 allok &= check("minimizer polyA", cabi.MODE_MINIMIZER, oracle.MODE_MINIMIZER, b4, o4, hint=150, k=21, w=11)
 b5, o5 = synth.ragged_reads([5000] * 20, 9, alphabet=b"AC")
 allok &= check("syncmer lowcomplex", cabi.MODE_SYNCMER, oracle.MODE_SYNCMER, b5, o5, k=21, s=11)
+for canon in (True, False):
+    allok &= check(f"kmer 150bp canon={canon}", cabi.MODE_KMER, oracle.MODE_KMER, b, o, hint=150, k=21, canonical=canon)
+    allok &= check(f"kmer ONT canon={canon}", cabi.MODE_KMER, oracle.MODE_KMER, b2, o2, k=31, canonical=canon)
+    allok &= check(f"kmer ragged canon={canon}", cabi.MODE_KMER, oracle.MODE_KMER, b3, o3, k=5, canonical=canon)
+    allok &= check(f"kmer circular canon={canon}", cabi.MODE_KMER, oracle.MODE_KMER, b, o, hint=150, k=21, canonical=canon, circular=True)
+bb = b3.copy(); bb[::97] = ord('-')
+for canon in (True, False):
+    allok &= check(f"kmer illegal canon={canon}", cabi.MODE_KMER, oracle.MODE_KMER, bb, o3, k=7, canonical=canon)
+for fr in (1, 2, 3, -1, -2, -3):
+    allok &= check(f"protein 150bp frame {fr}", cabi.MODE_PROTEIN, oracle.MODE_PROTEIN, b, o, hint=150, k=11, frame=fr)
+    allok &= check(f"protein ONT frame {fr}", cabi.MODE_PROTEIN, oracle.MODE_PROTEIN, b2, o2, k=11, frame=fr)
+    allok &= check(f"protein ragged frame {fr}", cabi.MODE_PROTEIN, oracle.MODE_PROTEIN, b3, o3, k=5, frame=fr)
+allok &= check("protein table 11 k=40", cabi.MODE_PROTEIN, oracle.MODE_PROTEIN, b2, o2, k=40, frame=-2, codon_table=11)
 print("ALL OK" if allok else "SOME FAILED", flush=True)
 
 dev = torch.device("cuda:0")
@@ -66,7 +79,9 @@ for n_reads in (10_000_000,):
     nb = n_reads * 150
     for name, mode, kw in (("minimizer", cabi.MODE_MINIMIZER, dict(k=21, w=11)),
                            ("nthash", cabi.MODE_NTHASH, dict(k=21)),
-                           ("syncmer", cabi.MODE_SYNCMER, dict(k=21, s=11))):
+                           ("syncmer", cabi.MODE_SYNCMER, dict(k=21, s=11)),
+                           ("kmer", cabi.MODE_KMER, dict(k=21)),
+                           ("protein", cabi.MODE_PROTEIN, dict(k=11, frame=1))):
         p = cabi.make_params(mode, max_read_len=150, **kw)
         cap = int(cabi.lib().b200sk_output_bound(p, nb, n_reads, 0))
         val = torch.empty(cap, dtype=torch.int64, device=dev)
