@@ -112,7 +112,8 @@ struct b200sk_ctx {
     int aux_table = -1;
     std::vector<uint8_t> aux_host;
     // host path device buffers
-    DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;
+    DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;       // slot 0
+    DevBuf d_bases2, d_off2, d_val2, d_pos2, d_ooff2, d_status2; // slot 1
     HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
     uint64_t launches = 0;
     bool timing = false;
@@ -503,7 +504,8 @@ void b200sk_destroy(b200sk_ctx *ctx) {
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->circ_bases,
                       &ctx->circ_off, &ctx->ill, &ctx->aux, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
-                      &ctx->d_status})
+                      &ctx->d_status, &ctx->d_bases2, &ctx->d_off2, &ctx->d_val2, &ctx->d_pos2, &ctx->d_ooff2,
+                      &ctx->d_status2})
         b->release();
     for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -601,8 +603,9 @@ int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_
     return 0;
 }
 
-// Host entry point.  Sub-batches of reads flow through three streams (H2D copy, kernels, D2H copy)
-// so the PCIe transfers of neighbouring sub-batches overlap the kernels.
+// Host entry point.  Sub-batches of reads flow through three streams (H2D copy, kernels, D2H copy) and
+// two device slots, so the PCIe transfers of neighbouring sub-batches overlap each other (full duplex)
+// and the kernels.  Output offsets are made global on the device (out_base = elements emitted so far).
 int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
                uint64_t n_reads, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
                int32_t **read_status, uint64_t *n_out) {
@@ -610,51 +613,177 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
     int rc = b200sk_check_params(p);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->own_stream;
-    const uint64_t base0 = read_off[0];
-    const uint64_t n_bases = read_off[n_reads] - base0;
-    // v1: one sub-batch (the pipelined version splits here)
-    CK(ctx->d_bases.reserve(n_bases + 64));
-    CK(ctx->d_off.reserve((n_reads + 1) * 8));
-    CK(ctx->d_ooff.reserve((n_reads + 1) * 8));
-    CK(ctx->d_status.reserve((n_reads + 1) * 4));
+    cudaStream_t s_in = ctx->copy_in, s_k = ctx->own_stream, s_out = ctx->copy_out;
+    const bool want_pos = p->want_pos != 0;
+    const uint64_t n_bases = read_off[n_reads] - read_off[0];
     CK(ctx->h_ooff.reserve((n_reads + 1) * 8));
     CK(ctx->h_status.reserve((n_reads + 1) * 4));
-    if (n_bases) CK(cudaMemcpyAsync(ctx->d_bases.p, bases + base0, n_bases, cudaMemcpyHostToDevice, st));
-    std::vector<uint64_t> rel;
-    const uint64_t *off_src = read_off;
-    if (base0 != 0) {
-        rel.resize(n_reads + 1);
-        for (uint64_t i = 0; i <= n_reads; i++) rel[i] = read_off[i] - base0;
-        off_src = rel.data();
+    CK(ctx->h_meta.reserve(64));
+    uint64_t host_cap = b200sk_output_bound(p, n_bases, n_reads, 0);
+    CK(ctx->h_val.reserve(host_cap * 8 + 8));
+    if (want_pos) CK(ctx->h_pos.reserve(host_cap * 4 + 4));
+    uint64_t *h_ooff = (uint64_t *)ctx->h_ooff.p;
+    volatile uint64_t *h_meta = (volatile uint64_t *)ctx->h_meta.p;
+    if (n_reads == 0) {
+        h_ooff[0] = 0;
+        if (out_val) *out_val = (uint64_t *)ctx->h_val.p;
+        if (out_pos) *out_pos = want_pos ? (uint32_t *)ctx->h_pos.p : nullptr;
+        if (out_off) *out_off = h_ooff;
+        if (read_status) *read_status = (int32_t *)ctx->h_status.p;
+        if (n_out) *n_out = 0;
+        return 0;
     }
-    CK(cudaMemcpyAsync(ctx->d_off.p, off_src, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    uint64_t cap = b200sk_output_bound(p, n_bases, n_reads, 0);
-    uint64_t total = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        CK(ctx->d_val.reserve(cap * 8 + 64));
-        if (p->want_pos) CK(ctx->d_pos.reserve(cap * 4 + 64));
-        rc = b200sk_run_device(ctx, p, (const uint8_t *)ctx->d_bases.p, (const uint64_t *)ctx->d_off.p, n_reads,
-                               n_bases, (uint64_t *)ctx->d_val.p, p->want_pos ? (uint32_t *)ctx->d_pos.p : nullptr,
-                               (uint64_t *)ctx->d_ooff.p, (int32_t *)ctx->d_status.p, cap, st, &total);
-        if (rc != B200SK_ERR_CAPACITY) break;
-        cap = total; // exact requirement reported by the first pass
+    // sub-batch boundaries: about kSubBytes of bases each
+    uint64_t kSubBytes = 384ull << 20;
+    if (const char *e = getenv("B200SK_SUB_BYTES")) { // testing knob: force many small sub-batches
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 16) kSubBytes = v;
     }
-    if (rc) return rc;
-    CK(ctx->h_val.reserve(total * 8 + 8));
-    if (p->want_pos) CK(ctx->h_pos.reserve(total * 4 + 4));
-    if (total) {
-        CK(cudaMemcpyAsync(ctx->h_val.p, ctx->d_val.p, total * 8, cudaMemcpyDeviceToHost, st));
-        if (p->want_pos) CK(cudaMemcpyAsync(ctx->h_pos.p, ctx->d_pos.p, total * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<uint64_t> cut;
+    cut.push_back(0);
+    while (cut.back() < n_reads) {
+        const uint64_t r0 = cut.back();
+        const uint64_t target = read_off[r0] + kSubBytes;
+        uint64_t r1 = (uint64_t)(std::upper_bound(read_off + r0, read_off + n_reads + 1, target) - read_off);
+        if (r1 > r0 + 1) r1--; // last read whose end is <= target ... but always advance by at least one read
+        if (r1 <= r0) r1 = r0 + 1;
+        if (r1 > n_reads) r1 = n_reads;
+        // very short reads: bound the read count too so offsets stay a small share of the slot
+        if (r1 - r0 > (64ull << 20)) r1 = r0 + (64ull << 20);
+        cut.push_back(r1);
     }
-    CK(cudaMemcpyAsync(ctx->h_ooff.p, ctx->d_ooff.p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (n_reads) CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, n_reads * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const size_t n_sub = cut.size() - 1;
+    uint64_t max_sub_bases = 0, max_sub_reads = 0;
+    for (size_t j = 0; j < n_sub; j++) {
+        max_sub_bases = std::max<uint64_t>(max_sub_bases, read_off[cut[j + 1]] - (read_off[cut[j]] & ~15ull));
+        max_sub_reads = std::max<uint64_t>(max_sub_reads, cut[j + 1] - cut[j]);
+    }
+    struct Slot {
+        DevBuf bases, off, val, pos, ooff, status;
+        cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+        uint64_t cap = 0;
+        bool out_pending = false;
+    };
+    Slot slot[2];
+    auto free_slots = [&]() {
+        for (auto &sl : slot) {
+            sl.bases.release(); sl.off.release(); sl.val.release(); sl.pos.release(); sl.ooff.release();
+            sl.status.release();
+            if (sl.in_done) cudaEventDestroy(sl.in_done);
+            if (sl.k_done) cudaEventDestroy(sl.k_done);
+            if (sl.out_done) cudaEventDestroy(sl.out_done);
+        }
+    };
+    // the slot buffers persist in the ctx between calls (allocation is not free): move them in and out
+    DevBuf *persist[2][6] = {{&ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff, &ctx->d_status},
+                             {&ctx->d_bases2, &ctx->d_off2, &ctx->d_val2, &ctx->d_pos2, &ctx->d_ooff2, &ctx->d_status2}};
+    for (int i = 0; i < 2; i++) {
+        slot[i].bases = *persist[i][0]; slot[i].off = *persist[i][1]; slot[i].val = *persist[i][2];
+        slot[i].pos = *persist[i][3]; slot[i].ooff = *persist[i][4]; slot[i].status = *persist[i][5];
+        for (int q = 0; q < 6; q++) { persist[i][q]->p = nullptr; persist[i][q]->cap = 0; }
+        const uint64_t cv = slot[i].val.cap >= 64 ? (slot[i].val.cap - 64) / 8 : 0;
+        const uint64_t cp = slot[i].pos.cap >= 64 ? (slot[i].pos.cap - 64) / 4 : 0;
+        slot[i].cap = want_pos ? std::min(cv, cp) : cv;
+    }
+    auto save_slots = [&]() {
+        for (int i = 0; i < 2; i++) {
+            *persist[i][0] = slot[i].bases; *persist[i][1] = slot[i].off; *persist[i][2] = slot[i].val;
+            *persist[i][3] = slot[i].pos; *persist[i][4] = slot[i].ooff; *persist[i][5] = slot[i].status;
+            slot[i].bases = DevBuf(); slot[i].off = DevBuf(); slot[i].val = DevBuf(); slot[i].pos = DevBuf();
+            slot[i].ooff = DevBuf(); slot[i].status = DevBuf();
+        }
+        free_slots();
+    };
+#define CKS(call)                                                 \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) {                                  \
+            cudaDeviceSynchronize();                              \
+            save_slots();                                         \
+            return cuda_fail(ctx, _e, #call);                     \
+        }                                                         \
+    } while (0)
+    for (auto &sl : slot) {
+        CKS(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+        CKS(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+        CKS(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+        CKS(sl.bases.reserve(max_sub_bases + 64));
+        CKS(sl.off.reserve((max_sub_reads + 1) * 8));
+        CKS(sl.ooff.reserve((max_sub_reads + 1) * 8));
+        CKS(sl.status.reserve((max_sub_reads + 1) * 4));
+    }
+    auto issue_h2d = [&](size_t j) -> cudaError_t {
+        Slot &sl = slot[j & 1];
+        const uint64_t r0 = cut[j], r1 = cut[j + 1];
+        const uint64_t b0 = read_off[r0] & ~15ull, b1 = read_off[r1];
+        cudaError_t e;
+        if (b1 > b0 && (e = cudaMemcpyAsync(sl.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s_in)) != cudaSuccess)
+            return e;
+        if ((e = cudaMemcpyAsync(sl.off.p, read_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s_in)) != cudaSuccess)
+            return e;
+        return cudaEventRecord(sl.in_done, s_in);
+    };
+    uint64_t running = 0;
+    CKS(issue_h2d(0));
+    for (size_t j = 0; j < n_sub; j++) {
+        Slot &sl = slot[j & 1];
+        const uint64_t r0 = cut[j], r1 = cut[j + 1], nr = r1 - r0;
+        const uint64_t b0 = read_off[r0] & ~15ull, nb = read_off[r1] - read_off[r0];
+        // the other slot's kernel (sub-batch j-1) has been waited for below, so its inputs are free
+        if (j + 1 < n_sub) CKS(issue_h2d(j + 1));
+        CKS(cudaStreamWaitEvent(s_k, sl.in_done, 0));
+        if (sl.out_pending) CKS(cudaStreamWaitEvent(s_k, sl.out_done, 0)); // slot outputs still draining
+        uint64_t cap = std::max<uint64_t>(sl.cap, b200sk_output_bound(p, nb, nr, 0));
+        uint64_t total = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if (cap > sl.cap) {
+                if (sl.out_pending) CKS(cudaEventSynchronize(sl.out_done));
+                CKS(sl.val.reserve(cap * 8 + 64));
+                if (want_pos) CKS(sl.pos.reserve(cap * 4 + 64));
+                sl.cap = cap;
+            }
+            const uint8_t *dbase = (const uint8_t *)sl.bases.p - b0; // offsets stay absolute
+            rc = enqueue(ctx, *p, dbase, (const uint64_t *)sl.off.p, nr, nb, (uint64_t *)sl.val.p,
+                         want_pos ? (uint32_t *)sl.pos.p : nullptr, (uint64_t *)sl.ooff.p, (int32_t *)sl.status.p,
+                         sl.cap, running, s_k, nullptr);
+            if (rc) { cudaDeviceSynchronize(); save_slots(); return rc; }
+            CKS(cudaMemcpyAsync((void *)h_meta, (uint64_t *)sl.ooff.p + nr, 8, cudaMemcpyDeviceToHost, s_k));
+            CKS(cudaMemcpyAsync((void *)(h_meta + 1), (unsigned long long *)ctx->meta.p + 1, 8, cudaMemcpyDeviceToHost, s_k));
+            CKS(cudaEventRecord(sl.k_done, s_k));
+            CKS(cudaEventSynchronize(sl.k_done));
+            total = h_meta[0] - running;
+            const uint64_t flags = h_meta[1];
+            if (flags & B200SK_FLAG_SPAN) { cudaDeviceSynchronize(); save_slots(); return B200SK_ERR_BAD_ARG; }
+            if (!(flags & B200SK_FLAG_CAPACITY)) break;
+            cap = total; // exact requirement reported by the first pass
+            if (attempt == 1) { cudaDeviceSynchronize(); save_slots(); return B200SK_ERR_CAPACITY; }
+        }
+        if (running + total > host_cap) { // estimate too small: grow the pinned result arrays, keeping their content
+            CKS(cudaStreamSynchronize(s_out));
+            host_cap = (running + total) + (running + total) / 4 + 1024;
+            CKS(ctx->h_val.reserve(host_cap * 8 + 8, true));
+            if (want_pos) CKS(ctx->h_pos.reserve(host_cap * 4 + 4, true));
+        }
+        CKS(cudaStreamWaitEvent(s_out, sl.k_done, 0));
+        if (total) {
+            CKS(cudaMemcpyAsync((uint64_t *)ctx->h_val.p + running, sl.val.p, total * 8, cudaMemcpyDeviceToHost, s_out));
+            if (want_pos)
+                CKS(cudaMemcpyAsync((uint32_t *)ctx->h_pos.p + running, sl.pos.p, total * 4, cudaMemcpyDeviceToHost, s_out));
+        }
+        CKS(cudaMemcpyAsync(h_ooff + r0, sl.ooff.p, (nr + 1) * 8, cudaMemcpyDeviceToHost, s_out));
+        CKS(cudaMemcpyAsync((int32_t *)ctx->h_status.p + r0, sl.status.p, nr * 4, cudaMemcpyDeviceToHost, s_out));
+        CKS(cudaEventRecord(sl.out_done, s_out));
+        sl.out_pending = true;
+        running += total;
+    }
+    CKS(cudaStreamSynchronize(s_out));
+    save_slots();
+#undef CKS
     if (out_val) *out_val = (uint64_t *)ctx->h_val.p;
-    if (out_pos) *out_pos = p->want_pos ? (uint32_t *)ctx->h_pos.p : nullptr;
-    if (out_off) *out_off = (uint64_t *)ctx->h_ooff.p;
+    if (out_pos) *out_pos = want_pos ? (uint32_t *)ctx->h_pos.p : nullptr;
+    if (out_off) *out_off = h_ooff;
     if (read_status) *read_status = (int32_t *)ctx->h_status.p;
-    if (n_out) *n_out = total;
+    if (n_out) *n_out = running;
     return 0;
 }
 

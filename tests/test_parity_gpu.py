@@ -257,3 +257,21 @@ def test_c2_c3_scale_properties(gpu_ctx):
     mv_np = mv.cpu().numpy().view(np.uint64)
     got = np.concatenate([mv_np[o_np[i]:o_np[i + 1]] for i in idx])
     assert np.array_equal(got, ref["val"])
+
+
+def test_host_pipeline_many_subbatches(gpu_ctx, monkeypatch):
+    """b200sk_run splits the batch into sub-batches that flow through two device slots; force tiny
+    sub-batches (ragged boundaries, unaligned starts) and compare the stitched result with the oracle."""
+    monkeypatch.setenv("B200SK_SUB_BYTES", "20000")
+    lens = np.concatenate([np.full(700, 150), synth.ont_like_lengths(30, 5, mean=4000), [0, 7, 31, 150, 33]])
+    b, o = synth.ragged_reads(lens, 21)
+    for mode, kw in ((cabi.MODE_MINIMIZER, dict(k=21, w=11)), (cabi.MODE_SYNCMER, dict(k=21, s=11)),
+                     (cabi.MODE_NTHASH, dict(k=21)), (cabi.MODE_KMER, dict(k=21, canonical=False)),
+                     (cabi.MODE_PROTEIN, dict(k=11, frame=-2)), (cabi.MODE_MINIMIZER, dict(k=21, w=11, circular=True))):
+        res, ref = run_both(gpu_ctx, mode, b, o, **kw)
+        assert_same(res, ref, f"mode={mode}")
+    # a view that does not start at offset 0 of the buffer
+    res = gpu_ctx.run(cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11), b, o[100:])
+    ref = oracle.run_batch(b, o[100:], oracle.MODE_MINIMIZER, k=21, w=11, threads=4)
+    assert np.array_equal(res["val"], ref["val"]) and np.array_equal(res["pos"], ref["pos"])
+    assert np.array_equal(res["off"], ref["off"])
