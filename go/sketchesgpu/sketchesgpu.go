@@ -1,0 +1,265 @@
+// Package sketchesgpu is the cgo shim that puts libb200sketch.so behind the method set of
+// github.com/shenwei356/bio/sketches (Iterator / Sketch / ProteinIterator): constructors with the same
+// names, arguments and errors, Next()/Index() with the same meaning.
+//
+// The reference API is a pull iterator over ONE sequence; a cgo call per element (~100 ns) would be an order
+// of magnitude slower than the Go loop it replaces, so the shim is batch-shaped underneath:
+//
+//	b := sketchesgpu.NewBatch(ctx)            // pinned staging buffer, C-owned
+//	for chunk := range reader.ChunkChan(...)  // seqio/fastx/reader.go:562
+//	    for _, rec := range chunk.Data { b.Add(rec.Seq) }
+//	res, _ := b.MinimizerSketch(k, w, false)  // ONE cgo call: the whole batch is sketched on the GPU
+//	for i := range chunk.Data {
+//	    sk := res.Sketch(i)                   // *sketchesgpu.Sketch with the reference's method set
+//	    for { v, ok := sk.Next(); if !ok { break }; _ = sk.Index() }
+//	}
+//
+// NOTE: this file is authored against include/b200sketch.h but has NOT been compiled: the build image has
+// no Go toolchain (INTEGRATION.md).  The Python mirror (bio_b200/sketches.py) exercises the same C ABI and
+// is what the parity tests run.
+package sketchesgpu
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../bio_b200/lib -lb200sketch -Wl,-rpath,${SRCDIR}/../../bio_b200/lib
+#include <stdlib.h>
+#include <string.h>
+#include "b200sketch.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"unsafe"
+
+	"github.com/shenwei356/bio/seq"
+)
+
+// The reference's exported errors (sketches/iterator.go:34-53, sketches/sketch.go:32-42).
+var (
+	ErrInvalidK    = fmt.Errorf("sketches: invalid k-mer size")
+	ErrShortSeq    = fmt.Errorf("sketches: sequence too short")
+	ErrIllegalBase = errors.New("sketches: illegal base")
+	ErrKTooLarge   = fmt.Errorf("sketches: k-mer size is too large")
+	ErrInvalidS    = fmt.Errorf("kmers: invalid s-mer size")
+	ErrInvalidW    = fmt.Errorf("kmers: invalid minimimzer window")
+)
+
+func codeToError(rc C.int) error {
+	switch rc {
+	case C.B200SK_OK:
+		return nil
+	case C.B200SK_ERR_INVALID_K:
+		return ErrInvalidK
+	case C.B200SK_ERR_SHORT_SEQ:
+		return ErrShortSeq
+	case C.B200SK_ERR_INVALID_W:
+		return ErrInvalidW
+	case C.B200SK_ERR_INVALID_S:
+		return ErrInvalidS
+	case C.B200SK_ERR_ILLEGAL_BASE:
+		return ErrIllegalBase
+	case C.B200SK_ERR_K_OVERFLOW:
+		return ErrKTooLarge
+	default:
+		return errors.New(C.GoString(C.b200sk_strerror(rc)))
+	}
+}
+
+// Context owns one GPU (one per goroutine; not goroutine-safe, like the reference's iterators).
+type Context struct{ h *C.b200sk_ctx }
+
+// NewContext binds CUDA device `device`.  There is no CPU fallback: without a device this fails.
+func NewContext(device int) (*Context, error) {
+	var h *C.b200sk_ctx
+	if rc := C.b200sk_create(&h, C.int(device)); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	return &Context{h}, nil
+}
+
+// Close releases the device buffers.
+func (c *Context) Close() { C.b200sk_destroy(c.h); c.h = nil }
+
+// Batch packs record.Seq.Seq bytes into a C-owned pinned buffer (cgo must not let C keep Go pointers).
+type Batch struct {
+	ctx    *Context
+	bases  unsafe.Pointer // pinned, capBases bytes
+	nBases int
+	cap    int
+	off    []C.uint64_t // read offsets, len = reads+1
+	maxLen int
+	alpha  C.int32_t
+}
+
+// NewBatch allocates a staging buffer of capBytes (grown on demand).
+func NewBatch(ctx *Context, capBytes int) *Batch {
+	return &Batch{ctx: ctx, bases: C.b200sk_alloc_pinned(C.size_t(capBytes)), cap: capBytes,
+		off: []C.uint64_t{0}, alpha: C.B200SK_ALPHABET_DNA_REDUNDANT}
+}
+
+// Add appends one sequence (the bytes are copied: fastx.Reader reuses its buffer, reader.go:229-232).
+func (b *Batch) Add(s *seq.Seq) {
+	n := len(s.Seq)
+	if b.nBases+n+64 > b.cap {
+		ncap := 2*(b.nBases+n) + 64
+		nb := C.b200sk_alloc_pinned(C.size_t(ncap))
+		C.memcpy(nb, b.bases, C.size_t(b.nBases))
+		C.b200sk_free_pinned(b.bases)
+		b.bases, b.cap = nb, ncap
+	}
+	if n > 0 {
+		C.memcpy(unsafe.Add(b.bases, b.nBases), unsafe.Pointer(&s.Seq[0]), C.size_t(n))
+	}
+	b.nBases += n
+	b.off = append(b.off, C.uint64_t(b.nBases))
+	if n > b.maxLen {
+		b.maxLen = n
+	}
+	switch s.Alphabet {
+	case seq.DNA:
+		b.alpha = C.B200SK_ALPHABET_DNA
+	case seq.RNA:
+		b.alpha = C.B200SK_ALPHABET_RNA
+	case seq.RNAredundant:
+		b.alpha = C.B200SK_ALPHABET_RNA_REDUNDANT
+	case seq.Unlimit:
+		b.alpha = C.B200SK_ALPHABET_UNLIMIT
+	case seq.Protein:
+		b.alpha = C.B200SK_ALPHABET_PROTEIN
+	}
+}
+
+// Reset empties the batch, keeping the buffer.
+func (b *Batch) Reset() { b.nBases, b.off, b.maxLen = 0, b.off[:1], 0 }
+
+// Free releases the pinned buffer.
+func (b *Batch) Free() { C.b200sk_free_pinned(b.bases); b.bases = nil }
+
+// Result holds the library-owned output arrays of one run (valid until the next run on the context).
+type Result struct {
+	val    []uint64
+	pos    []uint32
+	off    []uint64
+	status []int32
+}
+
+func (b *Batch) run(p *C.b200sk_params) (*Result, error) {
+	if rc := C.b200sk_check_params(p); rc != 0 { // what the reference constructor returns before looking at a sequence
+		return nil, codeToError(rc)
+	}
+	p.alphabet = b.alpha
+	p.want_pos = 1
+	p.max_read_len = C.uint32_t(b.maxLen)
+	n := len(b.off) - 1
+	var v *C.uint64_t
+	var ps *C.uint32_t
+	var o *C.uint64_t
+	var st *C.int32_t
+	var total C.uint64_t
+	rc := C.b200sk_run(b.ctx.h, p, (*C.uint8_t)(b.bases), &b.off[0], C.uint64_t(n), &v, &ps, &o, &st, &total)
+	if rc != 0 {
+		return nil, codeToError(rc)
+	}
+	return &Result{
+		val:    unsafe.Slice((*uint64)(unsafe.Pointer(v)), int(total)),
+		pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
+		off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), n+1),
+		status: unsafe.Slice((*int32)(unsafe.Pointer(st)), n),
+	}, nil
+}
+
+// KmerIterator == sketches.NewKmerIterator over every read (iterator.go:668).
+func (b *Batch) KmerIterator(k int, canonical, circular bool) (*Result, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_KMER, k: C.int32_t(k), canonical: cbool(canonical), circular: cbool(circular)}
+	return b.run(&p)
+}
+
+// HashIterator == sketches.NewHashIterator (iterator.go:615).
+func (b *Batch) HashIterator(k int, canonical, circular bool) (*Result, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_NTHASH, k: C.int32_t(k), canonical: cbool(canonical), circular: cbool(circular)}
+	return b.run(&p)
+}
+
+// MinimizerSketch == sketches.NewMinimizerSketch (sketch.go:85).
+func (b *Batch) MinimizerSketch(k, w int, circular bool) (*Result, error) {
+	if w > (1<<31)-1 {
+		return nil, ErrInvalidW
+	}
+	p := C.b200sk_params{mode: C.B200SK_MODE_MINIMIZER, k: C.int32_t(k), w: C.int32_t(w), circular: cbool(circular)}
+	return b.run(&p)
+}
+
+// SyncmerSketch == sketches.NewSyncmerSketch (sketch.go:142).
+func (b *Batch) SyncmerSketch(k, s int, circular bool) (*Result, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_SYNCMER, k: C.int32_t(k), s: C.int32_t(s), circular: cbool(circular)}
+	return b.run(&p)
+}
+
+// ProteinIterator == sketches.NewProteinIterator (iterator-protein.go:46).
+func (b *Batch) ProteinIterator(k, codonTable, frame int) (*Result, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_PROTEIN, k: C.int32_t(k), codon_table: C.int32_t(codonTable), frame: C.int32_t(frame)}
+	return b.run(&p)
+}
+
+func cbool(b bool) C.int32_t {
+	if b {
+		return 1
+	}
+	return 0
+}
+
+// Iterator replays one read's slice with the reference's method set
+// (sketches.Iterator / sketches.Sketch / sketches.ProteinIterator: Next, Index).
+type Iterator struct {
+	val []uint64
+	pos []uint32
+	i   int
+	err error // the constructor / NextKmer error of this read
+}
+
+// Sketch is the same replay type under the reference's other name.
+type Sketch = Iterator
+
+// Iterator returns read i's iterator, or the error the reference constructor returns for that read
+// (ErrShortSeq ...).  For k-mer codes an illegal base is reported by Next after the codes before it
+// (iterator.go:730-748).
+func (r *Result) Iterator(i int) (*Iterator, error) {
+	st := C.int(r.status[i])
+	it := &Iterator{val: r.val[r.off[i]:r.off[i+1]], pos: r.pos[r.off[i]:r.off[i+1]]}
+	if st == C.B200SK_ERR_ILLEGAL_BASE {
+		it.err = ErrIllegalBase
+		return it, nil
+	}
+	if st != 0 {
+		return nil, codeToError(st)
+	}
+	return it, nil
+}
+
+// Sketch is Iterator under the name used for minimizers and syncmers.
+func (r *Result) Sketch(i int) (*Sketch, error) { return r.Iterator(i) }
+
+// Next returns the next element (sketches.Iterator.NextHash / Sketch.Next / ProteinIterator.Next).
+func (it *Iterator) Next() (uint64, bool) {
+	if it.i >= len(it.val) {
+		return 0, false
+	}
+	v := it.val[it.i]
+	it.i++
+	return v, true
+}
+
+// NextKmer mirrors (*Iterator).NextKmer (iterator.go:708): the deferred illegal-base error comes last.
+func (it *Iterator) NextKmer() (uint64, bool, error) {
+	if it.i >= len(it.val) {
+		return 0, false, it.err
+	}
+	v := it.val[it.i]
+	it.i++
+	return v, true, nil
+}
+
+// Index returns the 0-based position of the last returned element (iterator.go:776, sketch.go:488).
+func (it *Iterator) Index() int { return int(it.pos[it.i-1]) }
