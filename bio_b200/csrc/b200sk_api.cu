@@ -19,8 +19,8 @@ cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *ti
                               unsigned long long *ticket, cudaStream_t st);
 cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st);
 int main_kernel_occupancy(const KArgs &a, int threads);
-cudaError_t launch_minimizer_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
-bool minimizer_reg_supported(int w);
+cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
+bool sparse_reg_supported(int mode, int k, int w, int s);
 cudaError_t launch_scan_counts(const KArgs &a, uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st);
 cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *ill,
                                  cudaStream_t st);
@@ -90,6 +90,7 @@ struct Plan {
 };
 
 const uint32_t kChunk = 256;        // positions per chunk for long reads
+const uint32_t kChunkReg = 128;     // ... for the register-window kernels (shared memory per lane is the limit)
 const uint32_t kSingleMaxLen = 384; // reads up to this length are one item each
 const uint32_t kSmemCtl = 14336 + 256;
 const uint32_t kSmemLimit = 227 * 1024;
@@ -161,7 +162,8 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         pl.C = np ? np : 1;
         pl.span_max = (uint32_t)max_len;
     } else {
-        pl.C = kChunk;
+        pl.C = (mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER) && sparse_reg_supported(mode, k, w, s)
+                   ? kChunkReg : kChunk;
         if ((uint64_t)pl.C + halo > 20000) return B200SK_ERR_UNSUPPORTED;
         pl.span_max = (uint32_t)(pl.C + halo);
         if (mode == B200SK_MODE_PROTEIN && p.alphabet != B200SK_ALPHABET_PROTEIN) pl.span_max *= 3; // codons
@@ -200,31 +202,30 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         pl.lcap = (uint32_t)std::min<double>(pl.C, e);
         if (pl.lcap < 1) pl.lcap = 1;
     }
-    pl.reg = mode == B200SK_MODE_MINIMIZER && minimizer_reg_supported(w);
+    pl.reg = sparse && sparse_reg_supported(mode, k, w, s);
     if (pl.reg) {
-        // tables 2 KB + control, tile, lists of (lcap+1) slots x (8 B value + 1 B position delta)
-        int best_warps = -1;
+        // one tile per warp.  tables 4 KB, then per warp: mbarrier 16 B, tile, k-mer ring (syncmer),
+        // lists of (lcap+1) slots x 32 lanes x (8 B value + 1 B position delta).
+        int best_nw = 0;
         Plan best = pl;
-        for (int T : {128, 96, 64}) {
+        for (uint32_t shave = 0; shave <= 2 && shave + 8 < pl.lcap; shave++) {
             Plan c = pl;
-            c.T = T;
-            c.sm_tile = 2048 + 256;
-            c.sm_tile_bytes = up16((uint32_t)T * c.span_max + 32);
-            c.sm_ring = c.sm_tile + c.sm_tile_bytes;
-            c.sm_ring_bytes = 0;
-            c.sm_listv = c.sm_ring;
-            c.sm_listp = c.sm_listv + up16((c.lcap + 1) * T * 8);
-            c.sm_total = c.sm_listp + up16((c.lcap + 1) * T);
-            if (c.sm_total > kSmemLimit) continue;
-            int ctas = (int)(233472u / (c.sm_total + 1024u));
-            ctas = std::min(ctas, 65536 / (T * 128)); // registers: <= 128 per thread
-            ctas = std::min(ctas, 32);
-            if (ctas < 1) continue;
-            c.ctas_per_sm = ctas;
-            const int warps = ctas * T / 32;
-            if (warps > best_warps) { best_warps = warps; best = c; }
+            c.lcap = pl.lcap - shave;
+            c.sm_tile = 4096;
+            c.sm_tile_bytes = up16(32u * c.span_max + 32);
+            c.sm_ring = 16 + c.sm_tile_bytes;
+            c.sm_listv = c.sm_ring + (uint32_t)d * 256u;
+            c.sm_listp = c.sm_listv + (c.lcap + 1) * 256u;
+            c.sm_ring_bytes = up16(c.sm_listp + (c.lcap + 1) * 32u); // per-warp stride
+            int nw = (int)((232448u - 1024u - c.sm_tile) / c.sm_ring_bytes);
+            if (nw > 16) nw = 16;
+            if (nw < 1) continue;
+            c.T = nw * 32;
+            c.ctas_per_sm = 1;
+            c.sm_total = c.sm_tile + (uint32_t)nw * c.sm_ring_bytes;
+            if (nw > best_nw) { best_nw = nw; best = c; }
         }
-        if (best_warps > 0) { pl = best; return 0; }
+        if (best_nw > 0) { pl = best; return 0; }
         pl.reg = false;
     }
     for (int T : {128, 64, 32}) {
@@ -325,7 +326,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     bool have_items_host = true;
     if (max_len == 0) {
         // measure the longest read (and, with the chunked geometry, the item count)
-        a.C = kChunk;
+        { Plan tmp; if ((rc = make_plan(q, 0, tmp))) return rc; a.C = tmp.C; }
         CK(launch_prepass(a, meta + 2, st));
         ctx->launches++;
         unsigned long long hm[2];
@@ -382,7 +383,8 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         a.n_items_dev = nullptr;
         a.n_items = n_reads;
     }
-    const uint64_t n_tiles = (items_bound + pl.T - 1) / pl.T + 1;
+    const uint32_t tile_items = pl.reg ? 32u : (uint32_t)pl.T; // the register-window kernels tile per warp
+    const uint64_t n_tiles = (items_bound + tile_items - 1) / tile_items + 1;
     if (!pl.dense) {
         CK(ctx->tile_state.reserve(n_tiles * 8));
         CK(cudaMemsetAsync(ctx->tile_state.p, 0, n_tiles * 8, st));
@@ -391,10 +393,11 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     a.ticket = meta + 0;
     int occ = 1;
     if (pl.dense) CK(launch_dense(a, pl.T, 0, st, &occ));
-    else if (pl.reg) CK(launch_minimizer_reg(a, pl.T, 0, st, &occ));
+    else if (pl.reg) CK(launch_sparse_reg(a, pl.T, 0, st, &occ));
     else occ = main_kernel_occupancy(a, pl.T);
     uint64_t blocks = (uint64_t)occ * ctx->sm_count;
-    if (blocks > n_tiles) blocks = n_tiles;
+    const uint64_t tiles_per_block = pl.reg ? (uint64_t)pl.T / 32 : 1;
+    if (blocks > (n_tiles + tiles_per_block - 1) / tiles_per_block) blocks = (n_tiles + tiles_per_block - 1) / tiles_per_block;
     if (blocks < 1) blocks = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->timing) {
@@ -403,7 +406,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(cudaEventRecord(ev0, st));
     }
     if (pl.dense) CK(launch_dense(a, pl.T, (int)blocks, st, nullptr));
-    else if (pl.reg) CK(launch_minimizer_reg(a, pl.T, (int)blocks, st, nullptr));
+    else if (pl.reg) CK(launch_sparse_reg(a, pl.T, (int)blocks, st, nullptr));
     else CK(launch_main(a, pl.T, (int)blocks, st));
     ctx->launches++;
     if (ctx->timing) {

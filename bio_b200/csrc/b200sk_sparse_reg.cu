@@ -90,30 +90,28 @@ __device__ __forceinline__ void suffix_step(uint64_t &h, uint32_t &ph, uint32_t 
 __device__ __forceinline__ uint64_t min_u64(uint64_t a, uint64_t b) { return mux64(lt_mask(a, b), a, b); }
 
 // ------------------------------------------------------------------ sinks
-// emit(p, v, delta): record (v, delta) when p.  The slot address and the operands are computed
-// unconditionally; only the two stores and the counter depend on p, so the compiler predicates them
-// instead of branching (some lane of a warp emits on almost every step).
-struct ListSink { // staged in shared memory, [slot][thread]; slot `cap` is a scratch slot for overflow
-    uint32_t av, ap, sv, sp, cap, cnt; // av/ap: 32-bit shared-window addresses of this thread's slot 0
-    __device__ __forceinline__ void emit(uint32_t mu, uint32_t prev, uint64_t v) {
+// emit_if(p, v, delta): record (v, delta) when p.  The slot address and the operands are computed
+// unconditionally; only the two stores and the counter depend on p and they are PREDICATED, not branched
+// around (some lane of a warp emits on almost every step).
+struct ListSink { // staged in shared memory, [slot][lane]; slot `cap` is a scratch slot for overflow
+    uint32_t av, ap, cap, cnt; // av/ap: 32-bit shared-window addresses of this lane's slot 0
+    __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t delta) {
         const uint32_t slot = min(cnt, cap);
-        const uint32_t ov = av + slot * sv, op = ap + slot * sp;
-        const uint32_t delta = mu - prev;
-        // predicated stores (no branch): record iff the minimum moved
+        const uint32_t ov = av + slot * 256u, op = ap + slot * 32u; // 32 lanes x 8 B / x 1 B per slot
         asm volatile(
-            "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, %2;\n\t@q st.shared.u64 [%3], %4;\n\t"
-            "@q st.shared.u8 [%5], %6;\n\t@q add.u32 %0, %0, 1;\n\t}"
+            "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q st.shared.u64 [%2], %3;\n\t"
+            "@q st.shared.u8 [%4], %5;\n\t@q add.u32 %0, %0, 1;\n\t}"
             : "+r"(cnt)
-            : "r"(mu), "r"(prev), "r"(ov), "l"(v), "r"(op), "r"(delta));
+            : "r"(pred), "r"(ov), "l"(v), "r"(op), "r"(delta));
     }
 };
 struct GlobalSink { // straight to the final position (tiles where some item overflowed its list)
     uint64_t *gv;
     uint32_t *gp;
     uint32_t pos, cnt, skip;
-    __device__ __forceinline__ void emit(uint32_t mu, uint32_t prev, uint64_t v) {
-        if (mu != prev) {
-            pos += mu - prev;
+    __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t delta) {
+        if (pred) {
+            pos += delta;
             if (cnt >= skip) {
                 gv[cnt - skip] = v;
                 if (gp) gp[cnt - skip] = pos;
@@ -140,147 +138,237 @@ struct Roll {
 // ------------------------------------------------------------------ window minimum in registers
 // Block decomposition over blocks of W stream elements.  hs[j] holds the current block's element j
 // until the block ends, then the suffix minimum S[j] of that block; sp[j] = block-relative index of
-// S[j].  Positions are tracked relative to the start of the PREVIOUS block (frame), so all selects use
-// compile-time constants: S positions are 0..W-1, P positions W..2W-1.
+// S[j].  Positions are tracked relative to the start of the PREVIOUS block (the frame), so the position
+// operands are constants: S positions are 0..W-1, P positions W..2W-1.
 template <int W> struct WinReg {
     uint64_t hs[W];
     uint32_t sp[W];
     uint64_t pv;
     uint32_t pj;
-    uint32_t prev;  // frame-relative position of the previous window's minimum
     uint32_t wbase; // == W, but a run-time value: position constants are formed as wbase + J in a register
-                    // (IMAD, fma pipe) so that both selects of an update share ONE predicate; with an
-                    // immediate operand ptxas re-evaluates the 64-bit compare for the other polarity
+                    // (IMAD, fma pipe); with an immediate operand ptxas re-evaluates the 64-bit compare for
+                    // the other predicate polarity
 
-    __device__ __forceinline__ void init(uint32_t w_runtime) { prev = W - 1; pv = 0; pj = 0; wbase = w_runtime; }
+    __device__ __forceinline__ void init(uint32_t w_runtime) { pv = 0; pj = 0; wbase = w_runtime; }
 
-    // element j of the current block.  FIRST: block 0 (no previous block: only the last element closes a window)
-    template <class SinkT> __device__ __forceinline__ void push(const int J, const bool FIRST, uint64_t h, SinkT &sink) {
+    // element J of the current block.  FIRST: block 0 (no previous block: only the last element closes a
+    // window).  Returns true (compile-time) when a window closes here; (mv, mu) = its leftmost minimum.
+    __device__ __forceinline__ bool push(const int J, const bool FIRST, uint64_t h, uint64_t &mv, uint32_t &mu) {
         if (J == 0) { pv = h; pj = W; }
         else take_if_less(pv, pj, h, wbase + (uint32_t)J); // strictly less: the leftmost stays on ties
-        if (!FIRST || J == W - 1) {
-            uint64_t mv = pv;
-            uint32_t mu = pj;
+        const bool closes = !FIRST || J == W - 1;
+        if (closes) {
+            mv = pv;
+            mu = pj;
             if (J != W - 1) pick_min(mv, mu, pv, pj, hs[J + 1], sp[J + 1]);
-            sink.emit(mu, prev, mv);
-            prev = mu;
         }
         hs[J] = h;
+        return closes;
     }
-    // after element W-1: turn hs[] into suffix minima, shift the frame by one block
+    // after element W-1: turn hs[] into suffix minima (the frame then moves on by one block)
     __device__ __forceinline__ void close_block() {
         sp[W - 1] = W - 1;
 #pragma unroll
         for (int jj = W - 2; jj >= 1; jj--)
             suffix_step(hs[jj], sp[jj], wbase - (uint32_t)(W - jj), hs[jj + 1], sp[jj + 1]);
-        prev -= W;
     }
 };
 
-// NextMinimizer over one item; its codes start at shared offset sb; tabIn/tabOut = table offsets.
+#define B200SK_LD128(tab, o) lds_v2u64(sm, (tab) + lds_u8(sm, (o)) * 16u)
+
+// NextMinimizer (sketch.go:205-309) over one item; its codes start at shared offset sb.
 template <int W, class SinkT>
 __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t sb, uint32_t nstep, int k,
                                                    uint32_t w_runtime, uint32_t tabIn, uint32_t tabOut,
                                                    SinkT &sink) {
-#define B200SK_IN(o) lds_v2u64(sm, tabIn + lds_u8(sm, (o)) * 16u)
-#define B200SK_OUT(o) lds_v2u64(sm, tabOut + lds_u8(sm, (o)) * 16u)
     Roll h;
     h.f = 0; h.r = 0;
-    for (int j = 0; j < k - 1; j++) h.fold(B200SK_IN(sb + j));
+    for (int j = 0; j < k - 1; j++) h.fold(B200SK_LD128(tabIn, sb + j));
     WinReg<W> wm;
     wm.init(w_runtime);
-    uint32_t pin = sb + (uint32_t)k - 1; // next incoming code
-    uint32_t pout = sb - 1;              // next outgoing code is pout + 1 ... (block 0 starts one step late)
-    // block 0: the first k-mer has no outgoing base
-    h.fold(B200SK_IN(pin));
-    wm.push(0, true, h.canonical(), sink);
+    uint32_t prev = W - 1; // frame-relative position of the previous window's minimum (none yet)
+    uint32_t pin = sb + (uint32_t)k - 1; // incoming code of step 0
+    uint32_t pout = sb - 1;              // outgoing code of step j is pout + j (step 0 has none)
+    uint64_t mv;
+    uint32_t mu;
+#define B200SK_MIN_STEP(J, FIRST)                                          \
+    if (wm.push(J, FIRST, h.canonical(), mv, mu)) {                        \
+        sink.emit_if(mu != prev, mv, mu - prev); /* sketch.go:297-307 */   \
+        prev = mu;                                                         \
+    }
+    h.fold(B200SK_LD128(tabIn, pin)); // the first k-mer has no outgoing base
+    B200SK_MIN_STEP(0, true)
 #pragma unroll
     for (int j = 1; j < W; j++) {
-        h.roll(B200SK_IN(pin + j), B200SK_OUT(pout + j));
-        wm.push(j, true, h.canonical(), sink);
+        h.roll(B200SK_LD128(tabIn, pin + j), B200SK_LD128(tabOut, pout + j));
+        B200SK_MIN_STEP(j, true)
     }
     wm.close_block();
+    prev -= W;
     pin += W; pout += W;
     uint32_t u0 = W;
-    // full blocks
-    while (u0 + W <= nstep) {
+    while (u0 + W <= nstep) { // full blocks
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            h.roll(B200SK_IN(pin + j), B200SK_OUT(pout + j));
-            wm.push(j, false, h.canonical(), sink);
+            h.roll(B200SK_LD128(tabIn, pin + j), B200SK_LD128(tabOut, pout + j));
+            B200SK_MIN_STEP(j, false)
         }
         wm.close_block();
+        prev -= W;
         pin += W; pout += W;
         u0 += W;
     }
-    // tail: fewer than W elements left
+    const uint32_t rem = nstep - u0; // tail: fewer than W elements left
+#pragma unroll
+    for (int j = 0; j < W - 1; j++) {
+        if ((uint32_t)j >= rem) break;
+        h.roll(B200SK_LD128(tabIn, pin + j), B200SK_LD128(tabOut, pout + j));
+        B200SK_MIN_STEP(j, false)
+    }
+#undef B200SK_MIN_STEP
+}
+
+// NextSyncmer (sketch.go:312-477, bounded closed syncmers, s < k) over one item.  W = 2(k-s): the window of
+// s-mer hashes.  For the window starting at idx the leftmost minimum s-mer m anchors k-mer b = m if
+// m - idx < k-s, else m - (k-s) (sketch.go:414-420); a k-mer is emitted when b changes and b <= end.
+// The last k-s k-mer hashes wait in a shared-memory ring (slot = position mod (k-s)).
+// tabs: offsets of tInS {A, rolB_{s-1}}, tOutS {rolA_s, rorB_1}, tOutK {rolA_k, rorB_1} (16 B entries) and
+// tInK {rolB_{k-1}} (8 B entries).  lim0 = end - q0 (stream index of the last emittable k-mer).
+template <int W, class SinkT>
+__device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint32_t nstep, int s,
+                                                 uint32_t w_runtime, uint32_t tInS, uint32_t tOutS, uint32_t tInK,
+                                                 uint32_t tOutK, uint32_t kring, int32_t lim0, uint32_t halo,
+                                                 SinkT &sink) {
+    constexpr int D = W / 2;
+    Roll hs_, hk_; // s-mer and k-mer hashers
+    hs_.f = hs_.r = hk_.f = hk_.r = 0;
+    for (int j = 0; j < s - 1; j++) {
+        const uint32_t c = lds_u8(sm, sb + j);
+        const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);
+        hs_.fold(e);
+        hk_.fold(make_ulonglong2(e.x, *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u)));
+    }
+    WinReg<W> wm;
+    wm.init(w_runtime);
+    uint32_t prevb = W - 1; // frame-relative position of the previous window's k-mer (none yet: stream -1)
+    int32_t lim = lim0 + W;       // frame-relative version of lim0 (frame starts at -W in block 0)
+    uint32_t pin = sb + (uint32_t)s - 1; // incoming code of step 0
+    uint32_t pos = sb - 1;               // s-mer outgoing code of step j is pos + j
+    uint32_t pok = sb - 1 - D;           // k-mer outgoing code of step j is pok + j (steps <= D have none)
+    uint64_t mv;
+    uint32_t mu;
+#define B200SK_SYNC_STEP(J, FIRST)                                                                         \
+    {                                                                                                      \
+        const uint32_t c = lds_u8(sm, pin + (J));                                                          \
+        const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);                                                \
+        const uint64_t ek = *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u);                       \
+        if ((FIRST) && (J) == 0) hs_.fold(e); else hs_.roll(e, B200SK_LD128(tOutS, pos + (J)));           \
+        if ((FIRST) && (J) <= D) hk_.fold(make_ulonglong2(e.x, ek));                                       \
+        else hk_.roll(make_ulonglong2(e.x, ek), B200SK_LD128(tOutK, pok + (J)));                           \
+        *reinterpret_cast<uint64_t *>(sm + kring + ((J) % D) * 256u) = hk_.canonical(); /* k-mer (J-D) */  \
+        if (wm.push(J, FIRST, hs_.canonical(), mv, mu)) {                                                  \
+            const uint32_t off = mu - (uint32_t)((J) + 1);        /* m - idx */                            \
+            const uint32_t b = off < (uint32_t)D ? mu : mu - (uint32_t)D;                                  \
+            const uint64_t kv = *reinterpret_cast<const uint64_t *>(sm + kring + (mu % (uint32_t)D) * 256u); \
+            uint32_t ok = (b != prevb) & ((int32_t)b <= lim);                                              \
+            if ((FIRST) && (J) == W - 1) ok |= halo; /* a non-first chunk's seeding window: always staged, dropped later */ \
+            sink.emit_if(ok, kv, b - prevb);                                                               \
+            prevb = b;                                                                                     \
+        }                                                                                                  \
+    }
+#pragma unroll
+    for (int j = 0; j < W; j++) B200SK_SYNC_STEP(j, true)
+    wm.close_block();
+    prevb -= W; lim -= W;
+    pin += W; pos += W; pok += W;
+    uint32_t u0 = W;
+    while (u0 + W <= nstep) {
+#pragma unroll
+        for (int j = 0; j < W; j++) B200SK_SYNC_STEP(j, false)
+        wm.close_block();
+        prevb -= W; lim -= W;
+        pin += W; pos += W; pok += W;
+        u0 += W;
+    }
     const uint32_t rem = nstep - u0;
 #pragma unroll
     for (int j = 0; j < W - 1; j++) {
         if ((uint32_t)j >= rem) break;
-        h.roll(B200SK_IN(pin + j), B200SK_OUT(pout + j));
-        wm.push(j, false, h.canonical(), sink);
+        B200SK_SYNC_STEP(j, false)
     }
-#undef B200SK_IN
-#undef B200SK_OUT
+#undef B200SK_SYNC_STEP
 }
 
-// ------------------------------------------------------------------ kernel
-template <int W>
-__global__ void __launch_bounds__(128, 4) k_minimizer_reg(const KArgs a) {
+// ------------------------------------------------------------------ kernel: one tile per WARP
+// A tile is 32 consecutive items; every warp runs its own ticket -> TMA -> walk -> look-back -> ordered
+// copy loop with no block-wide barrier, so warps drift freely and cover each other's latencies.
+// Shared memory: tables at 0; warp w owns [sm_tile + w*stride, +stride):
+//   +0 mbarrier, +16 tile bytes, +sm_ring k-mer ring (syncmer), +sm_listv values, +sm_listp position deltas.
+template <int MODE, int W>
+__global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, T = blockDim.x;
-    // [0,1K) in-table, [1K,2K) out-table (64 codes x 16 B), then TileCtl, then tile / lists
-    ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem);
-    ulonglong2 *tOut = tIn + 64;
-    TileCtl *ctl = reinterpret_cast<TileCtl *>(smem + 2048);
-    uint8_t *tilebuf = smem + a.sm_tile;
-    uint64_t *listv = reinterpret_cast<uint64_t *>(smem + a.sm_listv);
-    uint8_t *listp = smem + a.sm_listp;
-    for (uint32_t c = tid; c < 64; c += T) {
-        const uint32_t b = byte_of_code(c);
-        const uint64_t f = fwd_seed(b), r = rev_seed(b);
-        tIn[c] = make_ulonglong2(f, rol64(r, (unsigned)(a.k - 1)));
-        tOut[c] = make_ulonglong2(rol64(f, (unsigned)a.k), ror64(r, 1));
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    constexpr bool SYNC = MODE == B200SK_MODE_SYNCMER;
+    constexpr int D = W / 2;
+    // tables (64 codes): [0,1K) in {A, rolB_{h-1}}, [1K,2K) out {rolA_h, rorB_1} for the streamed hash
+    // (h = k for minimizers, s for syncmers); syncmer adds [2K,3K) k-mer out table, [3K,3.5K) rolB_{k-1}
+    const int hk = SYNC ? a.s : a.k;
+    {
+        ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 64, *tOutK = tIn + 128;
+        uint64_t *tInK = reinterpret_cast<uint64_t *>(smem + 3072);
+        for (uint32_t c = tid; c < 64; c += blockDim.x) {
+            const uint32_t b = byte_of_code(c);
+            const uint64_t f = fwd_seed(b), r = rev_seed(b);
+            tIn[c] = make_ulonglong2(f, rol64(r, (unsigned)(hk - 1)));
+            tOut[c] = make_ulonglong2(rol64(f, (unsigned)hk), ror64(r, 1));
+            if (SYNC) {
+                tOutK[c] = make_ulonglong2(rol64(f, (unsigned)a.k), ror64(r, 1));
+                tInK[c] = rol64(r, (unsigned)(a.k - 1));
+            }
+        }
     }
-    if (tid == 0) {
-        mbar_init(&ctl->mbar, 1);
+    const uint32_t region = a.sm_tile + wid * a.sm_ring_bytes;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
+    uint8_t *tilebuf = smem + region + 16;
+    const uint32_t s_tile = region + 16;
+    const uint32_t s_kring = region + a.sm_ring + lane * 8u;
+    uint64_t *listv = reinterpret_cast<uint64_t *>(smem + region + a.sm_listv);
+    uint8_t *listp = smem + region + a.sm_listp;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
         fence_mbar_init();
     }
-    __syncthreads();
-    const uint32_t s_tIn = 0, s_tOut = 1024, s_tile = a.sm_tile;
-    const uint32_t s_lv = a.sm_listv + tid * 8u, s_lp = a.sm_listp + tid;
+    __syncthreads(); // tables + barriers ready; the only block-wide barrier
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
     uint32_t parity = 0;
     for (;;) {
-        if (tid == 0) ctl->tile = atomicAdd(a.ticket, 1ULL);
-        __syncthreads();
-        const uint64_t tile = ctl->tile;
-        const uint64_t item0 = tile * T;
+        uint64_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.ticket, 1ULL);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        const uint64_t item0 = tile * 32ull;
         if (item0 >= n_items) break;
-        const uint32_t nvalid = (uint32_t)min((uint64_t)T, n_items - item0);
+        const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_items - item0);
         Item it;
-        item_geometry<B200SK_MODE_MINIMIZER>(a, item0 + tid, n_items, it);
-        if (tid == 0) { ctl->lo = it.gb0; ctl->any_overflow = 0; }
-        if (tid == nvalid - 1) ctl->hi = it.gb0 + it.nb;
-        __syncthreads();
-        const uint64_t lo_al = ctl->lo & ~15ULL;
-        const uint64_t span = ctl->hi > lo_al ? ctl->hi - lo_al : 0;
+        item_geometry<MODE>(a, item0 + lane, n_items, it);
+        const uint64_t lo = __shfl_sync(0xffffffffu, it.gb0, 0);
+        const uint64_t hi = __shfl_sync(0xffffffffu, it.gb0 + it.nb, (int)nvalid - 1);
+        const uint64_t lo_al = lo & ~15ULL;
+        const uint64_t span = hi > lo_al ? hi - lo_al : 0;
         const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
         const bool span_ok = bytes <= a.sm_tile_bytes;
-        if (tid == 0 && bytes && span_ok) {
+        if (lane == 0 && bytes && span_ok) {
             fence_proxy_async(); // the previous tile's generic-proxy writes to this buffer precede the async write
-            mbar_expect_tx(&ctl->mbar, bytes);
-            tma_load_1d(tilebuf, a.bases + lo_al, bytes, &ctl->mbar);
+            mbar_expect_tx(mbar, bytes);
+            tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
         }
-        if (!span_ok && tid == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
+        if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
         if (it.valid && it.first_chunk && a.status) a.status[it.r] = it.status;
         if (bytes && span_ok) {
-            mbar_wait(&ctl->mbar, parity);
+            mbar_wait(mbar, parity);
             parity ^= 1u;
-            // ASCII -> codes, 16 bytes per thread per trip
-            for (uint32_t o = tid * 16u; o < bytes; o += T * 16u) {
+            // ASCII -> codes, 16 bytes per lane per trip
+            for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
                 uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
                 const uint32_t orr = v.x | v.y | v.z | v.w, andd = v.x & v.y & v.z & v.w;
                 if ((orr & 0x80808080u) == 0 && (andd & 0x40404040u) == 0x40404040u) {
@@ -292,57 +380,69 @@ __global__ void __launch_bounds__(128, 4) k_minimizer_reg(const KArgs a) {
                 *reinterpret_cast<uint4 *>(tilebuf + o) = v;
             }
         }
-        __syncthreads();
+        __syncwarp();
         ListSink sink;
-        sink.av = smem_base + s_lv; sink.ap = smem_base + s_lp; sink.sv = T * 8u; sink.sp = T; sink.cap = a.lcap; sink.cnt = 0;
+        sink.av = smem_base + region + a.sm_listv + lane * 8u;
+        sink.ap = smem_base + region + a.sm_listp + lane;
+        sink.cap = a.lcap; sink.cnt = 0;
         const uint32_t sb = s_tile + (uint32_t)(it.gb0 - lo_al);
         const bool run = it.valid && it.nstep && span_ok;
-        if (run) minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, s_tIn, s_tOut, sink);
+        const int32_t lim0 = (int32_t)(it.end - it.q0);
+        const uint32_t halo = it.q0 != it.p0 ? 1u : 0u;
+        if (run) {
+            if (SYNC)
+                syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
+                                    s_kring, lim0, halo, sink);
+            else
+                minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, sink);
+        }
+        __syncwarp();
         // a non-first chunk walks one window more (the one before its first own window) to seed the
         // de-duplication; that window always emits first and is dropped here
-        const uint32_t skip = (run && it.q0 != it.p0) ? 1u : 0u;
+        const uint32_t skip = (run && halo) ? 1u : 0u;
         const uint32_t cnt = sink.cnt - skip;
         const bool overflow = sink.cnt > a.lcap;
-        if (overflow) ctl->any_overflow = 1;
-        uint32_t total;
-        const uint32_t excl = block_excl_scan(cnt, ctl->warp_sums, &total);
-        if (tid < 32) {
-            const uint64_t b = lookback_exclusive(a.tile_state, tile, total);
-            if (tid == 0) ctl->base = b;
+        const bool any_overflow = __any_sync(0xffffffffu, overflow);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
         }
-        __syncthreads();
-        const uint64_t tb = ctl->base;
+        const uint32_t excl = inc - cnt;
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint64_t tb = lookback_exclusive(a.tile_state, tile, total);
         const uint64_t mine = tb + excl;
         if (it.valid && it.first_chunk) a.out_off[it.r] = a.out_base + mine;
         if (it.valid && it.last_item) a.out_off[a.n_reads] = a.out_base + mine + cnt;
         const bool fits = tb + total <= a.capacity;
-        if (!fits && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
+        if (!fits && lane == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
         if (fits && total) {
-            if (!ctl->any_overflow) {
+            if (!any_overflow) {
                 // ordered copy: scatter the staged lists into one contiguous buffer (the codes are dead
                 // now), then stream it out coalesced
-                const uint32_t OB = (a.sm_listv - a.sm_tile) / 12u;
+                const uint32_t OB = a.sm_tile_bytes / 12u;
                 uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
                 uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
                 for (uint32_t r0 = 0; r0 < total; r0 += OB) {
-                    __syncthreads();
                     uint32_t pos = it.q0 - 1u;
                     for (uint32_t j = 0; j < sink.cnt; j++) {
-                        pos += listp[j * T + tid];
+                        pos += listp[j * 32u + lane];
                         const uint32_t o = excl + j - skip - r0;
                         if (j >= skip && o < OB) { // unsigned compare also rejects entries before r0
-                            obv[o] = listv[j * T + tid];
+                            obv[o] = listv[j * 32u + lane];
                             obp[o] = pos;
                         }
                     }
-                    __syncthreads();
+                    __syncwarp();
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
-                    for (uint32_t i = tid; i < n; i += T) gv[i] = obv[i];
+                    for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
                     if (a.out_pos) {
                         uint32_t *gp = a.out_pos + tb + r0;
-                        for (uint32_t i = tid; i < n; i += T) gp[i] = obp[i];
+                        for (uint32_t i = lane; i < n; i += 32u) gp[i] = obp[i];
                     }
+                    __syncwarp();
                 }
             } else {
                 // rare (low-complexity reads): some item emitted more than its list holds.  Items that fit
@@ -351,9 +451,9 @@ __global__ void __launch_bounds__(128, 4) k_minimizer_reg(const KArgs a) {
                 if (!overflow) {
                     uint32_t pos = it.q0 - 1u;
                     for (uint32_t j = 0; j < sink.cnt; j++) {
-                        pos += listp[j * T + tid];
+                        pos += listp[j * 32u + lane];
                         if (j >= skip) {
-                            a.out_val[mine + j - skip] = listv[j * T + tid];
+                            a.out_val[mine + j - skip] = listv[j * 32u + lane];
                             if (a.out_pos) a.out_pos[mine + j - skip] = pos;
                         }
                     }
@@ -361,17 +461,22 @@ __global__ void __launch_bounds__(128, 4) k_minimizer_reg(const KArgs a) {
                     GlobalSink gs;
                     gs.gv = a.out_val + mine; gs.gp = a.out_pos ? a.out_pos + mine : nullptr;
                     gs.pos = it.q0 - 1u; gs.cnt = 0; gs.skip = skip;
-                    minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, s_tIn, s_tOut, gs);
+                    if (SYNC)
+                        syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
+                                            2048u, s_kring, lim0, halo, gs);
+                    else
+                        minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, gs);
                 }
+                __syncwarp();
             }
         }
-        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------ launch
-template <int W> static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
-    const void *fn = (const void *)k_minimizer_reg<W>;
+template <int MODE, int W>
+static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
+    const void *fn = (const void *)k_sparse_warp<MODE, W>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.sm_total);
     if (e != cudaSuccess) return e;
     if (occ) {
@@ -380,36 +485,60 @@ template <int W> static cudaError_t launch_w(const KArgs &a, int threads, int bl
         *occ = nb < 1 ? 1 : nb;
         return e;
     }
-    k_minimizer_reg<W><<<blocks, threads, a.sm_total, st>>>(a);
+    k_sparse_warp<MODE, W><<<blocks, threads, a.sm_total, st>>>(a);
     return cudaGetLastError();
 }
 
 // Window sizes with a register-resident instantiation.  B200SK_FAST_BUILD (development) keeps a handful.
 #ifdef B200SK_FAST_BUILD
 #define B200SK_WLIST B200SK_W(3) B200SK_W(5) B200SK_W(11) B200SK_W(15) B200SK_W(20)
+#define B200SK_DLIST B200SK_W(2) B200SK_W(10) B200SK_W(20)
 #else
 #define B200SK_WLIST                                                                                         \
     B200SK_W(2) B200SK_W(3) B200SK_W(4) B200SK_W(5) B200SK_W(6) B200SK_W(7) B200SK_W(8) B200SK_W(9)          \
     B200SK_W(10) B200SK_W(11) B200SK_W(12) B200SK_W(13) B200SK_W(14) B200SK_W(15) B200SK_W(16) B200SK_W(17)  \
     B200SK_W(18) B200SK_W(19) B200SK_W(20) B200SK_W(21) B200SK_W(22) B200SK_W(23) B200SK_W(24)
+// syncmer windows 2(k-s): even sizes
+#define B200SK_DLIST                                                                                         \
+    B200SK_W(2) B200SK_W(4) B200SK_W(6) B200SK_W(8) B200SK_W(10) B200SK_W(12) B200SK_W(14) B200SK_W(16)      \
+    B200SK_W(18) B200SK_W(20) B200SK_W(22) B200SK_W(24)
 #endif
 // occ != nullptr: only report the occupancy
-cudaError_t launch_minimizer_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
-    switch (a.w) {
-#define B200SK_W(W) case W: return launch_w<W>(a, threads, blocks, st, occ);
-        B200SK_WLIST
+cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
+    if (a.mode == B200SK_MODE_MINIMIZER) {
+        switch (a.w) {
+#define B200SK_W(W) case W: return launch_w<B200SK_MODE_MINIMIZER, W>(a, threads, blocks, st, occ);
+            B200SK_WLIST
+#undef B200SK_W
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    switch (2 * (a.k - a.s)) {
+#define B200SK_W(W) case W: return launch_w<B200SK_MODE_SYNCMER, W>(a, threads, blocks, st, occ);
+        B200SK_DLIST
 #undef B200SK_W
     default: return cudaErrorInvalidValue;
     }
 }
 
-bool minimizer_reg_supported(int w) {
-    switch (w) {
+bool sparse_reg_supported(int mode, int k, int w, int s) {
+    if (mode == B200SK_MODE_MINIMIZER) {
+        switch (w) {
 #define B200SK_W(W) case W: return true;
-        B200SK_WLIST
+            B200SK_WLIST
 #undef B200SK_W
-    default: return false;
+        default: return false;
+        }
     }
+    if (mode == B200SK_MODE_SYNCMER) {
+        switch (2 * (k - s)) {
+#define B200SK_W(W) case W: return true;
+            B200SK_DLIST
+#undef B200SK_W
+        default: return false;
+        }
+    }
+    return false;
 }
 
 } // namespace b200sk

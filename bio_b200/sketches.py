@@ -97,7 +97,8 @@ def default_context():
     return _ctx
 
 
-def _run_one(s, **kw):
+def _run_one(seq_, **kw):
+    s = seq_
     p = cabi.make_params(alphabet=_ALPHA.get(s.Alphabet, cabi.ALPHABET_DNA_REDUNDANT), **kw)
     rc = cabi.lib().b200sk_check_params(__import__("ctypes").byref(p))
     if rc != 0:
