@@ -249,7 +249,7 @@ def run_ours(args, rank, world, local_rank):
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                "kernel": "k_minimizer_reg<W=11>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
+                "kernel": "k_sparse_warp<MINIMIZER,W=11>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
                 "bytes_per_base": alg / nb, "peak_source": peak_src,
                 "kernel_share_of_step": kern_ms / ms_step}
     if traffic:
