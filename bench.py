@@ -247,6 +247,8 @@ def run_ours(args, rank, world, local_rank):
     alg = algorithmic_bytes(n, nb, n_out)
     achieved = alg / (kern_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
+    if traffic and int(traffic.get("reads_per_launch", -1)) != n:
+        traffic = None  # the committed capture is for another launch size
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                 "kernel": "k_sparse_warp<MINIMIZER,W=11>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,

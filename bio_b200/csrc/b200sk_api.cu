@@ -89,8 +89,9 @@ struct Plan {
              sm_total = 0;
 };
 
-const uint32_t kChunk = 256;        // positions per chunk for long reads
-const uint32_t kChunkReg = 128;     // ... for the register-window kernels (shared memory per lane is the limit)
+const uint32_t kChunk = 252;        // positions per chunk for long reads: 63 words, so the 32 lanes of a warp (consecutive
+                                    // chunks of one read) start on 32 different shared-memory banks
+const uint32_t kChunkReg = 132;     // ... for the register-window kernels (shared memory per lane is the limit)
 const uint32_t kSingleMaxLen = 384; // reads up to this length are one item each
 const uint32_t kSmemCtl = 14336 + 256;
 const uint32_t kSmemLimit = 227 * 1024;
