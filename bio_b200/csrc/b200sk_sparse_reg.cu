@@ -176,6 +176,27 @@ template <int W> struct WinReg {
 
 #define B200SK_LD128(tab, o) lds_v2u64(sm, (tab) + lds_u8(sm, (o)) * 16u)
 
+// The codes of one block of W steps, fetched as aligned 32-bit words (a quarter of the shared-memory
+// wavefronts of per-step byte loads, and a quarter of the cost of any bank conflict between lanes), then
+// lined up with one PRMT per 4 codes and picked out with one PRMT per code.
+template <int W> struct CodeWords {
+    static constexpr int NWORD = (W + 3 + 3) / 4; // words that cover bytes phi .. phi+W-1 for phi <= 3
+    static constexpr int NG = (W + 3) / 4;        // groups of 4 consecutive codes
+    uint32_t x[NG];
+    __device__ __forceinline__ void load(const uint8_t *sm, uint32_t p) { // p: shared offset of step 0's code
+        const uint32_t a = p & ~3u;
+        const uint32_t sel = 0x3210u + 0x1111u * (p & 3u);
+        uint32_t w[NWORD + 1];
+#pragma unroll
+        for (int i = 0; i < NWORD; i++) w[i] = *reinterpret_cast<const uint32_t *>(sm + a + 4u * i);
+        w[NWORD] = 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) x[g] = __byte_perm(w[g], w[g + 1 < NWORD ? g + 1 : NWORD], sel);
+    }
+    __device__ __forceinline__ uint32_t code(const int j) const { return __byte_perm(x[j >> 2], 0u, 0x4440u | (j & 3)); }
+};
+#define B200SK_TAB(tab, c) lds_v2u64(sm, (tab) + (c) * 16u)
+
 // NextMinimizer (sketch.go:205-309) over one item; its codes start at shared offset sb.
 template <int W, class SinkT>
 __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t sb, uint32_t nstep, int k,
@@ -191,16 +212,19 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
     uint32_t pout = sb - 1;              // outgoing code of step j is pout + j (step 0 has none)
     uint64_t mv;
     uint32_t mu;
+    CodeWords<W> cin, cout;
 #define B200SK_MIN_STEP(J, FIRST)                                          \
     if (wm.push(J, FIRST, h.canonical(), mv, mu)) {                        \
         sink.emit_if(mu != prev, mv, mu - prev); /* sketch.go:297-307 */   \
         prev = mu;                                                         \
     }
-    h.fold(B200SK_LD128(tabIn, pin)); // the first k-mer has no outgoing base
+    cin.load(sm, pin);
+    cout.load(sm, pout);
+    h.fold(B200SK_TAB(tabIn, cin.code(0))); // the first k-mer has no outgoing base
     B200SK_MIN_STEP(0, true)
 #pragma unroll
     for (int j = 1; j < W; j++) {
-        h.roll(B200SK_LD128(tabIn, pin + j), B200SK_LD128(tabOut, pout + j));
+        h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
         B200SK_MIN_STEP(j, true)
     }
     wm.close_block();
@@ -208,9 +232,11 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
     pin += W; pout += W;
     uint32_t u0 = W;
     while (u0 + W <= nstep) { // full blocks
+        cin.load(sm, pin);
+        cout.load(sm, pout);
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            h.roll(B200SK_LD128(tabIn, pin + j), B200SK_LD128(tabOut, pout + j));
+            h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
             B200SK_MIN_STEP(j, false)
         }
         wm.close_block();
@@ -219,10 +245,12 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
         u0 += W;
     }
     const uint32_t rem = nstep - u0; // tail: fewer than W elements left
+    cin.load(sm, pin);
+    cout.load(sm, pout);
 #pragma unroll
     for (int j = 0; j < W - 1; j++) {
         if ((uint32_t)j >= rem) break;
-        h.roll(B200SK_LD128(tabIn, pin + j), B200SK_LD128(tabOut, pout + j));
+        h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
         B200SK_MIN_STEP(j, false)
     }
 #undef B200SK_MIN_STEP

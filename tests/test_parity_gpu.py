@@ -275,3 +275,45 @@ def test_host_pipeline_many_subbatches(gpu_ctx, monkeypatch):
     ref = oracle.run_batch(b, o[100:], oracle.MODE_MINIMIZER, k=21, w=11, threads=4)
     assert np.array_equal(res["val"], ref["val"]) and np.array_equal(res["pos"], ref["pos"])
     assert np.array_equal(res["off"], ref["off"])
+
+
+@pytest.mark.parametrize("w", list(range(1, 27)) + [33, 40])
+def test_every_minimizer_window_size(gpu_ctx, w):
+    """w = 2..24 run the register-window kernel (one template instantiation each), w = 1 the dense kernel,
+    larger w the generic shared-memory-ring kernel."""
+    lens = np.concatenate([np.full(300, 150), np.array([0, 19, 20 + w - 1, 20 + w, 400, 1500, 37, 251, 276, 277])])
+    b, o = synth.ragged_reads(lens, 100 + w, alphabet=b"ACGTACGTACGTN")
+    res, ref = run_both(gpu_ctx, cabi.MODE_MINIMIZER, b, o, k=21, w=w)
+    assert_same(res, ref, f"w={w}")
+    res, ref = run_both(gpu_ctx, cabi.MODE_MINIMIZER, b[: 300 * 150], o[:301], hint=150, k=21, w=w)
+    assert_same(res, ref, f"w={w} hint")
+
+
+@pytest.mark.parametrize("d", list(range(0, 15)))
+def test_every_syncmer_window_size(gpu_ctx, d):
+    """k-s = 1..12 run the register-window kernel, 0 the dense kernel, larger the generic kernel."""
+    k = 24
+    s = k - d
+    lens = np.concatenate([np.full(300, 150), np.array([0, 2 * k - s - 2, 2 * k - s - 1, 2 * k - s, 400, 1500, 37, 251])])
+    b, o = synth.ragged_reads(lens, 200 + d, alphabet=b"ACGTACGTACGTN")
+    res, ref = run_both(gpu_ctx, cabi.MODE_SYNCMER, b, o, k=k, s=s)
+    assert_same(res, ref, f"k-s={d}")
+    res, ref = run_both(gpu_ctx, cabi.MODE_SYNCMER, b[: 300 * 150], o[:301], hint=150, k=k, s=s)
+    assert_same(res, ref, f"k-s={d} hint")
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 31, 32, 33, 63, 64, 65, 100])
+def test_kmer_sizes(gpu_ctx, k):
+    """Small and large k, including k >= 64 where the rotations wrap (unverified against the Go module;
+    GPU == oracle)."""
+    b, o = synth.ragged_reads([150] * 200 + [0, k - 1 if k > 1 else 0, k, k + 1, 700], 300 + k)
+    res, ref = run_both(gpu_ctx, cabi.MODE_NTHASH, b, o, k=k)
+    assert_same(res, ref, f"nthash k={k}")
+    res, ref = run_both(gpu_ctx, cabi.MODE_MINIMIZER, b, o, k=k, w=5)
+    assert_same(res, ref, f"minimizer k={k}")
+    if k <= 32:
+        res, ref = run_both(gpu_ctx, cabi.MODE_KMER, b, o, k=k, canonical=bool(k & 1))
+        assert_same(res, ref, f"kmer k={k}")
+    if k >= 3:
+        res, ref = run_both(gpu_ctx, cabi.MODE_SYNCMER, b, o, k=k, s=k - 2)
+        assert_same(res, ref, f"syncmer k={k}")
