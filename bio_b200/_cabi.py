@@ -31,7 +31,7 @@ ERR_CAPACITY = -103
 ERR_BAD_ARG = -104
 ERR_NOMEM = -105
 
-MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN = range(5)
+MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN, MODE_PROTEIN_MINIMIZER = range(6)
 ALPHABET_DNA_REDUNDANT, ALPHABET_DNA, ALPHABET_RNA_REDUNDANT, ALPHABET_RNA, ALPHABET_UNLIMIT, ALPHABET_PROTEIN = range(6)
 
 # every symbol include/b200sketch.h declares (tests check the .so exports all of them)

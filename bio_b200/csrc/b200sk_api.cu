@@ -26,6 +26,10 @@ cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint
                                  cudaStream_t st);
 cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
 bool build_codon_aux(int id, uint8_t *aux);
+cudaError_t launch_scan_geom(const uint64_t *off, uint64_t n_reads, const ReadGeom &g, uint64_t *out,
+                             uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st);
+cudaError_t launch_translate(const uint8_t *bases, const uint64_t *off, const uint64_t *aa_off, uint64_t n_reads,
+                             int frame, const uint8_t *aux, uint8_t *aa, cudaStream_t st);
 cudaError_t launch_circularize(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, int k,
                                uint8_t *bases2, uint64_t *off2, uint64_t *tile_state,
                                unsigned long long *ticket, cudaStream_t st);
@@ -110,7 +114,7 @@ struct b200sk_ctx {
     DevBuf scan_state; // item scan look-back words
     DevBuf item_first;
     DevBuf circ_bases, circ_off;
-    DevBuf ill, aux;
+    DevBuf ill, aux, aa_bases, aa_off;
     int aux_table = -1;
     std::vector<uint8_t> aux_host;
     // host path device buffers
@@ -142,11 +146,13 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     const int mode = p.mode;
     const int k = p.k, w = p.w, s = p.s;
     const int d = mode == B200SK_MODE_SYNCMER ? k - s : 0;
-    const uint32_t ww = mode == B200SK_MODE_MINIMIZER ? (uint32_t)w : mode == B200SK_MODE_SYNCMER ? 2u * d : 0u;
+    const uint32_t ww = (mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_PROTEIN_MINIMIZER) ? (uint32_t)w
+                        : mode == B200SK_MODE_SYNCMER ? 2u * d : 0u;
     uint64_t halo; // bases an item touches beyond its C positions
     double density;
     switch (mode) {
-    case B200SK_MODE_MINIMIZER: halo = (uint64_t)w + k - 1; density = 2.0 / (w + 1.0); break;
+    case B200SK_MODE_MINIMIZER:
+    case B200SK_MODE_PROTEIN_MINIMIZER: halo = (uint64_t)w + k - 1; density = 2.0 / (w + 1.0); break;
     case B200SK_MODE_SYNCMER: halo = 2ull * d + s - 1; density = 2.0 / (d + 1.0); break;
     case B200SK_MODE_PROTEIN: halo = (uint64_t)k - 1; density = 1.0; break;
     default: halo = (uint64_t)k - 1; density = 1.0; break;
@@ -170,7 +176,8 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         if (mode == B200SK_MODE_PROTEIN && p.alphabet != B200SK_ALPHABET_PROTEIN) pl.span_max *= 3; // codons
     }
     if (pl.span_max < 16) pl.span_max = 16;
-    const bool sparse = mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER;
+    const bool sparse = mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER ||
+                        mode == B200SK_MODE_PROTEIN_MINIMIZER;
     pl.lcap = 0;
     pl.dense = !sparse;
     if (pl.dense) {
@@ -275,7 +282,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     if (q.mode == B200SK_MODE_SYNCMER && q.s == q.k) { q.mode = B200SK_MODE_NTHASH; q.canonical = 1; }
     if (q.mode == B200SK_MODE_MINIMIZER && q.w == 1) { q.mode = B200SK_MODE_NTHASH; q.canonical = 1; }
     if (q.mode == B200SK_MODE_MINIMIZER || q.mode == B200SK_MODE_SYNCMER) q.canonical = 1;
-    if (q.mode == B200SK_MODE_PROTEIN) q.circular = 0; // the reference's protein iterator has no circular option
+    if (q.mode == B200SK_MODE_PROTEIN || q.mode == B200SK_MODE_PROTEIN_MINIMIZER) q.circular = 0; // no such option
 
     KArgs a;
     memset(&a, 0, sizeof(a));
@@ -290,7 +297,9 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         ctx->launches++;
         a.ill = (const uint32_t *)ctx->ill.p;
     }
-    if (q.mode == B200SK_MODE_PROTEIN && q.alphabet != B200SK_ALPHABET_PROTEIN) {
+    const bool translate = (q.mode == B200SK_MODE_PROTEIN || q.mode == B200SK_MODE_PROTEIN_MINIMIZER) &&
+                           q.alphabet != B200SK_ALPHABET_PROTEIN;
+    if (translate) {
         if (ctx->aux_table != q.codon_table) {
             ctx->aux_host.resize(4608);
             if (!build_codon_aux(q.codon_table, ctx->aux_host.data())) return B200SK_ERR_CODON_TABLE;
@@ -303,6 +312,35 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     } else if (q.mode == B200SK_MODE_PROTEIN) {
         CK(ctx->aux.reserve(4608));
         a.aux = (const uint8_t *)ctx->aux.p; // unused for amino-acid input, but the kernel copies the area
+    }
+    if (q.mode == B200SK_MODE_PROTEIN_MINIMIZER) {
+        // sketch-protein.go:84: translate the frame once (k_translate), then every window of w consecutive
+        // wyhash values over the amino acids.  Length checks keep looking at the record's own length.
+        a.off_orig = d_off;
+        if (translate) {
+            ReadGeom g;
+            memset(&g, 0, sizeof(g));
+            g.mode = 100; g.frame = q.frame; g.k = q.k;
+            const size_t sb2 = ((n_reads + 1023) / 1024 + 1) * 8;
+            CK(ctx->aa_off.reserve((n_reads + 1) * 8));
+            CK(ctx->aa_bases.reserve(n_bases / 3 + n_reads + 64));
+            CK(ctx->scan_state.reserve(sb2));
+            CK(cudaMemsetAsync(ctx->scan_state.p, 0, sb2, st));
+            CK(cudaMemsetAsync(meta + 4, 0, 8, st));
+            CK(launch_scan_geom(d_off, n_reads, g, (uint64_t *)ctx->aa_off.p, (uint64_t *)ctx->scan_state.p, meta + 4, st));
+            CK(launch_translate(d_bases, d_off, (const uint64_t *)ctx->aa_off.p, n_reads, q.frame,
+                                (const uint8_t *)ctx->aux.p, (uint8_t *)ctx->aa_bases.p, st));
+            ctx->launches += 2;
+            a.bases = (const uint8_t *)ctx->aa_bases.p;
+            a.off = (const uint64_t *)ctx->aa_off.p;
+            n_bases = n_bases / 3 + n_reads;
+        }
+        if (q.w == 1) { // every amino-acid k-mer (sketch-protein.go:95,120-124): the dense protein kernel
+            q.mode = B200SK_MODE_PROTEIN;
+            a.mode = B200SK_MODE_PROTEIN;
+            q.alphabet = B200SK_ALPHABET_PROTEIN;
+            a.alphabet = B200SK_ALPHABET_PROTEIN;
+        }
     }
 
     if (q.circular) {
@@ -322,6 +360,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     }
 
     uint64_t max_len = p.max_read_len;
+    if (p.mode == B200SK_MODE_PROTEIN_MINIMIZER && translate && max_len) max_len = max_len / 3 + 1;
     Plan pl;
     uint64_t n_items_host = n_reads;
     bool have_items_host = true;
@@ -451,6 +490,16 @@ int b200sk_check_params(const b200sk_params *p) {
         if (p->frame < -3 || p->frame > 3 || p->frame == 0) return B200SK_ERR_INVALID_FRAME; // seq.go:694
         return 0;
     }
+    case B200SK_MODE_PROTEIN_MINIMIZER: {
+        if (p->k < 1) return B200SK_ERR_INVALID_K;       // sketch-protein.go:63
+        if (p->w < 1) return B200SK_ERR_INVALID_W;       // sketch-protein.go:70
+        if (p->alphabet == B200SK_ALPHABET_PROTEIN) return 0;
+        if (p->alphabet == B200SK_ALPHABET_UNLIMIT) return B200SK_ERR_BAD_ARG;
+        uint8_t tmp[4608];
+        if (!build_codon_aux(p->codon_table, tmp)) return B200SK_ERR_CODON_TABLE;
+        if (p->frame < -3 || p->frame > 3 || p->frame == 0) return B200SK_ERR_INVALID_FRAME;
+        return 0;
+    }
     default:
         return B200SK_ERR_BAD_ARG;
     }
@@ -507,7 +556,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->circ_bases,
-                      &ctx->circ_off, &ctx->ill, &ctx->aux, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
+                      &ctx->circ_off, &ctx->ill, &ctx->aux, &ctx->aa_bases, &ctx->aa_off, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
                       &ctx->d_status, &ctx->d_bases2, &ctx->d_off2, &ctx->d_val2, &ctx->d_pos2, &ctx->d_ooff2,
                       &ctx->d_status2})
         b->release();
@@ -563,6 +612,9 @@ uint64_t b200sk_output_bound(const b200sk_params *p, uint64_t n_bases, uint64_t 
     case B200SK_MODE_KMER: return (p->canonical ? 1 : 2) * nb;
     case B200SK_MODE_NTHASH: return nb;
     case B200SK_MODE_PROTEIN: return nb / 3 + n_reads;
+    case B200SK_MODE_PROTEIN_MINIMIZER:
+        if (exact || p->w <= 1) return nb / 3 + n_reads;
+        return (uint64_t)((nb / 3 + n_reads) * (2.0 / (p->w + 1.0)) * 1.25) + n_reads + 1024;
     case B200SK_MODE_MINIMIZER:
         if (exact || p->w <= 1) return nb;
         return (uint64_t)(nb * (2.0 / (p->w + 1.0)) * 1.25) + n_reads + 1024;

@@ -10,6 +10,7 @@
 // then writes every lane's 128-byte run with coalesced stores.
 #include "../../include/b200sk_codon_data.h"
 #include "b200sk_tile.cuh"
+#include "b200sk_protein.cuh"
 
 namespace b200sk {
 
@@ -64,70 +65,44 @@ __global__ void k_first_illegal(const uint8_t *__restrict__ bases, const uint64_
     }
 }
 
-// ------------------------------------------------------------------ wyhash (zeebo/wyhash v0.0.1 Hash(b, seed))
-// Published wyhash v1 layout: 32-byte blocks, tail by len & 31, final mum(seed, len ^ p5).  The tail
-// reads 8 bytes as two 32-bit halves with the first half high.  Reference parity of this function is
-// unpinned (no reference test checks a protein hash value); it is bit-exact against oracle/.
-#define WYP0 0xa0761d6478bd642fULL
-#define WYP1 0xe7037ed1a0b428dbULL
-#define WYP2 0x8ebc6af09c88c6e3ULL
-#define WYP3 0x589965cc75374cc3ULL
-#define WYP4 0x1d8e4e27c47d124fULL
-#define WYP5 0xeb44accab455d165ULL
-__device__ __forceinline__ uint64_t wymum(uint64_t a, uint64_t b) { return __umul64hi(a, b) ^ (a * b); }
-
-struct ByteSrc { // little-endian reads of an unaligned byte string in shared memory
-    const uint8_t *p;
-    __device__ __forceinline__ uint64_t r8(uint32_t i) const { return p[i]; }
-    __device__ __forceinline__ uint64_t r16(uint32_t i) const { return r8(i) | (r8(i + 1) << 8); }
-    __device__ __forceinline__ uint64_t r32(uint32_t i) const { return r16(i) | (r16(i + 2) << 16); }
-    __device__ __forceinline__ uint64_t r64(uint32_t i) const { return r32(i) | (r32(i + 4) << 32); }
-    __device__ __forceinline__ uint64_t r64s(uint32_t i) const { return (r32(i) << 32) | r32(i + 4); }
-};
-
-__device__ __forceinline__ uint64_t wy_tail_word(const ByteSrc &s, uint32_t o, uint32_t n) { // n in 1..8
-    switch (n) {
-    case 1: return s.r8(o);
-    case 2: return s.r16(o);
-    case 3: return (s.r16(o) << 8) | s.r8(o + 2);
-    case 4: return s.r32(o);
-    case 5: return (s.r32(o) << 8) | s.r8(o + 4);
-    case 6: return (s.r32(o) << 16) | s.r16(o + 4);
-    case 7: return (s.r32(o) << 24) | (s.r16(o + 4) << 8) | s.r8(o + 6);
-    default: return s.r64s(o);
+// ------------------------------------------------------------------ translation of one frame of every read
+// seq.Seq.Translate(table, frame, trim=false, clean=false, allowUnknownCodon=true, markInitCodonAsM=false)
+// (sketch-protein.go:84, codon_tables.go:205-285): aa[aa_off[r] + t], one warp per read.
+__global__ void __launch_bounds__(256) k_translate(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
+                                                   const uint64_t *__restrict__ aa_off, uint64_t n_reads, int frame,
+                                                   const uint8_t *__restrict__ aux, uint8_t *aa) {
+    __shared__ uint8_t tab[4608];
+    for (uint32_t i = threadIdx.x; i < 4608; i += blockDim.x) tab[i] = aux[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint8_t *pl = tab + 4352;
+    for (uint64_t r = warp; r < n_reads; r += nwarps) {
+        const uint8_t *s = bases + off[r];
+        const uint64_t L = off[r + 1] - off[r];
+        const uint64_t o = aa_off[r], n = aa_off[r + 1] - o;
+        if (frame > 0) {
+            for (uint64_t t = lane; t < n; t += 32) {
+                const uint64_t i = (uint64_t)(frame - 1) + 3 * t;
+                aa[o + t] = (uint8_t)codon_aa(tab, s[i], s[i + 1], s[i + 2]);
+            }
+        } else {
+            for (uint64_t t = lane; t < n; t += 32) {
+                const uint64_t i = L - (uint64_t)(-frame) - 3 * t;
+                aa[o + t] = (uint8_t)codon_aa(tab, pl[s[i]], pl[s[i - 1]], pl[s[i - 2]]);
+            }
+        }
     }
 }
 
-__device__ __forceinline__ uint64_t wyhash_dev(const ByteSrc &s, uint32_t len, uint64_t seed) {
-    uint32_t o = 0;
-    for (uint32_t i = 0; i + 32 <= len; i += 32, o += 32)
-        seed = wymum(seed ^ WYP0, wymum(s.r64(o) ^ WYP1, s.r64(o + 8) ^ WYP2) ^
-                                      wymum(s.r64(o + 16) ^ WYP3, s.r64(o + 24) ^ WYP4));
-    seed ^= WYP0;
-    const uint32_t t = len & 31u;
-    if (t == 0) {
-    } else if (t <= 8) {
-        seed = wymum(seed, wy_tail_word(s, o, t) ^ WYP1);
-    } else if (t <= 16) {
-        seed = wymum(s.r64s(o) ^ seed, wy_tail_word(s, o + 8, t - 8) ^ WYP2);
-    } else if (t <= 24) {
-        seed = wymum(s.r64s(o) ^ seed, s.r64s(o + 8) ^ WYP2) ^ wymum(seed, wy_tail_word(s, o + 16, t - 16) ^ WYP3);
-    } else {
-        seed = wymum(s.r64s(o) ^ seed, s.r64s(o + 8) ^ WYP2) ^
-               wymum(s.r64s(o + 16) ^ seed, wy_tail_word(s, o + 24, t - 24) ^ WYP4);
-    }
-    return wymum(seed, (uint64_t)len ^ WYP5);
-}
-
-// ------------------------------------------------------------------ codon lookup
-// aux layout: [0,4096) matrix[i][j][k] over 4-bit IUPAC codes, [4096,4352) base2code (0xff = invalid),
-// [4352,4608) DNA pair letters.  CodonTable.Get: seq/codon_tables.go:152-170 with allowUnknownCodon=true.
-__device__ __forceinline__ uint32_t codon_aa(const uint8_t *tab, uint32_t b0, uint32_t b1, uint32_t b2) {
-    const uint32_t c0 = tab[4096 + b0], c1 = tab[4096 + b1], c2 = tab[4096 + b2];
-    if ((c0 | c1 | c2) & 0x80u) return 'X'; // invalid base, unknown codons allowed
-    if (b0 == '-' && b1 == '-' && b2 == '-') return '-';
-    const uint32_t aa = tab[(c0 << 8) | (c1 << 4) | c2];
-    return aa ? aa : 'X';
+cudaError_t launch_translate(const uint8_t *bases, const uint64_t *off, const uint64_t *aa_off, uint64_t n_reads,
+                             int frame, const uint8_t *aux, uint8_t *aa, cudaStream_t st) {
+    uint64_t cb = (n_reads + 7) / 8;
+    if (cb > 148 * 16) cb = 148 * 16;
+    if (cb == 0) cb = 1;
+    k_translate<<<(unsigned)cb, 256, 0, st>>>(bases, off, aa_off, n_reads, frame, aux, aa);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ staged, coalesced output

@@ -18,6 +18,7 @@
 //   NextMinimizer          sketches/sketch.go:205-309   (== leftmost window minimum, de-duplicated by position)
 //   NextSyncmer            sketches/sketch.go:312-477   (== bounded closed syncmer closed form)
 #include "b200sk_tile.cuh"
+#include "b200sk_protein.cuh"
 
 namespace b200sk {
 
@@ -258,6 +259,27 @@ __device__ __forceinline__ void minimizer_item(const uint8_t *sb, const Item &it
     }
 }
 
+// ProteinMinimizerSketch.Next (sketch-protein.go:106-210) over one item: sb = the item's AMINO ACIDS (the
+// frame was translated by k_translate); every window of w consecutive wyhash(k residues, seed 1) values.
+template <bool DIRECT>
+__device__ __forceinline__ void protein_minimizer_item(const uint8_t *sb, const Item &it, int k, int w, WinMin &wm,
+                                                       Sink<DIRECT> &sink) {
+    uint32_t prev = 0xffffffffu;
+    const uint32_t first_own = it.p0 - it.q0;
+    for (uint32_t u = 0; u < it.nstep; u++) {
+        ByteSrc src;
+        src.p = sb + u;
+        const uint64_t h = wyhash_dev(src, (uint32_t)k, 1ull); // sketch-protein.go:118
+        uint64_t mv;
+        uint32_t mu;
+        if (wm.push(h, u, mv, mu)) {
+            const uint32_t win = u + 1 - (uint32_t)w;
+            if (mu != prev && win >= first_own) sink.emit(mv, mu);
+            prev = mu;
+        }
+    }
+}
+
 // NextSyncmer over one item (bounded closed syncmers; s < k here, s == k is the dense path).
 template <bool DIRECT>
 __device__ __forceinline__ void syncmer_item(const uint8_t *sb, const Item &it, int k, int s,
@@ -324,8 +346,8 @@ __global__ void __launch_bounds__(128) k_sparse(const KArgs a) {
     uint64_t *listv = reinterpret_cast<uint64_t *>(smem + a.sm_listv);
     uint16_t *listp = reinterpret_cast<uint16_t *>(smem + a.sm_listp);
 
-    const int hk = MODE == B200SK_MODE_MINIMIZER ? a.k : a.s; // size of the streamed hash
-    const int ww = MODE == B200SK_MODE_MINIMIZER ? a.w : 2 * (a.k - a.s);
+    const int hk = MODE == B200SK_MODE_SYNCMER ? a.s : a.k; // size of the streamed hash
+    const int ww = MODE == B200SK_MODE_SYNCMER ? 2 * (a.k - a.s) : a.w;
     for (uint32_t b = tid; b < 256; b += T) {
         const uint64_t f = fwd_seed(b), r = rev_seed(b);
         tabIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(hk - 1)));
@@ -384,6 +406,8 @@ __global__ void __launch_bounds__(128) k_sparse(const KArgs a) {
             wm.init(ringv + tid, ringu + tid, T, ww);
             if (MODE == B200SK_MODE_MINIMIZER)
                 minimizer_item<false>(sb, it, a.k, a.w, tabIn, tabOut, wm, sink);
+            else if (MODE == B200SK_MODE_PROTEIN_MINIMIZER)
+                protein_minimizer_item<false>(sb, it, a.k, a.w, wm, sink);
             else
                 syncmer_item<false>(sb, it, a.k, a.s, tabIn, tabOut, tabInK, tabOutK, wm, kring + tid, T, sink);
         }
@@ -442,6 +466,8 @@ __global__ void __launch_bounds__(128) k_sparse(const KArgs a) {
                     const uint8_t *gb = a.bases + it.gb0;
                     if (MODE == B200SK_MODE_MINIMIZER)
                         minimizer_item<true>(gb, it, a.k, a.w, tabIn, tabOut, wm, ds);
+                    else if (MODE == B200SK_MODE_PROTEIN_MINIMIZER)
+                        protein_minimizer_item<true>(gb, it, a.k, a.w, wm, ds);
                     else
                         syncmer_item<true>(gb, it, a.k, a.s, tabIn, tabOut, tabInK, tabOutK, wm, kring + tid, T, ds);
                 }
@@ -468,6 +494,16 @@ cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *ti
     if (blocks == 0) blocks = 1;
     k_scan_reads<false><<<(unsigned)blocks, 256, 0, st>>>(a.off, a.off_orig, a.n_reads, a.geom(), a.C, 0, item_first,
                                                          nullptr, tile_state, ticket);
+    return cudaGetLastError();
+}
+
+// generic per-read count scan (used for the amino-acid offsets of a translated frame)
+cudaError_t launch_scan_geom(const uint64_t *off, uint64_t n_reads, const ReadGeom &g, uint64_t *out,
+                             uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st) {
+    uint64_t tiles = (n_reads + 1023) / 1024;
+    uint64_t blocks = tiles < 148 * 8 ? tiles : 148 * 8;
+    if (blocks == 0) blocks = 1;
+    k_scan_reads<true><<<(unsigned)blocks, 256, 0, st>>>(off, nullptr, n_reads, g, 1, 0, out, nullptr, tile_state, ticket);
     return cudaGetLastError();
 }
 
@@ -512,6 +548,10 @@ cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st
         if ((e = set_smem((const void *)k_sparse<B200SK_MODE_SYNCMER>, a.sm_total)) != cudaSuccess) return e;
         k_sparse<B200SK_MODE_SYNCMER><<<blocks, threads, a.sm_total, st>>>(a);
         break;
+    case B200SK_MODE_PROTEIN_MINIMIZER:
+        if ((e = set_smem((const void *)k_sparse<B200SK_MODE_PROTEIN_MINIMIZER>, a.sm_total)) != cudaSuccess) return e;
+        k_sparse<B200SK_MODE_PROTEIN_MINIMIZER><<<blocks, threads, a.sm_total, st>>>(a);
+        break;
     default:
         return cudaErrorInvalidValue;
     }
@@ -521,7 +561,8 @@ cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st
 int main_kernel_occupancy(const KArgs &a, int threads) {
     int nb = 0;
     const void *fn = a.mode == B200SK_MODE_MINIMIZER ? (const void *)k_sparse<B200SK_MODE_MINIMIZER>
-                                                     : (const void *)k_sparse<B200SK_MODE_SYNCMER>;
+                     : a.mode == B200SK_MODE_SYNCMER ? (const void *)k_sparse<B200SK_MODE_SYNCMER>
+                                                     : (const void *)k_sparse<B200SK_MODE_PROTEIN_MINIMIZER>;
     set_smem(fn, a.sm_total);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, a.sm_total) != cudaSuccess) return 1;
     return nb < 1 ? 1 : nb;

@@ -95,6 +95,18 @@ __host__ __device__ inline uint32_t read_positions(const ReadGeom &g, uint64_t r
         const uint32_t naa = g.protein_input ? (uint32_t)L : frame_aa_count(L, g.frame);
         return naa >= (uint32_t)k ? naa - (uint32_t)k + 1 : 0u;
     }
+    case B200SK_MODE_PROTEIN_MINIMIZER: {
+        // sketch-protein.go:66,73: both length checks look at the un-translated length; here L is the
+        // amino-acid length (the frame was translated by k_translate) and orig the record's length
+        if (orig < 3ull * (uint64_t)k || orig < 3ull * (uint64_t)k + (uint64_t)g.w - 1) {
+            *status = B200SK_ERR_SHORT_SEQ;
+            return 0;
+        }
+        const uint64_t nk = L >= (uint64_t)k ? L - (uint64_t)k + 1 : 0;
+        return nk >= (uint64_t)g.w ? (uint32_t)(nk - (uint64_t)g.w + 1) : 0u;
+    }
+    case 100: // internal: amino acids of the frame (k_translate's output length)
+        return frame_aa_count(L, g.frame);
     default: return 0;
     }
 }

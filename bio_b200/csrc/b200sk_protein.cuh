@@ -1,0 +1,75 @@
+// Protein pieces shared by the dense protein kernel and the protein-minimizer kernel:
+// wyhash (zeebo/wyhash v0.0.1) and the codon lookup of CodonTable.Get.
+#pragma once
+#include "b200sk_device.cuh"
+
+namespace b200sk {
+
+// ------------------------------------------------------------------ wyhash (zeebo/wyhash v0.0.1 Hash(b, seed))
+// Published wyhash v1 layout: 32-byte blocks, tail by len & 31, final mum(seed, len ^ p5).  The tail
+// reads 8 bytes as two 32-bit halves with the first half high.  Reference parity of this function is
+// unpinned (no reference test checks a protein hash value); it is bit-exact against oracle/.
+#define WYP0 0xa0761d6478bd642fULL
+#define WYP1 0xe7037ed1a0b428dbULL
+#define WYP2 0x8ebc6af09c88c6e3ULL
+#define WYP3 0x589965cc75374cc3ULL
+#define WYP4 0x1d8e4e27c47d124fULL
+#define WYP5 0xeb44accab455d165ULL
+__device__ __forceinline__ uint64_t wymum(uint64_t a, uint64_t b) { return __umul64hi(a, b) ^ (a * b); }
+
+struct ByteSrc { // little-endian reads of an unaligned byte string in shared memory
+    const uint8_t *p;
+    __device__ __forceinline__ uint64_t r8(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ uint64_t r16(uint32_t i) const { return r8(i) | (r8(i + 1) << 8); }
+    __device__ __forceinline__ uint64_t r32(uint32_t i) const { return r16(i) | (r16(i + 2) << 16); }
+    __device__ __forceinline__ uint64_t r64(uint32_t i) const { return r32(i) | (r32(i + 4) << 32); }
+    __device__ __forceinline__ uint64_t r64s(uint32_t i) const { return (r32(i) << 32) | r32(i + 4); }
+};
+
+__device__ __forceinline__ uint64_t wy_tail_word(const ByteSrc &s, uint32_t o, uint32_t n) { // n in 1..8
+    switch (n) {
+    case 1: return s.r8(o);
+    case 2: return s.r16(o);
+    case 3: return (s.r16(o) << 8) | s.r8(o + 2);
+    case 4: return s.r32(o);
+    case 5: return (s.r32(o) << 8) | s.r8(o + 4);
+    case 6: return (s.r32(o) << 16) | s.r16(o + 4);
+    case 7: return (s.r32(o) << 24) | (s.r16(o + 4) << 8) | s.r8(o + 6);
+    default: return s.r64s(o);
+    }
+}
+
+__device__ __forceinline__ uint64_t wyhash_dev(const ByteSrc &s, uint32_t len, uint64_t seed) {
+    uint32_t o = 0;
+    for (uint32_t i = 0; i + 32 <= len; i += 32, o += 32)
+        seed = wymum(seed ^ WYP0, wymum(s.r64(o) ^ WYP1, s.r64(o + 8) ^ WYP2) ^
+                                      wymum(s.r64(o + 16) ^ WYP3, s.r64(o + 24) ^ WYP4));
+    seed ^= WYP0;
+    const uint32_t t = len & 31u;
+    if (t == 0) {
+    } else if (t <= 8) {
+        seed = wymum(seed, wy_tail_word(s, o, t) ^ WYP1);
+    } else if (t <= 16) {
+        seed = wymum(s.r64s(o) ^ seed, wy_tail_word(s, o + 8, t - 8) ^ WYP2);
+    } else if (t <= 24) {
+        seed = wymum(s.r64s(o) ^ seed, s.r64s(o + 8) ^ WYP2) ^ wymum(seed, wy_tail_word(s, o + 16, t - 16) ^ WYP3);
+    } else {
+        seed = wymum(s.r64s(o) ^ seed, s.r64s(o + 8) ^ WYP2) ^
+               wymum(s.r64s(o + 16) ^ seed, wy_tail_word(s, o + 24, t - 24) ^ WYP4);
+    }
+    return wymum(seed, (uint64_t)len ^ WYP5);
+}
+
+// ------------------------------------------------------------------ codon lookup
+// aux layout: [0,4096) matrix[i][j][k] over 4-bit IUPAC codes, [4096,4352) base2code (0xff = invalid),
+// [4352,4608) DNA pair letters.  CodonTable.Get: seq/codon_tables.go:152-170 with allowUnknownCodon=true.
+__device__ __forceinline__ uint32_t codon_aa(const uint8_t *tab, uint32_t b0, uint32_t b1, uint32_t b2) {
+    const uint32_t c0 = tab[4096 + b0], c1 = tab[4096 + b1], c2 = tab[4096 + b2];
+    if ((c0 | c1 | c2) & 0x80u) return 'X'; // invalid base, unknown codons allowed
+    if (b0 == '-' && b1 == '-' && b2 == '-') return '-';
+    const uint32_t aa = tab[(c0 << 8) | (c1 << 4) | c2];
+    return aa ? aa : 'X';
+}
+
+
+} // namespace b200sk

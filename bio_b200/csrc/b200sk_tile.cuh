@@ -59,7 +59,7 @@ __device__ __forceinline__ void item_geometry(const KArgs &a, uint64_t item, uin
     it.p0 = p0;
     it.q0 = q0;
     it.gb0 = o0 + q0;
-    if (MODE == B200SK_MODE_MINIMIZER) {
+    if (MODE == B200SK_MODE_MINIMIZER || MODE == B200SK_MODE_PROTEIN_MINIMIZER) {
         it.nstep = p1 - q0 + (uint32_t)a.w - 1;
         it.nb = it.nstep + (uint32_t)a.k - 1;
     } else { // SYNCMER

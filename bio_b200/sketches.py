@@ -209,6 +209,20 @@ def NewProteinIterator(s, k, codonTable, frame):
     return ProteinIterator(val, pos, False)
 
 
+class ProteinMinimizerSketch(Sketch):
+    """sketches.ProteinMinimizerSketch (sketch-protein.go:32)."""
+
+
+def NewProteinMinimizerSketch(S, k, codonTable, frame, w):
+    """sketch-protein.go:62"""
+    if w > (1 << 31) - 1:
+        raise ErrInvalidW()
+    val, pos, st = _run_one(S, mode=cabi.MODE_PROTEIN_MINIMIZER, k=k, codon_table=codonTable, frame=frame, w=w)
+    if st:
+        _raise(st)
+    return ProteinMinimizerSketch(val, pos, True)
+
+
 # ---- the batch shape -------------------------------------------------------------------------------------
 class Batch:
     """Records of one fastx chunk packed into concatenated bases + offsets; one C-ABI call sketches them all.
@@ -248,6 +262,9 @@ class Batch:
 
     def ProteinIterator(self, k, codonTable, frame):
         return self._run(mode=cabi.MODE_PROTEIN, k=k, codon_table=codonTable, frame=frame)
+
+    def ProteinMinimizerSketch(self, k, codonTable, frame, w):
+        return self._run(mode=cabi.MODE_PROTEIN_MINIMIZER, k=k, codon_table=codonTable, frame=frame, w=w)
 
 
 class BatchResult:

@@ -203,6 +203,16 @@ func (b *Batch) ProteinIterator(k, codonTable, frame int) (*Result, error) {
 	return b.run(&p)
 }
 
+// ProteinMinimizerSketch == sketches.NewProteinMinimizerSketch (sketch-protein.go:62).
+func (b *Batch) ProteinMinimizerSketch(k, codonTable, frame, w int) (*Result, error) {
+	if w > (1<<31)-1 {
+		return nil, ErrInvalidW
+	}
+	p := C.b200sk_params{mode: C.B200SK_MODE_PROTEIN_MINIMIZER, k: C.int32_t(k), w: C.int32_t(w),
+		codon_table: C.int32_t(codonTable), frame: C.int32_t(frame)}
+	return b.run(&p)
+}
+
 func cbool(b bool) C.int32_t {
 	if b {
 		return 1

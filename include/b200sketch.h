@@ -56,6 +56,7 @@ extern "C" {
 #define B200SK_MODE_MINIMIZER 2 /* NewMinimizerSketch   sketches/sketch.go:85    + NextMinimizer :205 */
 #define B200SK_MODE_SYNCMER 3   /* NewSyncmerSketch     sketches/sketch.go:142   + NextSyncmer :312   */
 #define B200SK_MODE_PROTEIN 4   /* NewProteinIterator   sketches/iterator-protein.go:46 + Next :76   */
+#define B200SK_MODE_PROTEIN_MINIMIZER 5 /* NewProteinMinimizerSketch sketches/sketch-protein.go:62 + Next :106 (k, w, codon_table, frame) */
 
 /* seq.Alphabet of the records (only NextKmer's non-canonical second strand
  * depends on it: RevComInplace, sketches/iterator.go:719, seq/seq.go:350). */

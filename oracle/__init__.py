@@ -28,7 +28,7 @@ ERR_INVALID_CODON = -10
 SORT_STABLE = 0
 SORT_GO14 = 1
 
-MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN = range(5)
+MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN, MODE_PROTEIN_MINIMIZER = range(6)
 
 
 def build():
@@ -71,6 +71,9 @@ def lib():
         L.ora_wyhash.argtypes = [u8p, C.c_uint64, C.c_uint64]
         L.ora_protein_iterator.restype = C.c_int64
         L.ora_protein_iterator.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, u64p, ip]
+        L.ora_protein_minimizer.restype = C.c_int64
+        L.ora_protein_minimizer.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            u64p, i64p, ip, ip]
         L.ora_pair_lut.restype = None
         L.ora_pair_lut.argtypes = [C.c_int, u8p]
         L.ora_run_batch.restype = C.c_uint64
@@ -180,6 +183,18 @@ def protein_iterator(seq, k, table=1, frame=1):
     n = lib().ora_protein_iterator(_p(s, C.c_uint8), len(s), k, table, frame,
                                    _p(out, C.c_uint64), C.byref(err))
     return out[:n].copy(), err.value
+
+
+def protein_minimizer(seq, k, w, table=1, frame=1, protein_input=False, policy=SORT_STABLE):
+    """sketches.NewProteinMinimizerSketch + Next/Index loop -> (vals, idxs, err, first_window_tie)."""
+    s = _as_u8(seq)
+    cap = len(s) + 4
+    val = np.zeros(cap, dtype=np.uint64)
+    idx = np.zeros(cap, dtype=np.int64)
+    err, tie = C.c_int(0), C.c_int(0)
+    n = lib().ora_protein_minimizer(_p(s, C.c_uint8), len(s), k, table, frame, w, int(protein_input), policy,
+                                    _p(val, C.c_uint64), _p(idx, C.c_int64), C.byref(err), C.byref(tie))
+    return val[:n].copy(), idx[:n].copy(), err.value, bool(tie.value)
 
 
 def pair_lut(alphabet=0):

@@ -848,10 +848,67 @@ int64_t ora_protein_iterator(const uint8_t *seq, size_t len, int k, int table, i
 }
 
 /* ------------------------------------------------------------------ */
+/* NewProteinMinimizerSketch / Next (sketches/sketch-protein.go:62-210) */
+/* The same sorted-buffer state machine as NextMinimizer over the       */
+/* wyhash stream of the translated frame.  protein_input != 0: the      */
+/* sequence already is amino acids (Alphabet == Protein, :86-87).       */
+/* out_idx receives Index() (= mI, :213-215).                           */
+/* ------------------------------------------------------------------ */
+int64_t ora_protein_minimizer(const uint8_t *seq, size_t len, int k, int table, int frame, int w,
+                              int protein_input, int sort_policy, uint64_t *out_val, int64_t *out_idx,
+                              int *err, int *first_window_tie) {
+    *err = ORA_OK;
+    if (first_window_tie) *first_window_tie = 0;
+    if (k < 1) { *err = ORA_ERR_INVALID_K; return 0; }                          /* :63 */
+    if ((int64_t)len < (int64_t)k * 3) { *err = ORA_ERR_SHORT_SEQ; return 0; }   /* :66 */
+    if (w < 1) { *err = ORA_ERR_INVALID_W; return 0; }                          /* :70 */
+    if ((int64_t)len < (int64_t)k * 3 + w - 1) { *err = ORA_ERR_SHORT_SEQ; return 0; } /* :73 */
+    uint8_t *aa = (uint8_t *)malloc(len + 4);
+    int64_t na;
+    if (!protein_input) {
+        na = ora_translate(seq, len, table, frame, 0, 0, 1, aa, err);           /* :84 */
+        if (*err) { free(aa); return 0; }
+    } else {
+        memcpy(aa, seq, len);
+        na = (int64_t)len;
+    }
+    int64_t idx = 0, end0 = na - k;                                              /* :92-93 */
+    int r = w - 1;                                                               /* :97 */
+    int skip = (w == 1);                                                         /* :95 */
+    iv_t *buf = (iv_t *)malloc(((size_t)w + 2) * sizeof(iv_t));
+    int blen = 0;
+    int64_t pre_min_idx = -1, n = 0;
+    for (;;) {
+        if (idx > end0) break;                                                   /* :113 */
+        uint64_t code = ora_wyhash(aa + idx, (uint64_t)k, 1);                    /* :118 */
+        if (skip) { out_val[n] = code; out_idx[n] = idx; n++; idx++; continue; } /* :120-124 */
+        if (idx < r) { buf[blen].idx = idx; buf[blen].val = code; blen++; idx++; continue; } /* :127-132 */
+        if (idx == r) {                                                          /* :135-147 */
+            buf[blen].idx = idx; buf[blen].val = code; blen++;
+            if (first_window_tie && has_equal_values(buf, blen)) *first_window_tie = 1;
+            first_window_sort(buf, blen, sort_policy);
+            out_val[n] = buf[0].val; out_idx[n] = buf[0].idx; n++;
+            pre_min_idx = buf[0].idx;
+            idx++;
+            continue;
+        }
+        evict_idx(buf, r, idx - w);                                              /* :152-160 */
+        insert_sorted(buf, r, idx, code);                                        /* :163-197 */
+        if (buf[0].idx == pre_min_idx) { idx++; continue; }                      /* :199-203 */
+        out_val[n] = buf[0].val; out_idx[n] = buf[0].idx; n++;                   /* :205-209 */
+        pre_min_idx = buf[0].idx;
+        idx++;
+    }
+    free(buf); free(aa);
+    return n;
+}
+
+/* ------------------------------------------------------------------ */
 /* Batch drivers (concatenated reads + offsets), multi-threaded.        */
 /* These are what bench.py times as the CPU baseline: the reference's   */
 /* per-record pull loop, one thread per contiguous shard of reads.      */
-/* mode: 0 kmer, 1 nthash, 2 minimizer, 3 syncmer, 4 protein            */
+/* mode: 0 kmer, 1 nthash, 2 minimizer, 3 syncmer, 4 protein,           */
+/*       5 protein minimizer (alphabet 5 = amino-acid input)            */
 /* Pass 1 (out_val == NULL) only counts; pass 2 writes at out_off[r].   */
 /* ------------------------------------------------------------------ */
 typedef struct {
@@ -903,6 +960,8 @@ static void *ora_worker(void *arg) {
         case 2: n = ora_minimizer(s, len, p->k, p->w, p->circular, p->sort_policy, val, idx, &err, &tie); have_idx = 1; break;
         case 3: n = ora_syncmer(s, len, p->k, p->s, p->circular, p->sort_policy, val, idx, &err, &tie); have_idx = 1; break;
         case 4: n = ora_protein_iterator(s, len, p->k, p->codon_table, p->frame, val, &err); break;
+        case 5: n = ora_protein_minimizer(s, len, p->k, p->codon_table, p->frame, p->w, p->alphabet == 5,
+                                          p->sort_policy, val, idx, &err, &tie); have_idx = 1; break;
         default: err = ORA_ERR_INVALID_K;
         }
         ties += (uint64_t)tie;

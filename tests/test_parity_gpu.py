@@ -12,7 +12,7 @@ from bio_b200 import synth
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-OMODE = {cabi.MODE_KMER: oracle.MODE_KMER, cabi.MODE_NTHASH: oracle.MODE_NTHASH,
+OMODE = {cabi.MODE_PROTEIN_MINIMIZER: oracle.MODE_PROTEIN_MINIMIZER, cabi.MODE_KMER: oracle.MODE_KMER, cabi.MODE_NTHASH: oracle.MODE_NTHASH,
          cabi.MODE_MINIMIZER: oracle.MODE_MINIMIZER, cabi.MODE_SYNCMER: oracle.MODE_SYNCMER,
          cabi.MODE_PROTEIN: oracle.MODE_PROTEIN}
 
@@ -317,3 +317,35 @@ def test_kmer_sizes(gpu_ctx, k):
     if k >= 3:
         res, ref = run_both(gpu_ctx, cabi.MODE_SYNCMER, b, o, k=k, s=k - 2)
         assert_same(res, ref, f"syncmer k={k}")
+
+
+@pytest.mark.parametrize("frame", [1, 2, 3, -1, -2, -3])
+@pytest.mark.parametrize("k,w", [(10, 5), (11, 1), (5, 12)])
+def test_protein_minimizer(gpu_ctx, frame, k, w):
+    """ProteinMinimizerSketch (sketches/sketch-protein.go): SURVEY.md 8f row 2."""
+    lens = np.concatenate([np.full(200, 150), synth.ont_like_lengths(12, 3, mean=3000),
+                           [0, 3 * k - 1, 3 * k, 3 * k + w - 2, 3 * k + w - 1, 3 * k + w + 5, 3 * (k + w), 700]])
+    b, o = synth.ragged_reads(lens, 400 + k + w, alphabet=b"ACGTACGTACGTN")
+    res, ref = run_both(gpu_ctx, cabi.MODE_PROTEIN_MINIMIZER, b, o, k=k, w=w, frame=frame)
+    assert_same(res, ref, f"frame={frame} k={k} w={w}")
+    res, ref = run_both(gpu_ctx, cabi.MODE_PROTEIN_MINIMIZER, b[: 200 * 150], o[:201], hint=150, k=k, w=w, frame=frame)
+    assert_same(res, ref, f"hint frame={frame} k={k} w={w}")
+
+
+def test_protein_minimizer_amino_acid_input(gpu_ctx):
+    aa = b"ACDEFGHIKLMNPQRSTVWY*X"
+    lens = [0, 10, 29, 30, 34, 35, 60, 500, 2000] * 20
+    b, o = synth.ragged_reads(lens, 77, alphabet=aa)
+    p = cabi.make_params(cabi.MODE_PROTEIN_MINIMIZER, 10, w=5, alphabet=cabi.ALPHABET_PROTEIN)
+    res = gpu_ctx.run(p, b, o)
+    ref = oracle.run_batch(b, o, oracle.MODE_PROTEIN_MINIMIZER, k=10, w=5, alphabet=5, threads=4)
+    assert_same(res, ref)
+    p = cabi.make_params(cabi.MODE_PROTEIN, 10, alphabet=cabi.ALPHABET_PROTEIN)
+    res = gpu_ctx.run(p, b, o)
+    # amino-acid input through the oracle: hash every 10-mer of reads with at least 30 residues
+    vals = []
+    for i, L in enumerate(lens):
+        if L >= 30:
+            s = b[int(o[i]):int(o[i + 1])]
+            vals += [oracle.wyhash(s[j:j + 10], 1) for j in range(L - 10 + 1)]
+    assert [int(v) for v in res["val"]] == vals

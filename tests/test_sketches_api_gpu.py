@@ -171,3 +171,23 @@ def test_batch_replay_equals_single_calls():
                 break
             got.append((v, it.Index()))
         assert got == [(int(v), int(p)) for v, p in zip(rv, ri)]
+
+
+def test_TestProteinMinimizer():
+    # sketches/sketch-protein_test.go:29-58 (the reference asserts nothing; values from the oracle)
+    s = "AAGTTTGAATCATTCAACTATCTAGTTTTCAGAGAACAATGTTCTCTAAAGAATAGAAAAGAGTCATTGTGCGGTGATGATGGCGGGAAGGATCCACCTG"
+    sequence = sk.NewSeq(sk.DNA, s)
+    k, w = 10, 3
+    sketch = sk.NewProteinMinimizerSketch(sequence, k, 1, 1, w)
+    got = []
+    while True:
+        code, ok = sketch.Next()
+        if not ok:
+            break
+        got.append((code, sketch.Index()))
+    rv, ri, err, _ = oracle.protein_minimizer(s, k, w, 1, 1)
+    assert err == 0 and got == [(int(v), int(i)) for v, i in zip(rv, ri)] and len(got) > 0
+    with pytest.raises(sk.ErrInvalidW):
+        sk.NewProteinMinimizerSketch(sequence, k, 1, 1, 0)
+    with pytest.raises(sk.ErrShortSeq):
+        sk.NewProteinMinimizerSketch(sk.NewSeq(sk.DNA, s[:31]), k, 1, 1, w)
