@@ -24,6 +24,9 @@ ERR_INVALID_FRAME = -7
 ERR_CODON_TABLE = -8
 ERR_TRANSLATE_SHORT = -9
 ERR_INVALID_CODON = -10
+ERR_INVALID_M = -11
+ERR_INVALID_SCALE = -12
+ERR_K_TOO_LARGE = -13
 ERR_CUDA = -100
 ERR_NO_DEVICE = -101
 ERR_UNSUPPORTED = -102
@@ -31,7 +34,7 @@ ERR_CAPACITY = -103
 ERR_BAD_ARG = -104
 ERR_NOMEM = -105
 
-MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN, MODE_PROTEIN_MINIMIZER = range(6)
+MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN, MODE_PROTEIN_MINIMIZER, MODE_SIMHASH = range(7)
 ALPHABET_DNA_REDUNDANT, ALPHABET_DNA, ALPHABET_RNA_REDUNDANT, ALPHABET_RNA, ALPHABET_UNLIMIT, ALPHABET_PROTEIN = range(6)
 
 # every symbol include/b200sketch.h declares (tests check the .so exports all of them)
@@ -48,17 +51,18 @@ class Params(C.Structure):
         ("mode", C.c_int32), ("k", C.c_int32), ("w", C.c_int32), ("s", C.c_int32),
         ("canonical", C.c_int32), ("circular", C.c_int32), ("codon_table", C.c_int32),
         ("frame", C.c_int32), ("alphabet", C.c_int32), ("want_pos", C.c_int32),
-        ("max_read_len", C.c_uint32), ("reserved", C.c_int32 * 5),
+        ("max_read_len", C.c_uint32), ("m", C.c_int32), ("scale", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
 def make_params(mode, k, w=0, s=0, canonical=True, circular=False, codon_table=1, frame=1,
-                alphabet=ALPHABET_DNA_REDUNDANT, want_pos=True, max_read_len=0):
+                alphabet=ALPHABET_DNA_REDUNDANT, want_pos=True, max_read_len=0, m=0, scale=1):
     p = Params()
     p.mode, p.k, p.w, p.s = mode, k, w, s
     p.canonical, p.circular = int(bool(canonical)), int(bool(circular))
     p.codon_table, p.frame, p.alphabet = codon_table, frame, alphabet
     p.want_pos, p.max_read_len = int(bool(want_pos)), int(max_read_len)
+    p.m, p.scale = m, scale
     return p
 
 

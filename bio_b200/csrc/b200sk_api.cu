@@ -190,6 +190,8 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
             aa_stride *= 4;
         }
         pl.lcap = aa_stride;
+        uint32_t ring_per_thread = 0; // SimHash: the window of n = k-m+1 m-mer hashes (w carries m)
+        if (mode == B200SK_MODE_SIMHASH) ring_per_thread = (uint32_t)(k - w + 1) * 8u;
         for (int T : {128, 64, 32}) {
             pl.T = T;
             pl.sm_ring = 8192 + 256;
@@ -197,7 +199,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
             pl.sm_tile = pl.sm_ring + pl.sm_ring_bytes;
             pl.sm_tile_bytes = up16((uint32_t)T * pl.span_max + 32);
             pl.sm_listv = pl.sm_tile + pl.sm_tile_bytes;
-            pl.sm_listp = pl.sm_listv + up16((uint32_t)T * aa_stride);
+            pl.sm_listp = pl.sm_listv + up16((uint32_t)T * (aa_stride + ring_per_thread));
             pl.sm_total = pl.sm_listp;
             if (pl.sm_total <= 112 * 1024) return 0;
         }
@@ -289,6 +291,10 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     a.bases = d_bases; a.off = d_off; a.off_orig = nullptr; a.n_reads = n_reads;
     a.mode = q.mode; a.k = q.k; a.w = q.w; a.s = q.s; a.canonical = q.canonical; a.frame = q.frame;
     a.alphabet = q.alphabet;
+    if (q.mode == B200SK_MODE_SIMHASH) { // inside the kernels w carries m and s carries scale
+        q.w = p.m; q.s = p.scale;
+        a.w = p.m; a.s = p.scale;
+    }
 
     if (q.mode == B200SK_MODE_KMER) {
         // NextKmer stops at the first illegal base (iterator.go:730-748): find it once per read
@@ -490,6 +496,13 @@ int b200sk_check_params(const b200sk_params *p) {
         if (p->frame < -3 || p->frame > 3 || p->frame == 0) return B200SK_ERR_INVALID_FRAME; // seq.go:694
         return 0;
     }
+    case B200SK_MODE_SIMHASH:
+        if (p->k < 1) return B200SK_ERR_INVALID_K;                       // iterator.go:114
+        if (p->k >= 65535) return B200SK_ERR_K_TOO_LARGE;                // iterator.go:117
+        if (p->m < 4 || p->m > p->k) return B200SK_ERR_INVALID_M;        // iterator.go:121
+        if (p->scale < 1 || p->scale > p->k - p->m + 1) return B200SK_ERR_INVALID_SCALE; // iterator.go:124
+        if (p->k - p->m + 1 > 255) return B200SK_ERR_UNSUPPORTED;        // 8 counter planes
+        return 0;
     case B200SK_MODE_PROTEIN_MINIMIZER: {
         if (p->k < 1) return B200SK_ERR_INVALID_K;       // sketch-protein.go:63
         if (p->w < 1) return B200SK_ERR_INVALID_W;       // sketch-protein.go:70
@@ -518,6 +531,9 @@ const char *b200sk_strerror(int code) {
     case B200SK_ERR_CODON_TABLE: return "seq: invalid codon table";
     case B200SK_ERR_TRANSLATE_SHORT: return "seq: sequence too short to translate";
     case B200SK_ERR_INVALID_CODON: return "seq: invalid DNA base";
+    case B200SK_ERR_INVALID_M: return "sketches: invalid m-mer size, should be in range of [4, k]";
+    case B200SK_ERR_INVALID_SCALE: return "sketches: invalid scale, should be in range of [1, k-m+1]";
+    case B200SK_ERR_K_TOO_LARGE: return "sketches: k-mer size is too large";
     case B200SK_ERR_CUDA: return "b200sketch: CUDA error";
     case B200SK_ERR_NO_DEVICE: return "b200sketch: no CUDA device (there is no CPU fallback)";
     case B200SK_ERR_UNSUPPORTED: return "b200sketch: parameters outside the implemented range";
@@ -611,6 +627,7 @@ uint64_t b200sk_output_bound(const b200sk_params *p, uint64_t n_bases, uint64_t 
     switch (p->mode) {
     case B200SK_MODE_KMER: return (p->canonical ? 1 : 2) * nb;
     case B200SK_MODE_NTHASH: return nb;
+    case B200SK_MODE_SIMHASH: return nb;
     case B200SK_MODE_PROTEIN: return nb / 3 + n_reads;
     case B200SK_MODE_PROTEIN_MINIMIZER:
         if (exact || p->w <= 1) return nb / 3 + n_reads;

@@ -137,58 +137,16 @@ struct DItem {
     bool valid, both; // both: k-mer second strand is emitted too
 };
 
+// item index -> (read, chunk) -> what the item computes and where its elements go
 template <int MODE>
-__global__ void __launch_bounds__(128) k_dense(const KArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, wid = tid >> 5;
-    uint8_t *tab = smem; // 8 KB: ntHash tables by byte / k-mer LUT / codon tables
-    TileCtl *ctl = reinterpret_cast<TileCtl *>(smem + 8192);
-    uint8_t *tilebuf = smem + a.sm_tile;
-    uint8_t *stage = smem + a.sm_ring + wid * (MODE == B200SK_MODE_KMER ? 2 : 1) * DENSE_WARP_STAGE;
-    uint8_t *row = stage + lane * DENSE_ROW;
+__device__ __forceinline__ void dense_item_geometry(const KArgs &a, const ReadGeom &g, uint64_t item_idx,
+                                                    uint64_t n_items, DItem &it) {
     const int k = a.k;
-    if (MODE == B200SK_MODE_NTHASH) {
-        ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(tab), *tOut = tIn + 256;
-        for (uint32_t b = tid; b < 256; b += T) {
-            const uint64_t f = fwd_seed(b), r = rev_seed(b);
-            tIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(k - 1)));
-            tOut[b] = make_ulonglong2(rol64(f, (unsigned)k), ror64(r, 1));
-        }
-    } else if (MODE == B200SK_MODE_KMER) {
-        for (uint32_t b = tid; b < 256; b += T) {
-            const uint32_t bit = base2bit_of(b);
-            const uint32_t cb = base2bit_of(pair_letter(a.alphabet, b));
-            tab[b] = (uint8_t)((bit & 3u) | ((cb & 3u) << 2) | (bit == 4 ? 0x10u : 0u));
-        }
-    } else {
-        for (uint32_t i = tid; i < 4608; i += T) tab[i] = a.aux[i];
-    }
-    if (tid == 0) {
-        mbar_init(&ctl->mbar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
-    const uint64_t total = a.out_off[a.n_reads] - a.out_base;
-    const bool fits = total <= a.capacity;
-    if (!fits) {
-        if (blockIdx.x == 0 && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
-        return;
-    }
-    const ReadGeom g = a.geom();
-    uint32_t parity = 0;
-    for (;;) {
-        if (tid == 0) ctl->tile = atomicAdd(a.ticket, 1ULL);
-        __syncthreads();
-        const uint64_t tile = ctl->tile;
-        const uint64_t item0 = tile * T;
-        if (item0 >= n_items) break;
-        // ---- geometry
-        DItem it;
-        it.valid = item0 + tid < n_items;
-        it.r = 0; it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0; it.p0 = 0; it.np = 0; it.L = 0; it.both = false;
-        if (it.valid) {
-            const uint64_t item = item0 + tid;
+    it.valid = item_idx < n_items;
+    it.r = 0; it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0; it.p0 = 0; it.np = 0; it.L = 0; it.both = false;
+    if (!it.valid) return;
+    {
+        const uint64_t item = item_idx;
             uint64_t r = item;
             uint32_t c = 0;
             if (a.item_first) {
@@ -233,7 +191,86 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     it.both = MODE == B200SK_MODE_KMER && !a.canonical && st == B200SK_OK;
                 }
             }
+    }
+}
+
+// Bit-sliced counters for SimHash: plane p holds bit p of the 64 per-bit-position counts.
+template <int NB> struct BitCounters {
+    uint64_t pl[NB];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int p = 0; p < NB; p++) pl[p] = 0;
+    }
+    __device__ __forceinline__ void add(uint64_t v) { // count[b] += bit b of v
+#pragma unroll
+        for (int p = 0; p < NB; p++) { const uint64_t t = pl[p] & v; pl[p] ^= v; v = t; }
+    }
+    __device__ __forceinline__ void sub(uint64_t v) { // count[b] -= bit b of v
+#pragma unroll
+        for (int p = 0; p < NB; p++) { const uint64_t t = ~pl[p] & v; pl[p] ^= v; v = t; }
+    }
+    __device__ __forceinline__ uint64_t ge(uint32_t thr) const { // bit b = (count[b] >= thr)
+        uint64_t gt = 0, eq = ~0ull;
+#pragma unroll
+        for (int p = NB - 1; p >= 0; p--) {
+            const uint64_t tb = (thr >> p) & 1u ? ~0ull : 0ull;
+            gt |= eq & pl[p] & ~tb;
+            eq &= ~(pl[p] ^ tb);
         }
+        return gt | eq;
+    }
+};
+
+template <int MODE, int NB = 1>
+__global__ void __launch_bounds__(128) k_dense(const KArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, wid = tid >> 5;
+    uint8_t *tab = smem; // 8 KB: ntHash tables by byte / k-mer LUT / codon tables
+    TileCtl *ctl = reinterpret_cast<TileCtl *>(smem + 8192);
+    uint8_t *tilebuf = smem + a.sm_tile;
+    uint8_t *stage = smem + a.sm_ring + wid * (MODE == B200SK_MODE_KMER ? 2 : 1) * DENSE_WARP_STAGE;
+    uint8_t *row = stage + lane * DENSE_ROW;
+    const int k = a.k;
+    if (MODE == B200SK_MODE_NTHASH || MODE == B200SK_MODE_SIMHASH) {
+        const int hk = MODE == B200SK_MODE_SIMHASH ? a.w : k; // SimHash hashes m-mers (a.w carries m)
+        ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(tab), *tOut = tIn + 256;
+        for (uint32_t b = tid; b < 256; b += T) {
+            const uint64_t f = fwd_seed(b), r = rev_seed(b);
+            tIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(hk - 1)));
+            tOut[b] = make_ulonglong2(rol64(f, (unsigned)hk), ror64(r, 1));
+        }
+    } else if (MODE == B200SK_MODE_KMER) {
+        for (uint32_t b = tid; b < 256; b += T) {
+            const uint32_t bit = base2bit_of(b);
+            const uint32_t cb = base2bit_of(pair_letter(a.alphabet, b));
+            tab[b] = (uint8_t)((bit & 3u) | ((cb & 3u) << 2) | (bit == 4 ? 0x10u : 0u));
+        }
+    } else {
+        for (uint32_t i = tid; i < 4608; i += T) tab[i] = a.aux[i];
+    }
+    if (tid == 0) {
+        mbar_init(&ctl->mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
+    const uint64_t total = a.out_off[a.n_reads] - a.out_base;
+    const bool fits = total <= a.capacity;
+    if (!fits) {
+        if (blockIdx.x == 0 && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
+        return;
+    }
+    const ReadGeom g = a.geom();
+    uint32_t parity = 0;
+    for (;;) {
+        if (tid == 0) ctl->tile = atomicAdd(a.ticket, 1ULL);
+        __syncthreads();
+        const uint64_t tile = ctl->tile;
+        const uint64_t item0 = tile * T;
+        if (item0 >= n_items) break;
+        // ---- geometry
+        DItem it;
+        dense_item_geometry<MODE>(a, g, item0 + tid, n_items, it);
         // tile byte range = [min gb0, max gb0+nb) over the items (reverse frames walk a read downwards, so
         // item order is not address order here)
         if (tid == 0) { ctl->lo = ~0ULL; ctl->hi = 0; }
@@ -333,6 +370,66 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                 const uint64_t b2 = it.obase - it.p0 + 2ull * it.np - 1 - i0;
                 flush_rows(stage + DENSE_WARP_STAGE, a.out_val, a.out_pos, b2, it.both ? n : 0u, -1,
                            it.np - 1 - i0, lane);
+            }
+        } else if (MODE == B200SK_MODE_SIMHASH) {
+            // NextSimHash (iterator.go:191-612): per k-mer, the per-bit majority over its n = k-m+1 m-mer
+            // hashes that pass the FracMinHash filter.  The window slides by one m-mer per k-mer: subtract the
+            // hash that leaves (ring in shared memory), add the one that enters, compare every bit count with
+            // the threshold (nPos+1)/2 -- all 64 bit positions at once in bit-sliced counters.
+            const int m = a.w, n = k - m + 1;
+            const ulonglong2 *tIn = reinterpret_cast<const ulonglong2 *>(tab), *tOut = tIn + 256;
+            const bool canonical = a.canonical != 0;
+            const uint64_t maxh = a.s > 1 ? 0xffffffffffffffffull / (uint64_t)a.s : 0xffffffffffffffffull; // :180-185
+            uint64_t *ring = reinterpret_cast<uint64_t *>(smem + a.sm_listv) + tid; // [n][T]
+            BitCounters<NB> cnt;
+            cnt.clear();
+            uint32_t npos = 0, slot = 0;
+            uint64_t fh = 0, rh = 0;
+            if (nstep) {
+                for (int j = 0; j < m - 1; j++) {
+                    const ulonglong2 e = tIn[sb[j]];
+                    fh = rol1(fh) ^ e.x;
+                    rh = ror1(rh) ^ e.y;
+                }
+                // the first n-1 m-mers only fill the window
+                for (int t = 0; t < n - 1; t++) {
+                    const ulonglong2 in = tIn[sb[t + m - 1]];
+                    ulonglong2 o = make_ulonglong2(0, 0);
+                    if (t) o = tOut[sb[t - 1]];
+                    fh = rol1(fh) ^ o.x ^ in.x;
+                    rh = ror1(rh) ^ o.y ^ in.y;
+                    uint64_t hv = (canonical && rh < fh) ? rh : fh;
+                    if (hv > maxh) hv = 0;
+                    ring[(uint32_t)t * T] = hv;
+                    cnt.add(hv);
+                    npos += hv != 0;
+                }
+                slot = (uint32_t)(n - 1);
+            }
+            for (uint32_t u0 = 0; u0 < maxn; u0 += DENSE_S) {
+                for (uint32_t e = 0; e < DENSE_S; e++) {
+                    const uint32_t u = u0 + e;
+                    if (u < nstep) {
+                        const uint32_t t = u + (uint32_t)n - 1; // m-mer entering the window of k-mer u
+                        const ulonglong2 in = tIn[sb[t + m - 1]];
+                        ulonglong2 o = make_ulonglong2(0, 0);
+                        if (t) o = tOut[sb[t - 1]];
+                        fh = rol1(fh) ^ o.x ^ in.x;
+                        rh = ror1(rh) ^ o.y ^ in.y;
+                        uint64_t hv = (canonical && rh < fh) ? rh : fh;
+                        if (hv > maxh) hv = 0;                          // iterator.go:281
+                        const uint64_t old = u ? ring[slot * T] : 0ull; // the m-mer of k-mer u-1 that left (:205)
+                        ring[slot * T] = hv;
+                        slot = slot + 1 == (uint32_t)n ? 0 : slot + 1;
+                        cnt.sub(old);
+                        npos -= old != 0;
+                        cnt.add(hv);
+                        npos += hv != 0;
+                        *reinterpret_cast<uint64_t *>(row + e * 8) = npos ? cnt.ge((npos + 1) >> 1) : 0ull; // :357-424
+                    }
+                }
+                const uint32_t nn = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
+                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, nn, 1, it.p0 + u0, lane);
             }
         } else { // PROTEIN
             uint8_t *aab = smem + a.sm_listv + tid * a.lcap; // lcap = per-thread amino-acid buffer stride
@@ -440,8 +537,9 @@ cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint
     return cudaGetLastError();
 }
 
-template <int MODE> static cudaError_t launch_dense_mode(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
-    const void *fn = (const void *)k_dense<MODE>;
+template <int MODE, int NB = 1>
+static cudaError_t launch_dense_mode(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
+    const void *fn = (const void *)k_dense<MODE, NB>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.sm_total);
     if (e != cudaSuccess) return e;
     if (occ) {
@@ -450,7 +548,7 @@ template <int MODE> static cudaError_t launch_dense_mode(const KArgs &a, int thr
         *occ = nb < 1 ? 1 : nb;
         return e;
     }
-    k_dense<MODE><<<blocks, threads, a.sm_total, st>>>(a);
+    k_dense<MODE, NB><<<blocks, threads, a.sm_total, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -459,6 +557,13 @@ cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t s
     case B200SK_MODE_NTHASH: return launch_dense_mode<B200SK_MODE_NTHASH>(a, threads, blocks, st, occ);
     case B200SK_MODE_KMER: return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
     case B200SK_MODE_PROTEIN: return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
+    case B200SK_MODE_SIMHASH: { // counter planes: enough bits for n = k-m+1 (a.w carries m)
+        const int n = a.k - a.w + 1;
+        if (n < 16) return launch_dense_mode<B200SK_MODE_SIMHASH, 4>(a, threads, blocks, st, occ);
+        if (n < 32) return launch_dense_mode<B200SK_MODE_SIMHASH, 5>(a, threads, blocks, st, occ);
+        if (n < 64) return launch_dense_mode<B200SK_MODE_SIMHASH, 6>(a, threads, blocks, st, occ);
+        return launch_dense_mode<B200SK_MODE_SIMHASH, 8>(a, threads, blocks, st, occ);
+    }
     default: return cudaErrorInvalidValue;
     }
 }

@@ -68,6 +68,7 @@ __host__ __device__ inline uint32_t read_positions(const ReadGeom &g, uint64_t r
     const int k = g.k;
     switch (g.mode) {
     case B200SK_MODE_NTHASH:
+    case B200SK_MODE_SIMHASH: // one SimHash per k-mer (iterator.go:128,151)
         if (orig < (uint64_t)k) { *status = B200SK_ERR_SHORT_SEQ; return 0; }
         return (uint32_t)(L - (uint64_t)k + 1);
     case B200SK_MODE_KMER: {

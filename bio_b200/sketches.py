@@ -42,10 +42,32 @@ class ErrIllegalBase(SketchesError):
 
 
 class ErrKTooLarge(SketchesError):
-    code = cabi.ERR_K_OVERFLOW
+    code = cabi.ERR_K_TOO_LARGE
 
     def __init__(self):
         super().__init__("sketches: k-mer size is too large")
+
+
+class ErrKOverflow(SketchesError):
+    """kmers.ErrKOverflow: what kmers.Encode returns for k > 32 (iterator.go:742)."""
+    code = cabi.ERR_K_OVERFLOW
+
+    def __init__(self):
+        super().__init__("unikmer: k-mer size (1-32) overflow")
+
+
+class ErrInvalidM(SketchesError):
+    code = cabi.ERR_INVALID_M
+
+    def __init__(self):
+        super().__init__("sketches: invalid m-mer size, should be in range of [4, k]")
+
+
+class ErrInvalidScale(SketchesError):
+    code = cabi.ERR_INVALID_SCALE
+
+    def __init__(self):
+        super().__init__("sketches: invalid scale, should be in range of [1, k-m+1]")
 
 
 class ErrInvalidS(SketchesError):
@@ -62,7 +84,8 @@ class ErrInvalidW(SketchesError):
         super().__init__("kmers: invalid minimimzer window")
 
 
-_BY_CODE = {c.code: c for c in (ErrInvalidK, ErrShortSeq, ErrIllegalBase, ErrKTooLarge, ErrInvalidS, ErrInvalidW)}
+_BY_CODE = {c.code: c for c in (ErrInvalidK, ErrShortSeq, ErrIllegalBase, ErrKTooLarge, ErrKOverflow, ErrInvalidS,
+                                ErrInvalidW, ErrInvalidM, ErrInvalidScale)}
 
 
 def _raise(code):
@@ -134,6 +157,10 @@ class Iterator:
         self._i += 1
         return v, True
 
+    def NextSimHash(self):
+        """(simhash, ok) -- iterator.go:191."""
+        return self.NextHash()
+
     def Next(self):
         """(code, ok, err) -- iterator.go:762."""
         return self.NextKmer()
@@ -178,6 +205,14 @@ def NewKmerIterator(s, k, canonical, circular):
 def NewHashIterator(s, k, canonical, circular):
     """iterator.go:615"""
     val, pos, st = _run_one(s, mode=cabi.MODE_NTHASH, k=k, canonical=canonical, circular=circular)
+    if st:
+        _raise(st)
+    return Iterator(val, pos)
+
+
+def NewSimHashIterator(s, k, m, scale, canonical, circular):
+    """iterator.go:113"""
+    val, pos, st = _run_one(s, mode=cabi.MODE_SIMHASH, k=k, m=m, scale=scale, canonical=canonical, circular=circular)
     if st:
         _raise(st)
     return Iterator(val, pos)
@@ -254,6 +289,9 @@ class Batch:
     def HashIterator(self, k, canonical, circular):
         return self._run(mode=cabi.MODE_NTHASH, k=k, canonical=canonical, circular=circular)
 
+    def SimHashIterator(self, k, m, scale, canonical, circular):
+        return self._run(mode=cabi.MODE_SIMHASH, k=k, m=m, scale=scale, canonical=canonical, circular=circular)
+
     def MinimizerSketch(self, k, w, circular):
         return self._run(mode=cabi.MODE_MINIMIZER, k=k, w=w, circular=circular)
 
@@ -284,6 +322,6 @@ class BatchResult:
             return Iterator(val, pos, deferred=st)
         if st:
             _raise(st)
-        if self.mode == cabi.MODE_NTHASH:
+        if self.mode in (cabi.MODE_NTHASH, cabi.MODE_SIMHASH):
             return Iterator(val, pos)
         return Sketch(val, pos, self.mode == cabi.MODE_MINIMIZER)

@@ -42,6 +42,8 @@ var (
 	ErrShortSeq    = fmt.Errorf("sketches: sequence too short")
 	ErrIllegalBase = errors.New("sketches: illegal base")
 	ErrKTooLarge   = fmt.Errorf("sketches: k-mer size is too large")
+	ErrInvalidM    = fmt.Errorf("sketches: invalid m-mer size, should be in range of [4, k]")
+	ErrInvalidScale = fmt.Errorf("sketches: invalid scale, should be in range of [1, k-m+1]")
 	ErrInvalidS    = fmt.Errorf("kmers: invalid s-mer size")
 	ErrInvalidW    = fmt.Errorf("kmers: invalid minimimzer window")
 )
@@ -60,8 +62,12 @@ func codeToError(rc C.int) error {
 		return ErrInvalidS
 	case C.B200SK_ERR_ILLEGAL_BASE:
 		return ErrIllegalBase
-	case C.B200SK_ERR_K_OVERFLOW:
+	case C.B200SK_ERR_K_TOO_LARGE:
 		return ErrKTooLarge
+	case C.B200SK_ERR_INVALID_M:
+		return ErrInvalidM
+	case C.B200SK_ERR_INVALID_SCALE:
+		return ErrInvalidScale
 	default:
 		return errors.New(C.GoString(C.b200sk_strerror(rc)))
 	}
@@ -179,6 +185,13 @@ func (b *Batch) KmerIterator(k int, canonical, circular bool) (*Result, error) {
 // HashIterator == sketches.NewHashIterator (iterator.go:615).
 func (b *Batch) HashIterator(k int, canonical, circular bool) (*Result, error) {
 	p := C.b200sk_params{mode: C.B200SK_MODE_NTHASH, k: C.int32_t(k), canonical: cbool(canonical), circular: cbool(circular)}
+	return b.run(&p)
+}
+
+// SimHashIterator == sketches.NewSimHashIterator (iterator.go:113).
+func (b *Batch) SimHashIterator(k, m, scale int, canonical, circular bool) (*Result, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_SIMHASH, k: C.int32_t(k), m: C.int32_t(m), scale: C.int32_t(scale),
+		canonical: cbool(canonical), circular: cbool(circular)}
 	return b.run(&p)
 }
 

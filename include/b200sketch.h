@@ -42,6 +42,9 @@ extern "C" {
 #define B200SK_ERR_CODON_TABLE (-8)     /* seq/seq.go:685 Translate: unknown table */
 #define B200SK_ERR_TRANSLATE_SHORT (-9) /* seq/codon_tables.go:206-208             */
 #define B200SK_ERR_INVALID_CODON (-10)  /* seq.ErrInvalidDNABase (not reachable: allowUnknownCodon=true) */
+#define B200SK_ERR_INVALID_M (-11)      /* sketches/iterator.go:50  ErrInvalidM     */
+#define B200SK_ERR_INVALID_SCALE (-12)  /* sketches/iterator.go:53  ErrInvalidScale */
+#define B200SK_ERR_K_TOO_LARGE (-13)    /* sketches/iterator.go:47  ErrKTooLarge (k >= 65535) */
 /* library-level conditions (no reference counterpart) */
 #define B200SK_ERR_CUDA (-100)          /* a CUDA runtime call failed; see b200sk_last_error */
 #define B200SK_ERR_NO_DEVICE (-101)     /* no CUDA device: there is NO CPU fallback */
@@ -56,6 +59,7 @@ extern "C" {
 #define B200SK_MODE_MINIMIZER 2 /* NewMinimizerSketch   sketches/sketch.go:85    + NextMinimizer :205 */
 #define B200SK_MODE_SYNCMER 3   /* NewSyncmerSketch     sketches/sketch.go:142   + NextSyncmer :312   */
 #define B200SK_MODE_PROTEIN 4   /* NewProteinIterator   sketches/iterator-protein.go:46 + Next :76   */
+#define B200SK_MODE_SIMHASH 6   /* NewSimHashIterator   sketches/iterator.go:113 + NextSimHash :191 (k, m, scale, canonical, circular) */
 #define B200SK_MODE_PROTEIN_MINIMIZER 5 /* NewProteinMinimizerSketch sketches/sketch-protein.go:62 + Next :106 (k, w, codon_table, frame) */
 
 /* seq.Alphabet of the records (only NextKmer's non-canonical second strand
@@ -81,7 +85,9 @@ typedef struct b200sk_params {
     int32_t want_pos;    /* 0: do not produce out_pos (dense modes: pos is just the running index) */
     uint32_t max_read_len; /* optional hint: length of the longest read (0 = unknown; the library then
                               measures it on the device, which costs one extra pass over read_off) */
-    int32_t reserved[5];
+    int32_t m;           /* MODE_SIMHASH: m-mer size, range [4, k] (iterator.go:121)             */
+    int32_t scale;       /* MODE_SIMHASH: FracMinHash scale of the m-mers, range [1, k-m+1] (:124) */
+    int32_t reserved[3];
 } b200sk_params;
 
 typedef struct b200sk_ctx b200sk_ctx; /* one per caller thread and device; not thread-safe */

@@ -24,11 +24,14 @@ ERR_INVALID_FRAME = -7
 ERR_CODON_TABLE = -8
 ERR_TRANSLATE_SHORT = -9
 ERR_INVALID_CODON = -10
+ERR_INVALID_M = -11
+ERR_INVALID_SCALE = -12
+ERR_K_TOO_LARGE = -13
 
 SORT_STABLE = 0
 SORT_GO14 = 1
 
-MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN, MODE_PROTEIN_MINIMIZER = range(6)
+MODE_KMER, MODE_NTHASH, MODE_MINIMIZER, MODE_SYNCMER, MODE_PROTEIN, MODE_PROTEIN_MINIMIZER, MODE_SIMHASH = range(7)
 
 
 def build():
@@ -39,7 +42,7 @@ def build():
 class _Params(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "mode", "k", "w", "s", "canonical", "circular", "codon_table", "frame",
-        "alphabet", "sort_policy")]
+        "alphabet", "sort_policy", "m", "scale")]
 
 
 _lib = None
@@ -74,6 +77,8 @@ def lib():
         L.ora_protein_minimizer.restype = C.c_int64
         L.ora_protein_minimizer.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             u64p, i64p, ip, ip]
+        L.ora_simhash_iterator.restype = C.c_int64
+        L.ora_simhash_iterator.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64p, ip]
         L.ora_pair_lut.restype = None
         L.ora_pair_lut.argtypes = [C.c_int, u8p]
         L.ora_run_batch.restype = C.c_uint64
@@ -197,6 +202,16 @@ def protein_minimizer(seq, k, w, table=1, frame=1, protein_input=False, policy=S
     return val[:n].copy(), idx[:n].copy(), err.value, bool(tie.value)
 
 
+def simhash_iterator(seq, k, m, scale, canonical=True, circular=False):
+    """sketches.NewSimHashIterator + NextSimHash loop -> (codes, err)."""
+    s = _as_u8(seq)
+    out = np.zeros(len(s) + max(k, 1) + 2, dtype=np.uint64)
+    err = C.c_int(0)
+    n = lib().ora_simhash_iterator(_p(s, C.c_uint8), len(s), k, m, scale, int(canonical), int(circular),
+                                   _p(out, C.c_uint64), C.byref(err))
+    return out[:n].copy(), err.value
+
+
 def pair_lut(alphabet=0):
     lut = np.zeros(256, dtype=np.uint8)
     lib().ora_pair_lut(alphabet, _p(lut, C.c_uint8))
@@ -205,7 +220,7 @@ def pair_lut(alphabet=0):
 
 def run_batch(bases, off, mode, k, w=0, s=0, canonical=True, circular=False, codon_table=1,
               frame=1, alphabet=0, sort_policy=SORT_STABLE, threads=1, want_output=True,
-              want_pos=True):
+              want_pos=True, m=0, scale=1):
     """The reference's per-record pull loop over a concatenated batch.
 
     Returns dict(counts, status, off, val, pos, ties, checksum); val/pos None if
@@ -214,7 +229,7 @@ def run_batch(bases, off, mode, k, w=0, s=0, canonical=True, circular=False, cod
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.uint64)
     n = len(off) - 1
-    p = _Params(mode, k, w, s, int(canonical), int(circular), codon_table, frame, alphabet, sort_policy)
+    p = _Params(mode, k, w, s, int(canonical), int(circular), codon_table, frame, alphabet, sort_policy, m, scale)
     counts = np.zeros(n, dtype=np.uint64)
     status = np.zeros(n, dtype=np.int32)
     ties = C.c_uint64(0)

@@ -48,6 +48,9 @@
 #define ORA_ERR_CODON_TABLE (-8)    /* seq/seq.go Translate: unknown table   */
 #define ORA_ERR_TRANSLATE_SHORT (-9)/* seq/codon_tables.go:206-208           */
 #define ORA_ERR_INVALID_CODON (-10) /* seq.ErrInvalidDNABase w/o allowUnknown */
+#define ORA_ERR_INVALID_M (-11)     /* sketches/iterator.go:50 ErrInvalidM     */
+#define ORA_ERR_INVALID_SCALE (-12) /* sketches/iterator.go:53 ErrInvalidScale */
+#define ORA_ERR_K_TOO_LARGE (-13)   /* sketches/iterator.go:47 ErrKTooLarge    */
 
 #define ORA_SORT_STABLE 0
 #define ORA_SORT_GO14 1
@@ -155,6 +158,71 @@ int64_t ora_hash_iterator(const uint8_t *seq, size_t len, int k, int canonical, 
     uint64_t v;
     while (nthi_next(&h, canonical, &v)) out[n++] = v;
     free(s2);
+    return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* NewSimHashIterator / NextSimHash (sketches/iterator.go:113-612)      */
+/* One 64-bit SimHash per k-mer over its k-m+1 m-mer ntHashes, after the */
+/* FracMinHash filter (hash > MaxUint64/scale -> dropped, :281,443).     */
+/* int16 counters and the sign-bit decode are kept literally (:359-424). */
+/* ------------------------------------------------------------------ */
+int64_t ora_simhash_iterator(const uint8_t *seq, size_t len, int k, int m, int scale, int canonical,
+                             int circular, uint64_t *out, int *err) {
+    *err = ORA_OK;
+    if (k < 1) { *err = ORA_ERR_INVALID_K; return 0; }                    /* :114 */
+    if (k >= 65535) { *err = ORA_ERR_K_TOO_LARGE; return 0; }             /* :117 */
+    if (m < 4 || m > k) { *err = ORA_ERR_INVALID_M; return 0; }           /* :121 */
+    if (scale < 1 || scale > k - m + 1) { *err = ORA_ERR_INVALID_SCALE; return 0; } /* :124 */
+    if (len < (size_t)k) { *err = ORA_ERR_SHORT_SEQ; return 0; }          /* :128 */
+    size_t length;
+    uint8_t *s2 = make_seq2(seq, len, k, circular, &length);
+    int64_t end = (int64_t)length - k + 1, idx = 0, n = 0;                /* :151 */
+    nthi_t h;
+    nthi_init(&h, s2, length, (unsigned)m);                               /* :159 */
+    int16_t sum[64];
+    memset(sum, 0, sizeof(sum));
+    int16_t n_pos = 0, thr;
+    int em = k - m, pre_i = 0, first = 1;
+    uint64_t *hashes = (uint64_t *)calloc((size_t)em + 1, sizeof(uint64_t));
+    const int frac = scale > 1;                                           /* :180 */
+    const uint64_t max_hash = frac ? UINT64_MAX / (uint64_t)scale : UINT64_MAX;
+    uint64_t hv, code;
+    while (idx != end) {                                                  /* :196 */
+        if (!first) {
+            uint64_t pre = hashes[pre_i];                                 /* :205 */
+            if (pre > 0) {
+                n_pos--;
+                for (int b = 0; b < 64; b++) sum[b] -= (int16_t)(pre >> (63 - b) & 1);
+            }
+            nthi_next(&h, canonical, &hv);                                /* :279 */
+            if (frac && hv > max_hash) hv = 0;                            /* :281 */
+            else if (hv > 0) n_pos++;
+            hashes[pre_i] = hv;                                           /* :288 */
+            if (hv > 0) for (int b = 0; b < 64; b++) sum[b] += (int16_t)(hv >> (63 - b) & 1);
+            pre_i = (pre_i == em) ? 0 : pre_i + 1;                        /* :432-436 */
+        } else {
+            n_pos = 0;
+            for (int j = 0; j <= em; j++) {                               /* :438-520 */
+                nthi_next(&h, canonical, &hv);
+                if (frac && hv > max_hash) { hashes[j] = 0; continue; }
+                hashes[j] = hv;
+                if (hv == 0) continue;
+                n_pos++;
+                for (int b = 0; b < 64; b++) sum[b] += (int16_t)(hv >> (63 - b) & 1);
+            }
+            pre_i = 0;
+            first = 0;
+        }
+        code = 0;
+        thr = (int16_t)((n_pos + 1) / 2);                                 /* :357,528 */
+        if (n_pos > 0)
+            for (int b = 0; b < 64; b++)
+                code |= (uint64_t)(((int16_t)(sum[b] - thr) >> 15 & 1) ^ 1) << (63 - b);
+        out[n++] = code;
+        idx++;
+    }
+    free(hashes); free(s2);
     return n;
 }
 
@@ -908,11 +976,11 @@ int64_t ora_protein_minimizer(const uint8_t *seq, size_t len, int k, int table, 
 /* These are what bench.py times as the CPU baseline: the reference's   */
 /* per-record pull loop, one thread per contiguous shard of reads.      */
 /* mode: 0 kmer, 1 nthash, 2 minimizer, 3 syncmer, 4 protein,           */
-/*       5 protein minimizer (alphabet 5 = amino-acid input)            */
+/*       5 protein minimizer (alphabet 5 = amino-acid input), 6 simhash */
 /* Pass 1 (out_val == NULL) only counts; pass 2 writes at out_off[r].   */
 /* ------------------------------------------------------------------ */
 typedef struct {
-    int mode, k, w, s, canonical, circular, codon_table, frame, alphabet, sort_policy;
+    int mode, k, w, s, canonical, circular, codon_table, frame, alphabet, sort_policy, m, scale;
 } ora_params;
 
 typedef struct {
@@ -960,6 +1028,7 @@ static void *ora_worker(void *arg) {
         case 2: n = ora_minimizer(s, len, p->k, p->w, p->circular, p->sort_policy, val, idx, &err, &tie); have_idx = 1; break;
         case 3: n = ora_syncmer(s, len, p->k, p->s, p->circular, p->sort_policy, val, idx, &err, &tie); have_idx = 1; break;
         case 4: n = ora_protein_iterator(s, len, p->k, p->codon_table, p->frame, val, &err); break;
+        case 6: n = ora_simhash_iterator(s, len, p->k, p->m, p->scale, p->canonical, p->circular, val, &err); break;
         case 5: n = ora_protein_minimizer(s, len, p->k, p->codon_table, p->frame, p->w, p->alphabet == 5,
                                           p->sort_policy, val, idx, &err, &tie); have_idx = 1; break;
         default: err = ORA_ERR_INVALID_K;

@@ -145,3 +145,28 @@ def test_oracle_regression_fixture():
         assert np.array_equal(r["pos"], z[name + "/pos"]), name
         assert np.array_equal(r["off"], z[name + "/off"]), name
         assert np.array_equal(r["status"], z[name + "/status"]), name
+
+
+def test_simhash_literal_equals_closed_form(golden):
+    """NextSimHash (iterator.go:191-612, int16 counters, sign-bit decode) == per-bit majority over the k-m+1
+    FracMinHash-filtered m-mer hashes of each k-mer."""
+    s = golden["iterator"]["TestKmerIterator"]["seq"]
+    for k, m, scale, canon in ((21, 5, 5, True), (31, 7, 1, False), (10, 4, 7, True), (12, 12, 1, True)):
+        hs, _ = oracle.hash_iterator(s, m, canon)
+        n = k - m + 1
+        mx = (2 ** 64 - 1) // scale if scale > 1 else 2 ** 64 - 1
+        want = []
+        for i in range(len(s) - k + 1):
+            w = [int(x) for x in hs[i:i + n] if int(x) <= mx and int(x) > 0]
+            code = 0
+            if w:
+                thr = (len(w) + 1) // 2
+                for b in range(64):
+                    if sum((x >> b) & 1 for x in w) >= thr:
+                        code |= 1 << b
+            want.append(code)
+        got, err = oracle.simhash_iterator(s, k, m, scale, canon)
+        assert err == 0 and [int(x) for x in got] == want
+    assert oracle.simhash_iterator(s, 21, 3, 1)[1] == oracle.ERR_INVALID_M
+    assert oracle.simhash_iterator(s, 21, 5, 18)[1] == oracle.ERR_INVALID_SCALE
+    assert oracle.simhash_iterator(s, 65535, 5, 1)[1] == oracle.ERR_K_TOO_LARGE

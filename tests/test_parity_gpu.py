@@ -12,7 +12,7 @@ from bio_b200 import synth
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-OMODE = {cabi.MODE_PROTEIN_MINIMIZER: oracle.MODE_PROTEIN_MINIMIZER, cabi.MODE_KMER: oracle.MODE_KMER, cabi.MODE_NTHASH: oracle.MODE_NTHASH,
+OMODE = {cabi.MODE_SIMHASH: oracle.MODE_SIMHASH, cabi.MODE_PROTEIN_MINIMIZER: oracle.MODE_PROTEIN_MINIMIZER, cabi.MODE_KMER: oracle.MODE_KMER, cabi.MODE_NTHASH: oracle.MODE_NTHASH,
          cabi.MODE_MINIMIZER: oracle.MODE_MINIMIZER, cabi.MODE_SYNCMER: oracle.MODE_SYNCMER,
          cabi.MODE_PROTEIN: oracle.MODE_PROTEIN}
 
@@ -349,3 +349,16 @@ def test_protein_minimizer_amino_acid_input(gpu_ctx):
             s = b[int(o[i]):int(o[i + 1])]
             vals += [oracle.wyhash(s[j:j + 10], 1) for j in range(L - 10 + 1)]
     assert [int(v) for v in res["val"]] == vals
+
+
+@pytest.mark.parametrize("k,m,scale,canonical", [(21, 5, 5, True), (31, 5, 5, True), (31, 7, 1, False), (21, 21, 1, True),
+                                                  (64, 4, 3, True), (100, 10, 8, False), (16, 5, 12, True)])
+def test_simhash(gpu_ctx, k, m, scale, canonical):
+    """SimHashIterator (sketches/iterator.go:113-612): SURVEY.md 8f row 3."""
+    lens = np.concatenate([np.full(200, 150), synth.ont_like_lengths(10, 9, mean=2500), [0, k - 1, k, k + 1, 700]])
+    b, o = synth.ragged_reads(lens, 500 + k + m, alphabet=b"ACGTACGTACGTNacgt")
+    res, ref = run_both(gpu_ctx, cabi.MODE_SIMHASH, b, o, k=k, m=m, scale=scale, canonical=canonical)
+    assert_same(res, ref, f"k={k} m={m} scale={scale}")
+    res, ref = run_both(gpu_ctx, cabi.MODE_SIMHASH, b[: 200 * 150], o[:201], hint=150, k=k, m=m, scale=scale,
+                        canonical=canonical, circular=True)
+    assert_same(res, ref, "hint+circular")

@@ -112,8 +112,16 @@ def test_constructor_errors():
         sk.NewSyncmerSketch(s, 5, 6, False)
     with pytest.raises(sk.ErrInvalidS):
         sk.NewSyncmerSketch(s, 5, 0, False)
-    with pytest.raises(sk.ErrKTooLarge):
+    with pytest.raises(sk.ErrKOverflow):
         sk.NewKmerIterator(sk.NewSeq(sk.DNA, "ACGT" * 20), 33, True, False)
+    with pytest.raises(sk.ErrInvalidM):
+        sk.NewSimHashIterator(s, 8, 3, 1, True, False)
+    with pytest.raises(sk.ErrInvalidM):
+        sk.NewSimHashIterator(s, 8, 9, 1, True, False)
+    with pytest.raises(sk.ErrInvalidScale):
+        sk.NewSimHashIterator(s, 8, 5, 5, True, False)
+    with pytest.raises(sk.ErrKTooLarge):
+        sk.NewSimHashIterator(s, 65535, 5, 1, True, False)
     with pytest.raises(sk.ErrShortSeq):
         sk.NewProteinIterator(s, 4, 1, 1)
 
@@ -191,3 +199,21 @@ def test_TestProteinMinimizer():
         sk.NewProteinMinimizerSketch(sequence, k, 1, 1, 0)
     with pytest.raises(sk.ErrShortSeq):
         sk.NewProteinMinimizerSketch(sk.NewSeq(sk.DNA, s[:31]), k, 1, 1, w)
+
+
+def test_TestSimHashIterator():
+    # sketches/iterator_test.go:105-145: two 21-bp strings (one with a lowercase base), k=21, m=5, scale=5;
+    # the reference asserts the count only, the values come from the oracle
+    for _s in ("GAACAATGTTCTCTAAAATTG", "GcACAATGTTCTCTAAAATTG"):
+        sequence = sk.NewSeq(sk.DNA, _s)
+        k = 21
+        it = sk.NewSimHashIterator(sequence, k, 5, 5, True, False)
+        codes = []
+        while True:
+            code, ok = it.NextSimHash()
+            if not ok:
+                break
+            codes.append(code)
+        assert len(codes) == len(_s) - k + 1
+        ref, err = oracle.simhash_iterator(_s, k, 5, 5, True, False)
+        assert err == 0 and codes == [int(x) for x in ref]
