@@ -318,7 +318,8 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
     torch.from_numpy(hb).copy_(d_bases[:nb])
     ho[:] = np.arange(n + 1, dtype=np.uint64) * np.uint64(READ_LEN)
     torch.cuda.synchronize()
-    p = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN)
+    # Index() values of a 150-bp read fit one byte: ask for uint8 positions (a quarter less D2H traffic)
+    p = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN, pos_width=1)
     res = None
 
     def step():
@@ -342,7 +343,7 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
     chk = int(res["val"][:1000].sum()) if n_out else 0
     out = {"value": nb * world * args.e2e_steps / dt, "unit": "bases/s",
            "h2d_bytes_per_step": nb + (n + 1) * 8,
-           "d2h_bytes_per_step": n_out * 12 + (n + 1) * 8 + n * 4,
+           "d2h_bytes_per_step": n_out * 9 + (n + 1) * 8 + n * 4, "pos_width": 1,
            "reads_per_gpu_per_step": n, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
            "api": "b200sk_run (host pointers, pinned)", "checksum_first_1000": chk}
     L.b200sk_free_pinned(hb_ptr)

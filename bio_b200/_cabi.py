@@ -51,18 +51,18 @@ class Params(C.Structure):
         ("mode", C.c_int32), ("k", C.c_int32), ("w", C.c_int32), ("s", C.c_int32),
         ("canonical", C.c_int32), ("circular", C.c_int32), ("codon_table", C.c_int32),
         ("frame", C.c_int32), ("alphabet", C.c_int32), ("want_pos", C.c_int32),
-        ("max_read_len", C.c_uint32), ("m", C.c_int32), ("scale", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("max_read_len", C.c_uint32), ("m", C.c_int32), ("scale", C.c_int32), ("pos_width", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
 def make_params(mode, k, w=0, s=0, canonical=True, circular=False, codon_table=1, frame=1,
-                alphabet=ALPHABET_DNA_REDUNDANT, want_pos=True, max_read_len=0, m=0, scale=1):
+                alphabet=ALPHABET_DNA_REDUNDANT, want_pos=True, max_read_len=0, m=0, scale=1, pos_width=0):
     p = Params()
     p.mode, p.k, p.w, p.s = mode, k, w, s
     p.canonical, p.circular = int(bool(canonical)), int(bool(circular))
     p.codon_table, p.frame, p.alphabet = codon_table, frame, alphabet
     p.want_pos, p.max_read_len = int(bool(want_pos)), int(max_read_len)
-    p.m, p.scale = m, scale
+    p.m, p.scale, p.pos_width = m, scale, pos_width
     return p
 
 
@@ -209,7 +209,8 @@ class Context:
             a = a.view(dt)
             return a.copy() if copy else a
 
-        return dict(val=view(ov, t, np.uint64), pos=view(op, t, np.uint32) if params.want_pos else None,
+        pdt = {1: np.uint8, 2: np.uint16}.get(int(params.pos_width), np.uint32)
+        return dict(val=view(ov, t, np.uint64), pos=view(op, t, pdt) if params.want_pos else None,
                     off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t)
 
     # ---- device entry points: torch CUDA tensors (plumbing only: pointers + the current stream)

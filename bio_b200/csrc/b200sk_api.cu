@@ -262,8 +262,10 @@ int ensure_meta(b200sk_ctx *ctx) {
 
 // Everything that runs on the device for one batch (no host synchronisation unless the longest
 // read must be measured).  d_flags: where the kernels OR their flags (device memory).
+inline uint32_t pos_width_of(const b200sk_params &p) { return p.pos_width == 1 ? 1u : p.pos_width == 2 ? 2u : 4u; }
+
 int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, const uint64_t *d_off,
-            uint64_t n_reads, uint64_t n_bases, uint64_t *d_val, uint32_t *d_pos, uint64_t *d_ooff,
+            uint64_t n_reads, uint64_t n_bases, uint64_t *d_val, void *d_pos, uint64_t *d_ooff,
             int32_t *d_status, uint64_t capacity, uint64_t out_base, cudaStream_t st, uint32_t *d_flags) {
     int rc = b200sk_check_params(&p);
     if (rc) return rc;
@@ -396,6 +398,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     a.sm_ring_bytes = pl.sm_ring_bytes; a.sm_listv = pl.sm_listv; a.sm_listp = pl.sm_listp;
     a.sm_total = pl.sm_total;
     a.out_val = d_val; a.out_pos = p.want_pos ? d_pos : nullptr; a.out_off = d_ooff; a.status = d_status;
+    a.pos_width = pos_width_of(p);
     a.capacity = d_val ? capacity : 0; a.out_base = out_base;
     a.flags = d_flags ? d_flags : (uint32_t *)(meta + 1);
 
@@ -471,6 +474,13 @@ int b200sk_version(void) { return 100; }
 
 int b200sk_check_params(const b200sk_params *p) {
     if (!p) return B200SK_ERR_BAD_ARG;
+    if (p->pos_width != 0 && p->pos_width != 1 && p->pos_width != 2 && p->pos_width != 4) return B200SK_ERR_BAD_ARG;
+    if (p->want_pos && (p->pos_width == 1 || p->pos_width == 2)) {
+        // every Index() must fit: needs the hint, counted on the extended length when circular
+        const uint64_t lim = p->pos_width == 1 ? 256 : 65536;
+        const uint64_t ext = p->circular && p->k > 0 ? (uint64_t)p->k - 1 : 0;
+        if (p->max_read_len == 0 || (uint64_t)p->max_read_len + ext > lim) return B200SK_ERR_BAD_ARG;
+    }
     switch (p->mode) {
     case B200SK_MODE_KMER:
         if (p->k < 1) return B200SK_ERR_INVALID_K;       // iterator.go:669
@@ -694,7 +704,8 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
     CK(ctx->h_meta.reserve(64));
     uint64_t host_cap = b200sk_output_bound(p, n_bases, n_reads, 0);
     CK(ctx->h_val.reserve(host_cap * 8 + 8));
-    if (want_pos) CK(ctx->h_pos.reserve(host_cap * 4 + 4));
+    const uint32_t pw = pos_width_of(*p);
+    if (want_pos) CK(ctx->h_pos.reserve(host_cap * pw + 4));
     uint64_t *h_ooff = (uint64_t *)ctx->h_ooff.p;
     volatile uint64_t *h_meta = (volatile uint64_t *)ctx->h_meta.p;
     if (n_reads == 0) {
@@ -817,7 +828,7 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
             }
             const uint8_t *dbase = (const uint8_t *)sl.bases.p - b0; // offsets stay absolute
             rc = enqueue(ctx, *p, dbase, (const uint64_t *)sl.off.p, nr, nb, (uint64_t *)sl.val.p,
-                         want_pos ? (uint32_t *)sl.pos.p : nullptr, (uint64_t *)sl.ooff.p, (int32_t *)sl.status.p,
+                         want_pos ? sl.pos.p : nullptr, (uint64_t *)sl.ooff.p, (int32_t *)sl.status.p,
                          sl.cap, running, s_k, nullptr);
             if (rc) { cudaDeviceSynchronize(); save_slots(); return rc; }
             CKS(cudaMemcpyAsync((void *)h_meta, (uint64_t *)sl.ooff.p + nr, 8, cudaMemcpyDeviceToHost, s_k));
@@ -835,13 +846,13 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
             CKS(cudaStreamSynchronize(s_out));
             host_cap = (running + total) + (running + total) / 4 + 1024;
             CKS(ctx->h_val.reserve(host_cap * 8 + 8, true));
-            if (want_pos) CKS(ctx->h_pos.reserve(host_cap * 4 + 4, true));
+            if (want_pos) CKS(ctx->h_pos.reserve(host_cap * pw + 4, true));
         }
         CKS(cudaStreamWaitEvent(s_out, sl.k_done, 0));
         if (total) {
             CKS(cudaMemcpyAsync((uint64_t *)ctx->h_val.p + running, sl.val.p, total * 8, cudaMemcpyDeviceToHost, s_out));
             if (want_pos)
-                CKS(cudaMemcpyAsync((uint32_t *)ctx->h_pos.p + running, sl.pos.p, total * 4, cudaMemcpyDeviceToHost, s_out));
+                CKS(cudaMemcpyAsync((uint8_t *)ctx->h_pos.p + running * pw, sl.pos.p, total * pw, cudaMemcpyDeviceToHost, s_out));
         }
         CKS(cudaMemcpyAsync(h_ooff + r0, sl.ooff.p, (nr + 1) * 8, cudaMemcpyDeviceToHost, s_out));
         CKS(cudaMemcpyAsync((int32_t *)ctx->h_status.p + r0, sl.status.p, nr * 4, cudaMemcpyDeviceToHost, s_out));

@@ -108,8 +108,8 @@ cudaError_t launch_translate(const uint8_t *bases, const uint64_t *off, const ui
 // ------------------------------------------------------------------ staged, coalesced output
 // Each lane filled `n` (<= 16) entries of its row; entry e goes to out[b + d*e] (d = +1, or -1 for the
 // second strand of both-strand k-mers), position p0 + d*e.  Two lanes' rows leave per iteration.
-__device__ __forceinline__ void flush_rows(const uint8_t *stage, uint64_t *out_val, uint32_t *out_pos, uint64_t b,
-                                           uint32_t n, int d, uint32_t p0, unsigned lane) {
+__device__ __forceinline__ void flush_rows(const uint8_t *stage, uint64_t *out_val, void *out_pos, uint32_t pw,
+                                           uint64_t b, uint32_t n, int d, uint32_t p0, unsigned lane) {
     __syncwarp();
 #pragma unroll 4
     for (int j = 0; j < 32; j += 2) {
@@ -123,7 +123,7 @@ __device__ __forceinline__ void flush_rows(const uint8_t *stage, uint64_t *out_v
             const uint64_t v = *reinterpret_cast<const uint64_t *>(stage + src * DENSE_ROW + e * 8);
             const uint64_t idx = bb + (uint64_t)((int64_t)dd * (int64_t)e);
             out_val[idx] = v;
-            if (out_pos) out_pos[idx] = pp + (uint32_t)(dd * (int)e);
+            if (out_pos) store_pos(out_pos, pw, idx, pp + (uint32_t)(dd * (int)e));
         }
     }
     __syncwarp();
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, n, 1, it.p0 + u0, lane);
+                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
             }
         } else if (MODE == B200SK_MODE_KMER) {
             // iterator.go:736,740,754: code = (pre & mask1) << 2 | bit; rc = (bit ^ 3) << 2(k-1) | preRC >> 2.
@@ -364,11 +364,11 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, n, 1, it.p0 + u0, lane);
+                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
                 // strand 2: k-mer i = p0+u0+e lands at out_off[r] + np + (np-1-i), position np-1-i
                 const uint32_t i0 = it.p0 + u0;
                 const uint64_t b2 = it.obase - it.p0 + 2ull * it.np - 1 - i0;
-                flush_rows(stage + DENSE_WARP_STAGE, a.out_val, a.out_pos, b2, it.both ? n : 0u, -1,
+                flush_rows(stage + DENSE_WARP_STAGE, a.out_val, a.out_pos, a.pos_width, b2, it.both ? n : 0u, -1,
                            it.np - 1 - i0, lane);
             }
         } else if (MODE == B200SK_MODE_SIMHASH) {
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t nn = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, nn, 1, it.p0 + u0, lane);
+                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, nn, 1, it.p0 + u0, lane);
             }
         } else { // PROTEIN
             uint8_t *aab = smem + a.sm_listv + tid * a.lcap; // lcap = per-thread amino-acid buffer stride
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, it.obase + u0, n, 1, it.p0 + u0, lane);
+                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
             }
         }
         __syncthreads();

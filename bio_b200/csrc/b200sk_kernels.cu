@@ -220,11 +220,12 @@ template <> struct Sink<false> { // staged in shared memory, [slot][thread]
 };
 template <> struct Sink<true> { // straight to the final global position (overflow path)
     uint64_t *gv;
-    uint32_t *gp;
-    uint32_t posbase, cnt;
+    void *gp; // out_pos array (whole), element index gi + cnt
+    uint64_t gi;
+    uint32_t pw, posbase, cnt;
     __device__ __forceinline__ void emit(uint64_t v, uint32_t rel) {
         gv[cnt] = v;
-        if (gp) gp[cnt] = posbase + rel;
+        if (gp) store_pos(gp, pw, gi + cnt, posbase + rel);
         cnt++;
     }
 };
@@ -447,10 +448,8 @@ __global__ void __launch_bounds__(128) k_sparse(const KArgs a) {
                 const uint32_t n = min(OB, total - r0);
                 uint64_t *gv = a.out_val + tb + r0;
                 for (uint32_t i = tid; i < n; i += T) gv[i] = obv[i];
-                if (a.out_pos) {
-                    uint32_t *gp = a.out_pos + tb + r0;
-                    for (uint32_t i = tid; i < n; i += T) gp[i] = obp[i];
-                }
+                if (a.out_pos)
+                    for (uint32_t i = tid; i < n; i += T) store_pos(a.out_pos, a.pos_width, tb + r0 + i, obp[i]);
                 __syncthreads();
             }
             if (ctl->any_overflow) {
@@ -459,7 +458,7 @@ __global__ void __launch_bounds__(128) k_sparse(const KArgs a) {
                 // were overwritten by the ordered copy, so read them from global memory instead.
                 if (overflow) {
                     Sink<true> ds;
-                    ds.gv = a.out_val + mine; ds.gp = a.out_pos ? a.out_pos + mine : nullptr;
+                    ds.gv = a.out_val + mine; ds.gp = a.out_pos; ds.gi = mine; ds.pw = a.pos_width;
                     ds.posbase = it.q0; ds.cnt = 0;
                     WinMin wm;
                     wm.init(ringv + tid, ringu + tid, T, ww);

@@ -25,7 +25,8 @@ struct KArgs {
     uint64_t n_items;           // == item_first[n_reads] when chunked (read on device), else n_reads
     const uint64_t *n_items_dev;
     uint64_t *out_val;
-    uint32_t *out_pos;
+    void *out_pos;      // u8 / u16 / u32 elements (pos_width bytes each)
+    uint32_t pos_width; // 1, 2 or 4
     uint64_t *out_off;
     int32_t *status;
     uint64_t capacity;
@@ -48,6 +49,13 @@ struct KArgs {
     // dynamic shared memory layout (byte offsets)
     uint32_t sm_tile, sm_tile_bytes, sm_ring, sm_ring_bytes, sm_listv, sm_listp, sm_total;
 };
+
+// out_pos element store (the width is uniform across the grid)
+__device__ __forceinline__ void store_pos(void *base, uint32_t width, uint64_t idx, uint32_t v) {
+    if (width == 4) reinterpret_cast<uint32_t *>(base)[idx] = v;
+    else if (width == 1) reinterpret_cast<uint8_t *>(base)[idx] = (uint8_t)v;
+    else reinterpret_cast<uint16_t *>(base)[idx] = (uint16_t)v;
+}
 
 // amino acids a frame of a read of length L translates to (seq/codon_tables.go:219,255)
 __host__ __device__ inline uint32_t frame_aa_count(uint64_t L, int frame) {

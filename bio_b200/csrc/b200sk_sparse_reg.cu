@@ -107,14 +107,15 @@ struct ListSink { // staged in shared memory, [slot][lane]; slot `cap` is a scra
 };
 struct GlobalSink { // straight to the final position (tiles where some item overflowed its list)
     uint64_t *gv;
-    uint32_t *gp;
-    uint32_t pos, cnt, skip;
+    void *gp; // out_pos array (whole), element index gi + n
+    uint64_t gi;
+    uint32_t pw, pos, cnt, skip;
     __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t delta) {
         if (pred) {
             pos += delta;
             if (cnt >= skip) {
                 gv[cnt - skip] = v;
-                if (gp) gp[cnt - skip] = pos;
+                if (gp) store_pos(gp, pw, gi + cnt - skip, pos);
             }
             cnt++;
         }
@@ -466,10 +467,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
                     for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
-                    if (a.out_pos) {
-                        uint32_t *gp = a.out_pos + tb + r0;
-                        for (uint32_t i = lane; i < n; i += 32u) gp[i] = obp[i];
-                    }
+                    if (a.out_pos)
+                        for (uint32_t i = lane; i < n; i += 32u) store_pos(a.out_pos, a.pos_width, tb + r0 + i, obp[i]);
                     __syncwarp();
                 }
             } else {
@@ -482,12 +481,12 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                         pos += listp[j * 32u + lane];
                         if (j >= skip) {
                             a.out_val[mine + j - skip] = listv[j * 32u + lane];
-                            if (a.out_pos) a.out_pos[mine + j - skip] = pos;
+                            if (a.out_pos) store_pos(a.out_pos, a.pos_width, mine + j - skip, pos);
                         }
                     }
                 } else {
                     GlobalSink gs;
-                    gs.gv = a.out_val + mine; gs.gp = a.out_pos ? a.out_pos + mine : nullptr;
+                    gs.gv = a.out_val + mine; gs.gp = a.out_pos; gs.gi = mine; gs.pw = a.pos_width;
                     gs.pos = it.q0 - 1u; gs.cnt = 0; gs.skip = skip;
                     if (SYNC)
                         syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,

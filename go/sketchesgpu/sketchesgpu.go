@@ -157,6 +157,7 @@ func (b *Batch) run(p *C.b200sk_params) (*Result, error) {
 	}
 	p.alphabet = b.alpha
 	p.want_pos = 1
+	p.pos_width = 4 // a production shim picks 1 or 2 when b.maxLen allows and widens in Index()
 	p.max_read_len = C.uint32_t(b.maxLen)
 	n := len(b.off) - 1
 	var v *C.uint64_t

@@ -87,7 +87,11 @@ typedef struct b200sk_params {
                               measures it on the device, which costs one extra pass over read_off) */
     int32_t m;           /* MODE_SIMHASH: m-mer size, range [4, k] (iterator.go:121)             */
     int32_t scale;       /* MODE_SIMHASH: FracMinHash scale of the m-mers, range [1, k-m+1] (:124) */
-    int32_t reserved[3];
+    int32_t pos_width;   /* bytes per out_pos element: 0 or 4 = uint32 (default), 1 = uint8, 2 = uint16.  Narrow
+                            positions need the max_read_len hint (<= 256 resp. 65536): every Index() must fit.  The
+                            out_pos pointers then address uint8_t / uint16_t arrays (a third less PCIe traffic for
+                            150-bp reads). */
+    int32_t reserved[2];
 } b200sk_params;
 
 typedef struct b200sk_ctx b200sk_ctx; /* one per caller thread and device; not thread-safe */

@@ -362,3 +362,23 @@ def test_simhash(gpu_ctx, k, m, scale, canonical):
     res, ref = run_both(gpu_ctx, cabi.MODE_SIMHASH, b[: 200 * 150], o[:201], hint=150, k=k, m=m, scale=scale,
                         canonical=canonical, circular=True)
     assert_same(res, ref, "hint+circular")
+
+
+@pytest.mark.parametrize("pw", [1, 2])
+def test_narrow_positions(gpu_ctx, pw):
+    """pos_width = 1 / 2: out_pos as uint8 / uint16 (same values), for every kernel family."""
+    b, o = synth.uniform_reads(3000, 150, 77)
+    for mode, kw in ((cabi.MODE_MINIMIZER, dict(k=21, w=11)), (cabi.MODE_MINIMIZER, dict(k=21, w=30)),
+                     (cabi.MODE_SYNCMER, dict(k=21, s=11)), (cabi.MODE_NTHASH, dict(k=21)),
+                     (cabi.MODE_KMER, dict(k=21, canonical=False)), (cabi.MODE_PROTEIN, dict(k=11, frame=-1))):
+        p = cabi.make_params(mode, max_read_len=150, pos_width=pw, **kw)
+        res = gpu_ctx.run(p, b, o)
+        ref = oracle.run_batch(b, o, OMODE[mode], threads=4, **kw)
+        assert res["pos"].dtype == (np.uint8 if pw == 1 else np.uint16)
+        assert_same(res, ref, f"pw={pw} mode={mode}")
+    # the hint is mandatory and must cover the positions
+    with pytest.raises(cabi.SketchError):
+        gpu_ctx.run(cabi.make_params(cabi.MODE_NTHASH, 21, pos_width=pw), b, o)
+    if pw == 1:
+        with pytest.raises(cabi.SketchError):
+            gpu_ctx.run(cabi.make_params(cabi.MODE_NTHASH, 21, pos_width=1, max_read_len=300), b, o)
