@@ -183,7 +183,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     if (pl.dense) {
         // tables 8 KB + control, per-warp output staging (two areas for both-strand k-mers), tile,
         // per-thread amino-acid buffers (protein)
-        const uint32_t stage_w = (mode == B200SK_MODE_KMER ? 2u : 1u) * 32u * (16u * 8u + 8u);
+        const uint32_t stage_w = (mode == B200SK_MODE_KMER ? 2u : 1u) * (32u * (16u * 8u + 8u) + 512u);
         uint32_t aa_stride = 0;
         if (mode == B200SK_MODE_PROTEIN) {
             aa_stride = ((pl.C + (uint32_t)k - 1 + 3) / 4) | 1u; // odd number of words: conflict-free columns
@@ -197,7 +197,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
             pl.sm_ring = 8192 + 256;
             pl.sm_ring_bytes = (uint32_t)(T / 32) * stage_w;
             pl.sm_tile = pl.sm_ring + pl.sm_ring_bytes;
-            pl.sm_tile_bytes = up16((uint32_t)T * pl.span_max + 32);
+            pl.sm_tile_bytes = up16((uint32_t)T * pl.span_max + 64); // + alignment slop + word-granular look-ahead
             pl.sm_listv = pl.sm_tile + pl.sm_tile_bytes;
             pl.sm_listp = pl.sm_listv + up16((uint32_t)T * (aa_stride + ring_per_thread));
             pl.sm_total = pl.sm_listp;

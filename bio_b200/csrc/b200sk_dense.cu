@@ -16,7 +16,8 @@ namespace b200sk {
 
 #define DENSE_S 16                          /* steps staged per lane between flushes */
 #define DENSE_ROW (DENSE_S * 8 + 8)         /* bytes per lane row (+8: rows land on different banks) */
-#define DENSE_WARP_STAGE (32 * DENSE_ROW)   /* one staging area per warp (two for both-strand k-mers) */
+#define DENSE_WARP_STAGE (32 * DENSE_ROW + 512) /* one staging area per warp (two for both-strand k-mers): 32 rows +
+                                                   32 x 16 B of per-lane flush descriptors */
 
 // ------------------------------------------------------------------ 2-bit base code, pair letters
 // sketches/kmers.go:23-40 (IUPAC codes map to their first base; 4 = illegal)
@@ -105,25 +106,48 @@ cudaError_t launch_translate(const uint8_t *bases, const uint64_t *off, const ui
     return cudaGetLastError();
 }
 
+// N consecutive bytes starting at an arbitrary shared-memory address, fetched as aligned 32-bit words
+template <int N> struct ByteWords {
+    static constexpr int NWORD = (N + 3 + 3) / 4;
+    static constexpr int NG = (N + 3) / 4;
+    uint32_t x[NG];
+    __device__ __forceinline__ void load(const uint8_t *p) {
+        const uint32_t phi = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(p - phi);
+        const uint32_t sel = 0x3210u + 0x1111u * phi;
+        uint32_t w[NWORD + 1];
+#pragma unroll
+        for (int i = 0; i < NWORD; i++) w[i] = a[i];
+        w[NWORD] = 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) x[g] = __byte_perm(w[g], w[g + 1 < NWORD ? g + 1 : NWORD], sel);
+    }
+    __device__ __forceinline__ uint32_t byte(const int j) const { return __byte_perm(x[j >> 2], 0u, 0x4440u | (j & 3)); }
+};
+
 // ------------------------------------------------------------------ staged, coalesced output
 // Each lane filled `n` (<= 16) entries of its row; entry e goes to out[b + d*e] (d = +1, or -1 for the
 // second strand of both-strand k-mers), position p0 + d*e.  Two lanes' rows leave per iteration.
-__device__ __forceinline__ void flush_rows(const uint8_t *stage, uint64_t *out_val, void *out_pos, uint32_t pw,
+__device__ __forceinline__ void flush_rows(uint8_t *stage, uint64_t *out_val, void *out_pos, uint32_t pw,
                                            uint64_t b, uint32_t n, int d, uint32_t p0, unsigned lane) {
+    // every lane publishes where its row goes; the copy loop then reads the two rows' descriptors with one
+    // broadcast LDS.128 each (cheaper on the shared-memory pipe than four shuffles per iteration)
+    uint4 *info = reinterpret_cast<uint4 *>(stage + 32 * DENSE_ROW);
+    info[lane] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), n | (d < 0 ? 0x80000000u : 0u), p0);
     __syncwarp();
 #pragma unroll 4
     for (int j = 0; j < 32; j += 2) {
         const int src = j + (int)(lane >> 4);
         const uint32_t e = lane & 15u;
-        const uint64_t bb = __shfl_sync(0xffffffffu, b, src);
-        const uint32_t nn = __shfl_sync(0xffffffffu, n, src);
-        const int dd = __shfl_sync(0xffffffffu, d, src);
-        const uint32_t pp = __shfl_sync(0xffffffffu, p0, src);
+        const uint4 inf = info[src];
+        const uint32_t nn = inf.z & 0x7fffffffu;
         if (e < nn) {
             const uint64_t v = *reinterpret_cast<const uint64_t *>(stage + src * DENSE_ROW + e * 8);
-            const uint64_t idx = bb + (uint64_t)((int64_t)dd * (int64_t)e);
+            const uint64_t bb = ((uint64_t)inf.y << 32) | inf.x;
+            const bool neg = (inf.z >> 31) != 0;
+            const uint64_t idx = neg ? bb - e : bb + e;
             out_val[idx] = v;
-            if (out_pos) store_pos(out_pos, pw, idx, pp + (uint32_t)(dd * (int)e));
+            if (out_pos) store_pos(out_pos, pw, idx, neg ? inf.w - e : inf.w + e);
         }
     }
     __syncwarp();
@@ -318,14 +342,24 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     fh = rol1(fh) ^ e.x;
                     rh = ror1(rh) ^ e.y;
                 }
+            const uint8_t *sbs = nstep ? sb : tilebuf + 4;                          // a safe base for idle lanes
+            const uint32_t last_block = nstep ? ((nstep - 1) / DENSE_S) * DENSE_S : 0u; // first step of the last block
+            // the 16 incoming and 16 outgoing bases of a staging block are fetched as aligned words
+            // (ByteWords), a quarter of the shared-memory wavefronts of byte loads
             for (uint32_t u0 = 0; u0 < maxn; u0 += DENSE_S) {
-#pragma unroll 4
+                // lanes whose item is already finished (or absent) re-read their own last block: the loads stay
+                // unconditional (schedulable) and inside the tile
+                ByteWords<DENSE_S> win, wout;
+                const uint32_t ul = min(u0, last_block);
+                win.load(sbs + ul + k - 1);
+                wout.load(sbs + ul - 1);
+#pragma unroll
                 for (uint32_t e = 0; e < DENSE_S; e++) {
                     const uint32_t u = u0 + e;
                     if (u < nstep) {
-                        const ulonglong2 in = tIn[sb[u + k - 1]];
+                        const ulonglong2 in = tIn[win.byte(e)];
                         ulonglong2 o = make_ulonglong2(0, 0);
-                        if (u) o = tOut[sb[u - 1]];
+                        if (u) o = tOut[wout.byte(e)];
                         fh = rol1(fh) ^ o.x ^ in.x;
                         rh = ror1(rh) ^ o.y ^ in.y;
                         *reinterpret_cast<uint64_t *>(row + e * 8) = (canonical && rh < fh) ? rh : fh; // iterator.go:659
