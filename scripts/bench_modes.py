@@ -12,7 +12,7 @@ PEAK = 6448.1
 
 
 def run(name, p, bases, off, nb, n, steps=5, frames=None):
-    cap = int(cabi.lib().b200sk_output_bound(ctypes.byref(p), nb, n, 1 if p.mode in (0, 1, 4) else 0))
+    cap = int(cabi.lib().b200sk_output_bound(ctypes.byref(p), nb, n, 1 if p.mode in (0, 1, 4, 6) else 0))
     val = torch.empty(cap, dtype=torch.int64, device=dev)
     pos = torch.empty(cap, dtype=torch.int32, device=dev) if p.want_pos else None
     ooff = torch.empty(n + 1, dtype=torch.int64, device=dev)
@@ -44,6 +44,8 @@ run("C2 ntHash k=21 canonical, 10M x 150bp (values only)", cabi.make_params(cabi
 run("C3-geometry minimizer k=21 w=11, 10M x 150bp", cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150), bases, off, nb, n)
 run("syncmer k=21 s=11, 10M x 150bp", cabi.make_params(cabi.MODE_SYNCMER, 21, s=11, max_read_len=150), bases, off, nb, n)
 run("C1-geometry k-mer codes k=21 canonical, 10M x 150bp (values only)", cabi.make_params(cabi.MODE_KMER, 21, max_read_len=150, want_pos=False), bases, off, nb, n)
+run("SimHash k=31 m=5 scale=5, 10M x 150bp (values only)", cabi.make_params(cabi.MODE_SIMHASH, 31, m=5, scale=5, max_read_len=150, want_pos=False), bases, off, nb, n)
+run("ProteinMinimizer k=10 w=5 frame 1, 10M x 150bp", cabi.make_params(cabi.MODE_PROTEIN_MINIMIZER, 10, w=5, frame=1, max_read_len=150), bases, off, nb, n)
 for fr in (1, 2, 3, -1, -2, -3):
     run(f"C5 protein k=11 frame {fr}, 10M x 150bp (values only)", cabi.make_params(cabi.MODE_PROTEIN, 11, frame=fr, max_read_len=150, want_pos=False), bases, off, nb, n)
 del bases, off
