@@ -183,7 +183,8 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     if (pl.dense) {
         // tables 8 KB + control, per-warp output staging (two areas for both-strand k-mers), tile,
         // per-thread amino-acid buffers (protein)
-        const uint32_t stage_w = (mode == B200SK_MODE_KMER ? 2u : 1u) * (32u * (16u * 8u + 8u) + 512u);
+        const uint32_t kDenseS = mode == B200SK_MODE_KMER ? 8 : 16; // must match DENSE_S in b200sk_dense.cu
+        const uint32_t stage_w = (mode == B200SK_MODE_KMER ? 2u : 1u) * (32u * (kDenseS * 8u + 8u) + 512u);
         uint32_t aa_stride = 0;
         if (mode == B200SK_MODE_PROTEIN) {
             aa_stride = ((pl.C + (uint32_t)k - 1 + 3) / 4) | 1u; // odd number of words: conflict-free columns
@@ -194,7 +195,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         if (mode == B200SK_MODE_SIMHASH) ring_per_thread = (uint32_t)(k - w + 1) * 8u;
         for (int T : {128, 64, 32}) {
             pl.T = T;
-            pl.sm_ring = 8192 + 256;
+            pl.sm_ring = 8192 + 768; // byte tables, control block, pair tables
             pl.sm_ring_bytes = (uint32_t)(T / 32) * stage_w;
             pl.sm_tile = pl.sm_ring + pl.sm_ring_bytes;
             pl.sm_tile_bytes = up16((uint32_t)T * pl.span_max + 64); // + alignment slop + word-granular look-ahead

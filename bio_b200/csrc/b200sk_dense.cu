@@ -14,7 +14,10 @@
 
 namespace b200sk {
 
-#define DENSE_S 16                          /* steps staged per lane between flushes */
+// steps staged per lane between flushes: 16 (128-byte runs) except both-strand k-mers, which keep two
+// staging areas per warp and gain more from the occupancy of 8-step rows.  Must match dense_steps() in
+// b200sk_api.cu.
+#define DENSE_S (MODE == B200SK_MODE_KMER ? 8 : 16)
 #define DENSE_ROW (DENSE_S * 8 + 8)         /* bytes per lane row (+8: rows land on different banks) */
 #define DENSE_WARP_STAGE (32 * DENSE_ROW + 512) /* one staging area per warp (two for both-strand k-mers): 32 rows +
                                                    32 x 16 B of per-lane flush descriptors */
@@ -128,6 +131,7 @@ template <int N> struct ByteWords {
 // ------------------------------------------------------------------ staged, coalesced output
 // Each lane filled `n` (<= 16) entries of its row; entry e goes to out[b + d*e] (d = +1, or -1 for the
 // second strand of both-strand k-mers), position p0 + d*e.  Two lanes' rows leave per iteration.
+template <int MODE>
 __device__ __forceinline__ void flush_rows(uint8_t *stage, uint64_t *out_val, void *out_pos, uint32_t pw,
                                            uint64_t b, uint32_t n, int d, uint32_t p0, unsigned lane) {
     // every lane publishes where its row goes; the copy loop then reads the two rows' descriptors with one
@@ -135,10 +139,11 @@ __device__ __forceinline__ void flush_rows(uint8_t *stage, uint64_t *out_val, vo
     uint4 *info = reinterpret_cast<uint4 *>(stage + 32 * DENSE_ROW);
     info[lane] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), n | (d < 0 ? 0x80000000u : 0u), p0);
     __syncwarp();
+    constexpr int ROWS = 32 / DENSE_S; // rows that leave per iteration, DENSE_S lanes each
 #pragma unroll 4
-    for (int j = 0; j < 32; j += 2) {
-        const int src = j + (int)(lane >> 4);
-        const uint32_t e = lane & 15u;
+    for (int j = 0; j < 32; j += ROWS) {
+        const int src = j + (int)(lane / DENSE_S);
+        const uint32_t e = lane % DENSE_S;
         const uint4 inf = info[src];
         const uint32_t nn = inf.z & 0x7fffffffu;
         if (e < nn) {
@@ -263,6 +268,17 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
             tIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(hk - 1)));
             tOut[b] = make_ulonglong2(rol64(f, (unsigned)hk), ror64(r, 1));
         }
+        if (MODE == B200SK_MODE_NTHASH && tid < 20) { // pair tables of the all-ACGT fast path
+            const char letter[4] = {'A', 'C', 'T', 'G'}; // class = (byte >> 1) & 3
+            const uint32_t ci = tid & 3u, co = tid >> 2;
+            uint64_t x = fwd_seed((uint32_t)letter[ci]), y = rol64(rev_seed((uint32_t)letter[ci]), (unsigned)(k - 1));
+            if (co < 4) {
+                x ^= rol64(fwd_seed((uint32_t)letter[co]), (unsigned)k);
+                y ^= ror64(rev_seed((uint32_t)letter[co]), 1);
+            }
+            reinterpret_cast<uint64_t *>(smem + 8192 + 256)[tid] = x;
+            reinterpret_cast<uint64_t *>(smem + 8192 + 256 + 160)[tid] = y;
+        }
     } else if (MODE == B200SK_MODE_KMER) {
         for (uint32_t b = tid; b < 256; b += T) {
             const uint32_t bit = base2bit_of(b);
@@ -325,6 +341,40 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
             mbar_wait(&ctl->mbar, parity);
             parity ^= 1u;
         }
+        // ntHash fast path: when every byte of the tile is one of ACGTacgt the bytes are rewritten as 2-bit
+        // classes (a=0 c=1 t=2 g=3) and each step needs ONE pair-table lookup per strand instead of two
+        // 16-byte lookups.  Any other byte: the tile is fetched again and walks the general 256-entry tables.
+        bool fast = false;
+        if (MODE == B200SK_MODE_NTHASH && bytes && span_ok) {
+            uint32_t bad = 0;
+            for (uint32_t o = tid * 16u; o < bytes; o += T * 16u) {
+                uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t x = w[i] | 0x20202020u;             // lower case
+                    const uint32_t t = (x >> 1) & 0x03030303u;         // class of every byte
+                    const uint32_t u2 = t | (t >> 4);                  // nibble pairs in bytes 0 and 2
+                    const uint32_t sel = __byte_perm(u2, 0u, 0x4420u); // four nibbles = PRMT selector
+                    const uint32_t want = __byte_perm(0x67746361u, 0u, sel); // 'a','c','t','g' by class
+                    bad |= x ^ want;
+                    w[i] = t;
+                }
+                *reinterpret_cast<uint4 *>(tilebuf + o) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            // bytes outside [lo, hi) (alignment slop) may be anything: only the tile's own range decides.
+            // Slop bytes belong to neighbouring reads or padding; a false alarm only costs the slow path.
+            fast = __syncthreads_or(bad) == 0;
+            if (!fast) {
+                if (tid == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&ctl->mbar, bytes);
+                    tma_load_1d(tilebuf, a.bases + lo_al, bytes, &ctl->mbar);
+                }
+                mbar_wait(&ctl->mbar, parity);
+                parity ^= 1u;
+            }
+        }
         const uint32_t nstep = span_ok ? it.nstep : 0u;
         const uint8_t *sb = tilebuf + (uint32_t)(it.gb0 - lo_al);
         // warp-uniform trip count
@@ -336,13 +386,46 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
             const ulonglong2 *tIn = reinterpret_cast<const ulonglong2 *>(tab), *tOut = tIn + 256;
             const bool canonical = a.canonical != 0;
             uint64_t fh = 0, rh = 0;
-            if (nstep)
+            if (nstep && !fast)
                 for (int j = 0; j < k - 1; j++) {
                     const ulonglong2 e = tIn[sb[j]];
                     fh = rol1(fh) ^ e.x;
                     rh = ror1(rh) ^ e.y;
                 }
             const uint8_t *sbs = nstep ? sb : tilebuf + 4;                          // a safe base for idle lanes
+            if (fast) {
+                // pair tables: X[cin + 4 cout] = A[in] ^ rol(A[out], k), Y = rol(B[in], k-1) ^ ror(B[out], 1);
+                // cout = 4: no outgoing base (the folds of the first k-mer)
+                const uint8_t *tX = smem + 8192 + 256, *tY = tX + 160; // 20 x 8 B each, after the control block
+                if (nstep)
+                    for (int j = 0; j < k - 1; j++) {
+                        const uint32_t o8 = (uint32_t)sb[j] * 8u + 128u;
+                        fh = rol1(fh) ^ *reinterpret_cast<const uint64_t *>(tX + o8);
+                        rh = ror1(rh) ^ *reinterpret_cast<const uint64_t *>(tY + o8);
+                    }
+                const uint32_t last_block = nstep ? ((nstep - 1) / DENSE_S) * DENSE_S : 0u;
+                for (uint32_t u0 = 0; u0 < maxn; u0 += DENSE_S) {
+                    ByteWords<DENSE_S> win, wout;
+                    const uint32_t ul = min(u0, last_block);
+                    win.load(sbs + ul + k - 1);
+                    wout.load(sbs + ul - 1);
+#pragma unroll
+                    for (uint32_t e = 0; e < DENSE_S; e++) {
+                        const uint32_t u = u0 + e;
+                        if (u < nstep) {
+                            const uint32_t co = (e == 0 && u0 == 0) ? 4u : wout.byte(e);
+                            const uint32_t o8 = win.byte(e) * 8u + co * 32u;
+                            fh = rol1(fh) ^ *reinterpret_cast<const uint64_t *>(tX + o8);
+                            rh = ror1(rh) ^ *reinterpret_cast<const uint64_t *>(tY + o8);
+                            *reinterpret_cast<uint64_t *>(row + e * 8) = (canonical && rh < fh) ? rh : fh;
+                        }
+                    }
+                    const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
+                    flush_rows<MODE>(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
+                }
+                __syncthreads();
+                continue;
+            }
             const uint32_t last_block = nstep ? ((nstep - 1) / DENSE_S) * DENSE_S : 0u; // first step of the last block
             // the 16 incoming and 16 outgoing bases of a staging block are fetched as aligned words
             // (ByteWords), a quarter of the shared-memory wavefronts of byte loads
@@ -366,7 +449,7 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
+                flush_rows<MODE>(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
             }
         } else if (MODE == B200SK_MODE_KMER) {
             // iterator.go:736,740,754: code = (pre & mask1) << 2 | bit; rc = (bit ^ 3) << 2(k-1) | preRC >> 2.
@@ -398,11 +481,11 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
+                flush_rows<MODE>(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
                 // strand 2: k-mer i = p0+u0+e lands at out_off[r] + np + (np-1-i), position np-1-i
                 const uint32_t i0 = it.p0 + u0;
                 const uint64_t b2 = it.obase - it.p0 + 2ull * it.np - 1 - i0;
-                flush_rows(stage + DENSE_WARP_STAGE, a.out_val, a.out_pos, a.pos_width, b2, it.both ? n : 0u, -1,
+                flush_rows<MODE>(stage + DENSE_WARP_STAGE, a.out_val, a.out_pos, a.pos_width, b2, it.both ? n : 0u, -1,
                            it.np - 1 - i0, lane);
             }
         } else if (MODE == B200SK_MODE_SIMHASH) {
@@ -463,7 +546,7 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t nn = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, nn, 1, it.p0 + u0, lane);
+                flush_rows<MODE>(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, nn, 1, it.p0 + u0, lane);
             }
         } else { // PROTEIN
             uint8_t *aab = smem + a.sm_listv + tid * a.lcap; // lcap = per-thread amino-acid buffer stride
@@ -495,7 +578,7 @@ __global__ void __launch_bounds__(128) k_dense(const KArgs a) {
                     }
                 }
                 const uint32_t n = u0 < nstep ? min((uint32_t)DENSE_S, nstep - u0) : 0u;
-                flush_rows(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
+                flush_rows<MODE>(stage, a.out_val, a.out_pos, a.pos_width, it.obase + u0, n, 1, it.p0 + u0, lane);
             }
         }
         __syncthreads();
