@@ -1,6 +1,6 @@
 """Print instruction mix of the hot loop(s) of a kernel in the built library (dev helper)."""
 import collections, re, subprocess, sys
-lib = "bio_b200/lib/libb200sketch.so"
+lib = sys.argv[3] if len(sys.argv) > 3 else "bio_b200/lib/libb200sketch.so"
 pat = sys.argv[1]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", out)
@@ -23,12 +23,13 @@ for f in funcs[1:]:
                 j = addr[tgt]
                 body = [x[1] for x in ins[j:i + 1]]
                 l128 = sum("LDS.128" in b for b in body)
-                if l128 >= 4 and len(body) < 2500:
+                if (l128 >= 4 or sum("LDS.64" in b for b in body) >= 8) and len(body) < 2500:
                     c = collections.Counter()
                     for b in body:
                         op = b.split()[1] if b.startswith("@") else b.split()[0]
                         c[op.split(".")[0]] += 1
-                    print(f" loop {j}-{i} len {len(body)} LDS.128={l128} per-step={len(body) / (l128 / 2):.1f}")
+                    l64 = sum("LDS.64" in b for b in body)
+                    print(f" loop {j}-{i} len {len(body)} LDS.128={l128} LDS.64={l64}")
                     print("  ", c.most_common())
                     if len(sys.argv) > 2:
                         print("\n".join(body[: int(sys.argv[2])]))
