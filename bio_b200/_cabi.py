@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200sketch.so")
+LIB_PATH = os.environ.get("B200SK_LIB_PATH") or os.path.join(_HERE, "lib", "libb200sketch.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0

@@ -160,9 +160,6 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     const uint64_t ext = p.circular ? (uint64_t)(k - 1) : 0;
     if (max_len) max_len += ext;
     pl.chunked = !(max_len && max_len <= kSingleMaxLen);
-    // the register-window kernels stage an element's stream index inside its item as one byte
-    const bool reg_ok = (mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER) && sparse_reg_supported(mode, k, w, s);
-    if (reg_ok && max_len > 255 + (uint64_t)(mode == B200SK_MODE_SYNCMER ? s : k)) pl.chunked = true;
     if (!pl.chunked) {
         int32_t st;
         ReadGeom g;
@@ -218,21 +215,20 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
     }
     pl.reg = sparse && sparse_reg_supported(mode, k, w, s);
     if (pl.reg) {
-        // one tile per warp.  tables (2 KB + 1 KB fast tables; syncmer 3.5 KB + 1 KB), then per warp:
-        // mbarrier 16 B, tile, k-mer ring (syncmer), lists of (lcap+1) slots x (32 lanes x 8 B value + 8 B
-        // padding) and x 32 lanes x 1 B stream index.
+        // one tile per warp.  tables 4 KB, then per warp: mbarrier 16 B, tile, k-mer ring (syncmer),
+        // lists of (lcap+1) slots x 32 lanes x (8 B value + 1 B position delta).
         int best_nw = 0;
         Plan best = pl;
         for (uint32_t shave = 0; shave <= 2 && shave + 8 < pl.lcap; shave++) {
             Plan c = pl;
             c.lcap = pl.lcap - shave;
-            c.sm_tile = mode == B200SK_MODE_SYNCMER ? 3584u + 1024u : 2048u + 1024u;
+            c.sm_tile = 4096;
             c.sm_tile_bytes = up16(32u * c.span_max + 32);
             c.sm_ring = 16 + c.sm_tile_bytes;
             c.sm_listv = c.sm_ring + (uint32_t)d * 256u;
-            c.sm_listp = c.sm_listv + (c.lcap + 1) * 264u; // LIST_VSTRIDE in b200sk_sparse_reg.cu
+            c.sm_listp = c.sm_listv + (c.lcap + 1) * 256u;
             c.sm_ring_bytes = up16(c.sm_listp + (c.lcap + 1) * 32u); // per-warp stride
-            int nw = (int)((kSmemLimit - c.sm_tile) / c.sm_ring_bytes);
+            int nw = (int)((232448u - 1024u - c.sm_tile) / c.sm_ring_bytes);
             if (nw > 16) nw = 16;
             if (nw < 1) continue;
             c.T = nw * 32;

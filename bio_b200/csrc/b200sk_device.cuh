@@ -133,49 +133,6 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint64_t
     return excl;
 }
 
-// The same in two halves, so that work which does not need the prefix can sit between them: publish the
-// tile's own total first (later tiles can already add it up), resolve the exclusive prefix afterwards.
-// The spin on a tile that has not published yet backs off with nanosleep: a spinning warp otherwise takes
-// issue slots from the warps it is waiting for.
-__device__ __forceinline__ void lookback_publish(uint64_t *state, uint64_t tile, uint64_t total) {
-    if ((threadIdx.x & 31u) == 0)
-        st_state(state + tile, ((tile == 0 ? B200SK_FLAG_INC : B200SK_FLAG_AGG) << 62) | total);
-}
-__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t tile, uint64_t total) {
-    const unsigned lane = threadIdx.x & 31u;
-    if (tile == 0) return 0;
-    uint64_t excl = 0;
-    int64_t idx = (int64_t)tile - 1 - (int64_t)lane;
-    while (true) {
-        // the 32 predecessors idx .. idx-31, polled by the whole warp together (one uniform loop: per-lane
-        // spin loops would be executed one lane after the other)
-        uint64_t v;
-        for (;;) {
-            v = idx >= 0 ? ld_state(state + idx) : (B200SK_FLAG_INC << 62); // before tile 0: "inclusive 0"
-            // tiles further back than the nearest inclusive one do not matter
-            const unsigned incb = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
-            const unsigned emp = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_EMPTY);
-            const unsigned need = incb ? ((2u << (__ffs(incb) - 1)) - 1u) : 0xffffffffu;
-            if ((emp & need) == 0) break;
-            // no back-off: every nanosecond between a predecessor's publication and its detection is idle
-            // time of this warp, and one poll is one L2 round trip (a handful of instructions per ~0.5 us)
-        }
-        const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
-        uint64_t contrib = v & B200SK_VAL_MASK;
-        if (inc) {
-            const unsigned first = __ffs(inc) - 1;
-            if (lane > first) contrib = 0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl += contrib;
-        if (inc) break;
-        idx -= 32;
-    }
-    if (lane == 0) st_state(state + tile, (B200SK_FLAG_INC << 62) | (excl + total));
-    return excl;
-}
-
 // Block-wide exclusive scan of one uint32 per thread (blockDim.x <= 1024, multiple of 32).
 // warp_sums: shared scratch of >= 33 uint32.  Returns exclusive prefix; *block_total = sum.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t *block_total) {

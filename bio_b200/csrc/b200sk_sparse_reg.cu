@@ -90,18 +90,14 @@ __device__ __forceinline__ void suffix_step(uint64_t &h, uint32_t &ph, uint32_t 
 __device__ __forceinline__ uint64_t min_u64(uint64_t a, uint64_t b) { return mux64(lt_mask(a, b), a, b); }
 
 // ------------------------------------------------------------------ sinks
-// emit_if(p, v, rel): record (v, rel) when p; rel = stream index of the element inside the item (< 256).
-// The slot address and the operands are computed unconditionally; only the two stores and the counter
-// depend on p and they are PREDICATED, not branched around (some lane of a warp emits on almost every step).
-// Value slots are LIST_VSTRIDE = 264 bytes apart (32 lanes x 8 B + 8 B of padding): the per-step store of
-// a warp (one slot per lane) and the flush's column read (one lane's list, a slot per thread) are both
-// at most 2-way bank conflicted.
-#define LIST_VSTRIDE 264u
+// emit_if(p, v, delta): record (v, delta) when p.  The slot address and the operands are computed
+// unconditionally; only the two stores and the counter depend on p and they are PREDICATED, not branched
+// around (some lane of a warp emits on almost every step).
 struct ListSink { // staged in shared memory, [slot][lane]; slot `cap` is a scratch slot for overflow
     uint32_t av, ap, cap, cnt; // av/ap: 32-bit shared-window addresses of this lane's slot 0
     __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t delta) {
         const uint32_t slot = min(cnt, cap);
-        const uint32_t ov = av + slot * LIST_VSTRIDE, op = ap + slot * 32u; // 32 lanes x 8 B (+pad) / x 1 B per slot
+        const uint32_t ov = av + slot * 256u, op = ap + slot * 32u; // 32 lanes x 8 B / x 1 B per slot
         asm volatile(
             "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q st.shared.u64 [%2], %3;\n\t"
             "@q st.shared.u8 [%4], %5;\n\t@q add.u32 %0, %0, 1;\n\t}"
@@ -113,12 +109,13 @@ struct GlobalSink { // straight to the final position (tiles where some item ove
     uint64_t *gv;
     void *gp; // out_pos array (whole), element index gi + n
     uint64_t gi;
-    uint32_t pw, pos, cnt, skip; // pos: read-relative position of the item's stream element 0
-    __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t rel) {
+    uint32_t pw, pos, cnt, skip;
+    __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t delta) {
         if (pred) {
+            pos += delta;
             if (cnt >= skip) {
                 gv[cnt - skip] = v;
-                if (gp) store_pos(gp, pw, gi + cnt - skip, pos + rel);
+                if (gp) store_pos(gp, pw, gi + cnt - skip, pos);
             }
             cnt++;
         }
@@ -201,173 +198,63 @@ template <int W> struct CodeWords {
 };
 #define B200SK_TAB(tab, c) lds_v2u64(sm, (tab) + (c) * 16u)
 
-// ------------------------------------------------------------------ all-ACGT fast path
-// When every byte of a tile is one of ACGTacgt the tile is rewritten as cls * 40 = (cls << 3) | (cls << 5)
-// with cls = (byte >> 1) & 3 (a=0 c=1 t=2 g=3).  (in & 0x18) | (out & 0x60) is then directly the byte
-// offset into 16-entry PAIR tables of 8-byte entries,
-//     X[in, out] = A[in] ^ rol(A[out], h),   Y[in, out] = rol(B[in], h-1) ^ ror(B[out], 1),
-// so a rolling step is ONE table offset (one PRMT), two conflict-free LDS.64 and one three-input XOR per
-// 32-bit half -- against two code extractions, two address multiplies, two LDS.128 and two more XORs per
-// half with the general 64-entry tables.  The k-1 (s-1) initial folds go two bases at a time through
-//     F2X[c0, c1] = rol(A[c0], 1) ^ A[c1],   F2Y[c0, c1] = ror(RB[c0], 1) ^ RB[c1],   RB[c] = rol(B[c], h-1).
-// Fast-table block (byte offsets from its base FT): X 0, Y 128, F2X 256, F2Y 384, F1X 512 (A[c], 4 entries),
-// F1Y 544 (RB[c]); syncmer k-mer hasher: XK 576, YK 704, F2YK 832, F1YK 960.  992 bytes.
-#define FT_X 0u
-#define FT_Y 128u
-#define FT_F2X 256u
-#define FT_F2Y 384u
-#define FT_F1X 512u
-#define FT_F1Y 544u
-#define FT_XK 576u
-#define FT_YK 704u
-#define FT_F2YK 832u
-#define FT_F1YK 960u
-#define FT_BYTES 1024u
-__device__ __forceinline__ uint64_t lds_u64(const uint8_t *sm, uint32_t o) {
-    return *reinterpret_cast<const uint64_t *>(sm + o);
-}
-__device__ __forceinline__ void build_fast_tables(uint8_t *ft, uint32_t t, int h, int kk, bool sync) {
-    if (t >= 16) return;
-    const char letter[4] = {'A', 'C', 'T', 'G'}; // class = (byte >> 1) & 3
-    const uint32_t lo = t & 3u, hi = t >> 2;
-    const uint64_t Alo = fwd_seed((uint32_t)letter[lo]), Ahi = fwd_seed((uint32_t)letter[hi]);
-    const uint64_t Blo = rev_seed((uint32_t)letter[lo]), Bhi = rev_seed((uint32_t)letter[hi]);
-    uint64_t *q = reinterpret_cast<uint64_t *>(ft);
-    q[FT_X / 8 + t] = Alo ^ rol64(Ahi, (unsigned)h);
-    q[FT_Y / 8 + t] = rol64(Blo, (unsigned)(h - 1)) ^ ror64(Bhi, 1);
-    q[FT_F2X / 8 + t] = rol64(Alo, 1) ^ Ahi;
-    q[FT_F2Y / 8 + t] = ror64(rol64(Blo, (unsigned)(h - 1)), 1) ^ rol64(Bhi, (unsigned)(h - 1));
-    if (t < 4) {
-        q[FT_F1X / 8 + t] = Alo;
-        q[FT_F1Y / 8 + t] = rol64(Blo, (unsigned)(h - 1));
-    }
-    if (sync) {
-        q[FT_XK / 8 + t] = Alo ^ rol64(Ahi, (unsigned)kk);
-        q[FT_YK / 8 + t] = rol64(Blo, (unsigned)(kk - 1)) ^ ror64(Bhi, 1);
-        q[FT_F2YK / 8 + t] = ror64(rol64(Blo, (unsigned)(kk - 1)), 1) ^ rol64(Bhi, (unsigned)(kk - 1));
-        if (t < 4) q[FT_F1YK / 8 + t] = rol64(Blo, (unsigned)(kk - 1));
-    }
-}
-// ASCII word -> four fast-path bytes; bad accumulates a non-zero value when a byte is not one of ACGTacgt
-__device__ __forceinline__ uint32_t fast_word(uint32_t w, uint32_t &bad) {
-    const uint32_t x = w | 0x20202020u;                       // lower case
-    const uint32_t t = (x >> 1) & 0x03030303u;                // class of every byte
-    const uint32_t u2 = t | (t >> 4);                         // nibble pairs in bytes 0 and 2
-    const uint32_t sel = __byte_perm(u2, 0u, 0x4420u);        // four nibbles = PRMT selector
-    bad |= x ^ __byte_perm(0x67746361u, 0u, sel);             // 'a','c','t','g' by class
-    return t * 40u;
-}
-// pair-table offsets of one block of W steps: in bytes from pin, out bytes from pout
-template <int W> struct PairWords {
-    static constexpr int NWORD = (W + 3 + 3) / 4, NG = (W + 3) / 4;
-    uint32_t x[NG];
-    __device__ __forceinline__ void load(const uint8_t *sm, uint32_t pin, uint32_t pout) {
-        const uint32_t ai = pin & ~3u, ao = pout & ~3u;
-        const uint32_t si = 0x3210u + 0x1111u * (pin & 3u), so = 0x3210u + 0x1111u * (pout & 3u);
-        uint32_t wi[NWORD + 1], wo[NWORD + 1];
-#pragma unroll
-        for (int i = 0; i < NWORD; i++) {
-            wi[i] = *reinterpret_cast<const uint32_t *>(sm + ai + 4u * i);
-            wo[i] = *reinterpret_cast<const uint32_t *>(sm + ao + 4u * i);
-        }
-        wi[NWORD] = 0; wo[NWORD] = 0;
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const int g1 = g + 1 < NWORD ? g + 1 : NWORD;
-            x[g] = (__byte_perm(wi[g], wi[g1], si) & 0x18181818u) | (__byte_perm(wo[g], wo[g1], so) & 0x60606060u);
-        }
-    }
-    __device__ __forceinline__ uint32_t off(const int j) const { return __byte_perm(x[j >> 2], 0u, 0x4440u | (j & 3)); }
-};
-// the h-1 initial folds of a hasher over fast-path bytes starting at shared offset sb
-__device__ __forceinline__ void fast_fold(const uint8_t *sm, uint32_t ft, uint32_t sb, int n, uint64_t &f, uint64_t &r) {
-    int j = 0;
-    for (; j + 1 < n; j += 2) {
-        const uint32_t o = (lds_u8(sm, sb + j) & 0x18u) | (lds_u8(sm, sb + j + 1) & 0x60u);
-        f = rol64(f, 2) ^ lds_u64(sm, ft + FT_F2X + o);
-        r = ror64(r, 2) ^ lds_u64(sm, ft + FT_F2Y + o);
-    }
-    if (j < n) {
-        const uint32_t o = lds_u8(sm, sb + j) & 0x18u;
-        f = rol1(f) ^ lds_u64(sm, ft + FT_F1X + o);
-        r = ror1(r) ^ lds_u64(sm, ft + FT_F1Y + o);
-    }
-}
-
 // NextMinimizer (sketch.go:205-309) over one item; its codes start at shared offset sb.
-// FAST: the tile holds fast-path bytes and ft is the fast-table block; else 6-bit codes and tabIn/tabOut.
-template <int W, bool FAST, class SinkT>
+template <int W, class SinkT>
 __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t sb, uint32_t nstep, int k,
                                                    uint32_t w_runtime, uint32_t tabIn, uint32_t tabOut,
-                                                   uint32_t ft, SinkT &sink) {
+                                                   SinkT &sink) {
     Roll h;
     h.f = 0; h.r = 0;
-    if (FAST) fast_fold(sm, ft, sb, k - 1, h.f, h.r);
-    else
-        for (int j = 0; j < k - 1; j++) h.fold(B200SK_LD128(tabIn, sb + j));
+    for (int j = 0; j < k - 1; j++) h.fold(B200SK_LD128(tabIn, sb + j));
     WinReg<W> wm;
     wm.init(w_runtime);
     uint32_t prev = W - 1; // frame-relative position of the previous window's minimum (none yet)
-    uint32_t fb = 0u - (uint32_t)W; // stream index of the frame's position 0
     uint32_t pin = sb + (uint32_t)k - 1; // incoming code of step 0
     uint32_t pout = sb - 1;              // outgoing code of step j is pout + j (step 0 has none)
     uint64_t mv;
     uint32_t mu;
-    CodeWords<FAST ? 1 : W> cin, cout;
-    PairWords<FAST ? W : 1> pw;
-#define B200SK_LOAD_BLOCK()                                                \
-    if (FAST) pw.load(sm, pin, pout);                                      \
-    else { cin.load(sm, pin); cout.load(sm, pout); }
-#define B200SK_ROLL(J)                                                     \
-    if (FAST) {                                                            \
-        const uint32_t o = pw.off(J);                                      \
-        h.f = rol1(h.f) ^ lds_u64(sm, ft + FT_X + o);                      \
-        h.r = ror1(h.r) ^ lds_u64(sm, ft + FT_Y + o);                      \
-    } else h.roll(B200SK_TAB(tabIn, cin.code(J)), B200SK_TAB(tabOut, cout.code(J)));
+    CodeWords<W> cin, cout;
 #define B200SK_MIN_STEP(J, FIRST)                                          \
     if (wm.push(J, FIRST, h.canonical(), mv, mu)) {                        \
-        sink.emit_if(mu != prev, mv, mu + fb); /* sketch.go:297-307 */     \
+        sink.emit_if(mu != prev, mv, mu - prev); /* sketch.go:297-307 */   \
         prev = mu;                                                         \
     }
-    B200SK_LOAD_BLOCK()
-    if (FAST) { // the first k-mer has no outgoing base
-        const uint32_t o = pw.off(0) & 0x18u;
-        h.f = rol1(h.f) ^ lds_u64(sm, ft + FT_F1X + o);
-        h.r = ror1(h.r) ^ lds_u64(sm, ft + FT_F1Y + o);
-    } else h.fold(B200SK_TAB(tabIn, cin.code(0)));
+    cin.load(sm, pin);
+    cout.load(sm, pout);
+    h.fold(B200SK_TAB(tabIn, cin.code(0))); // the first k-mer has no outgoing base
     B200SK_MIN_STEP(0, true)
 #pragma unroll
     for (int j = 1; j < W; j++) {
-        B200SK_ROLL(j)
+        h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
         B200SK_MIN_STEP(j, true)
     }
     wm.close_block();
-    prev -= W; fb += W;
+    prev -= W;
     pin += W; pout += W;
     uint32_t u0 = W;
     while (u0 + W <= nstep) { // full blocks
-        B200SK_LOAD_BLOCK()
+        cin.load(sm, pin);
+        cout.load(sm, pout);
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            B200SK_ROLL(j)
+            h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
             B200SK_MIN_STEP(j, false)
         }
         wm.close_block();
-        prev -= W; fb += W;
+        prev -= W;
         pin += W; pout += W;
         u0 += W;
     }
     const uint32_t rem = nstep - u0; // tail: fewer than W elements left
-    B200SK_LOAD_BLOCK()
+    cin.load(sm, pin);
+    cout.load(sm, pout);
 #pragma unroll
     for (int j = 0; j < W - 1; j++) {
         if ((uint32_t)j >= rem) break;
-        B200SK_ROLL(j)
+        h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
         B200SK_MIN_STEP(j, false)
     }
 #undef B200SK_MIN_STEP
-#undef B200SK_ROLL
-#undef B200SK_LOAD_BLOCK
 }
 
 // NextSyncmer (sketch.go:312-477, bounded closed syncmers, s < k) over one item.  W = 2(k-s): the window of
@@ -375,79 +262,38 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
 // m - idx < k-s, else m - (k-s) (sketch.go:414-420); a k-mer is emitted when b changes and b <= end.
 // The last k-s k-mer hashes wait in a shared-memory ring (slot = position mod (k-s)).
 // tabs: offsets of tInS {A, rolB_{s-1}}, tOutS {rolA_s, rorB_1}, tOutK {rolA_k, rorB_1} (16 B entries) and
-// tInK {rolB_{k-1}} (8 B entries); FAST: the fast-table block ft instead.  lim0 = end - q0 (stream index
-// of the last emittable k-mer).
-template <int W, bool FAST, class SinkT>
+// tInK {rolB_{k-1}} (8 B entries).  lim0 = end - q0 (stream index of the last emittable k-mer).
+template <int W, class SinkT>
 __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint32_t nstep, int s,
                                                  uint32_t w_runtime, uint32_t tInS, uint32_t tOutS, uint32_t tInK,
-                                                 uint32_t tOutK, uint32_t ft, uint32_t kring, int32_t lim0,
-                                                 uint32_t halo, SinkT &sink) {
+                                                 uint32_t tOutK, uint32_t kring, int32_t lim0, uint32_t halo,
+                                                 SinkT &sink) {
     constexpr int D = W / 2;
     Roll hs_, hk_; // s-mer and k-mer hashers
     hs_.f = hs_.r = hk_.f = hk_.r = 0;
-    if (FAST) {
-        int j = 0;
-        for (; j + 1 < s - 1; j += 2) {
-            const uint32_t o = (lds_u8(sm, sb + j) & 0x18u) | (lds_u8(sm, sb + j + 1) & 0x60u);
-            const uint64_t x = lds_u64(sm, ft + FT_F2X + o);
-            hs_.f = rol64(hs_.f, 2) ^ x;
-            hs_.r = ror64(hs_.r, 2) ^ lds_u64(sm, ft + FT_F2Y + o);
-            hk_.r = ror64(hk_.r, 2) ^ lds_u64(sm, ft + FT_F2YK + o);
-        }
-        if (j < s - 1) {
-            const uint32_t o = lds_u8(sm, sb + j) & 0x18u;
-            hs_.f = rol1(hs_.f) ^ lds_u64(sm, ft + FT_F1X + o);
-            hs_.r = ror1(hs_.r) ^ lds_u64(sm, ft + FT_F1Y + o);
-            hk_.r = ror1(hk_.r) ^ lds_u64(sm, ft + FT_F1YK + o);
-        }
-        hk_.f = hs_.f; // both hashers fold the same bases with the same forward seeds
-    } else
-        for (int j = 0; j < s - 1; j++) {
-            const uint32_t c = lds_u8(sm, sb + j);
-            const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);
-            hs_.fold(e);
-            hk_.fold(make_ulonglong2(e.x, *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u)));
-        }
+    for (int j = 0; j < s - 1; j++) {
+        const uint32_t c = lds_u8(sm, sb + j);
+        const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);
+        hs_.fold(e);
+        hk_.fold(make_ulonglong2(e.x, *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u)));
+    }
     WinReg<W> wm;
     wm.init(w_runtime);
     uint32_t prevb = W - 1; // frame-relative position of the previous window's k-mer (none yet: stream -1)
-    uint32_t fb = 0u - (uint32_t)W; // stream index of the frame's position 0
     int32_t lim = lim0 + W;       // frame-relative version of lim0 (frame starts at -W in block 0)
     uint32_t pin = sb + (uint32_t)s - 1; // incoming code of step 0
     uint32_t pos = sb - 1;               // s-mer outgoing code of step j is pos + j
     uint32_t pok = sb - 1 - D;           // k-mer outgoing code of step j is pok + j (steps <= D have none)
     uint64_t mv;
     uint32_t mu;
-#define B200SK_SYNC_HASH(J, FIRST)                                                                         \
-    if (FAST) {                                                                                            \
-        const uint32_t ci = lds_u8(sm, pin + (J)) & 0x18u;                                                 \
-        if ((FIRST) && (J) == 0) {                                                                         \
-            hs_.f = rol1(hs_.f) ^ lds_u64(sm, ft + FT_F1X + ci);                                           \
-            hs_.r = ror1(hs_.r) ^ lds_u64(sm, ft + FT_F1Y + ci);                                           \
-        } else {                                                                                           \
-            const uint32_t o = ci | (lds_u8(sm, pos + (J)) & 0x60u);                                       \
-            hs_.f = rol1(hs_.f) ^ lds_u64(sm, ft + FT_X + o);                                              \
-            hs_.r = ror1(hs_.r) ^ lds_u64(sm, ft + FT_Y + o);                                              \
-        }                                                                                                  \
-        if ((FIRST) && (J) <= D) {                                                                         \
-            hk_.f = rol1(hk_.f) ^ lds_u64(sm, ft + FT_F1X + ci);                                           \
-            hk_.r = ror1(hk_.r) ^ lds_u64(sm, ft + FT_F1YK + ci);                                          \
-        } else {                                                                                           \
-            const uint32_t o = ci | (lds_u8(sm, pok + (J)) & 0x60u);                                       \
-            hk_.f = rol1(hk_.f) ^ lds_u64(sm, ft + FT_XK + o);                                             \
-            hk_.r = ror1(hk_.r) ^ lds_u64(sm, ft + FT_YK + o);                                             \
-        }                                                                                                  \
-    } else {                                                                                               \
+#define B200SK_SYNC_STEP(J, FIRST)                                                                         \
+    {                                                                                                      \
         const uint32_t c = lds_u8(sm, pin + (J));                                                          \
         const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);                                                \
         const uint64_t ek = *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u);                       \
         if ((FIRST) && (J) == 0) hs_.fold(e); else hs_.roll(e, B200SK_LD128(tOutS, pos + (J)));           \
         if ((FIRST) && (J) <= D) hk_.fold(make_ulonglong2(e.x, ek));                                       \
         else hk_.roll(make_ulonglong2(e.x, ek), B200SK_LD128(tOutK, pok + (J)));                           \
-    }
-#define B200SK_SYNC_STEP(J, FIRST)                                                                         \
-    {                                                                                                      \
-        B200SK_SYNC_HASH(J, FIRST)                                                                         \
         *reinterpret_cast<uint64_t *>(sm + kring + ((J) % D) * 256u) = hk_.canonical(); /* k-mer (J-D) */  \
         if (wm.push(J, FIRST, hs_.canonical(), mv, mu)) {                                                  \
             const uint32_t off = mu - (uint32_t)((J) + 1);        /* m - idx */                            \
@@ -455,21 +301,21 @@ __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint3
             const uint64_t kv = *reinterpret_cast<const uint64_t *>(sm + kring + (mu % (uint32_t)D) * 256u); \
             uint32_t ok = (b != prevb) & ((int32_t)b <= lim);                                              \
             if ((FIRST) && (J) == W - 1) ok |= halo; /* a non-first chunk's seeding window: always staged, dropped later */ \
-            sink.emit_if(ok, kv, b + fb);                                                                  \
+            sink.emit_if(ok, kv, b - prevb);                                                               \
             prevb = b;                                                                                     \
         }                                                                                                  \
     }
 #pragma unroll
     for (int j = 0; j < W; j++) B200SK_SYNC_STEP(j, true)
     wm.close_block();
-    prevb -= W; lim -= W; fb += W;
+    prevb -= W; lim -= W;
     pin += W; pos += W; pok += W;
     uint32_t u0 = W;
     while (u0 + W <= nstep) {
 #pragma unroll
         for (int j = 0; j < W; j++) B200SK_SYNC_STEP(j, false)
         wm.close_block();
-        prevb -= W; lim -= W; fb += W;
+        prevb -= W; lim -= W;
         pin += W; pos += W; pok += W;
         u0 += W;
     }
@@ -480,66 +326,20 @@ __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint3
         B200SK_SYNC_STEP(j, false)
     }
 #undef B200SK_SYNC_STEP
-#undef B200SK_SYNC_HASH
-}
-
-// The flush of one tile's staged lists (no list overflowed): list after list, lane j takes slot j.
-// meta = count | skip << 9 | exclusive offset << 10 of the lane's list; PW = bytes per position (0: none).
-// lean: one item per read (no halo element to skip, stream index = position) and at most 32 slots per list --
-// fully unrolled, every shared-memory offset an immediate.
-template <int PW>
-__device__ __forceinline__ void flush_lists(const uint8_t *listv, const uint8_t *listp, uint64_t *gv, uint8_t *gp,
-                                            uint32_t meta, uint32_t q0, bool lean, uint32_t lane) {
-    auto put = [&](const uint8_t *pv, const uint8_t *pp, uint32_t o, uint32_t q) {
-        gv[o] = *reinterpret_cast<const uint64_t *>(pv);
-        if (PW) {
-            const uint32_t pos = q + *pp;
-            if (PW == 1) gp[o] = (uint8_t)pos;
-            else if (PW == 2) reinterpret_cast<uint16_t *>(gp)[o] = (uint16_t)pos;
-            else reinterpret_cast<uint32_t *>(gp)[o] = pos;
-        }
-    };
-    if (lean) {
-        const uint8_t *lv = listv + lane * LIST_VSTRIDE, *lp = listp + lane * 32u;
-#pragma unroll
-        for (uint32_t L = 0; L < 32u; L++) {
-            const uint32_t m = __shfl_sync(0xffffffffu, meta, (int)L);
-            if (lane < (m & 0x1ffu)) put(lv + L * 8u, lp + L, (m >> 10) + lane, 0u);
-        }
-    } else {
-        for (uint32_t L = 0; L < 32u; L++) {
-            const uint32_t m = __shfl_sync(0xffffffffu, meta, (int)L);
-            const uint32_t q = __shfl_sync(0xffffffffu, q0, (int)L);
-            const uint32_t sL = (m >> 9) & 1u, nL = m & 0x1ffu;
-            for (uint32_t j = lane + sL; j < nL; j += 32u)
-                put(listv + j * LIST_VSTRIDE + L * 8u, listp + j * 32u + L, (m >> 10) + j - sL, q);
-        }
-    }
 }
 
 // ------------------------------------------------------------------ kernel: one tile per WARP
-// A tile is 32 consecutive items; every warp runs its own loop with no block-wide barrier, so warps drift
-// freely and cover each other's latencies:
-//   wait for the tile's TMA -> rewrite bytes (fast bytes if all ACGT, else 6-bit codes) -> walk (lists) ->
-//   scan + publish the tile's count -> resolve the look-back -> take the NEXT ticket and start its TMA
-//   (the tile buffer is dead) -> flush the lists while that copy is in flight.
+// A tile is 32 consecutive items; every warp runs its own ticket -> TMA -> walk -> look-back -> ordered
+// copy loop with no block-wide barrier, so warps drift freely and cover each other's latencies.
 // Shared memory: tables at 0; warp w owns [sm_tile + w*stride, +stride):
-//   +0 mbarrier, +16 tile bytes, +sm_ring k-mer ring (syncmer), +sm_listv values, +sm_listp stream indices.
-struct WarpTile {
-    uint64_t tile, lo_al;
-    uint32_t bytes;
-    bool span_ok, live;
-};
-
+//   +0 mbarrier, +16 tile bytes, +sm_ring k-mer ring (syncmer), +sm_listv values, +sm_listp position deltas.
 template <int MODE, int W>
 __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     constexpr bool SYNC = MODE == B200SK_MODE_SYNCMER;
     // tables (64 codes): [0,1K) in {A, rolB_{h-1}}, [1K,2K) out {rolA_h, rorB_1} for the streamed hash
-    // (h = k for minimizers, s for syncmers); syncmer adds [2K,3K) k-mer out table, [3K,3.5K) rolB_{k-1};
-    // then the fast-table block (FT_BYTES)
-    constexpr uint32_t FT = SYNC ? 3584u : 2048u;
+    // (h = k for minimizers, s for syncmers); syncmer adds [2K,3K) k-mer out table, [3K,3.5K) rolB_{k-1}
     const int hk = SYNC ? a.s : a.k;
     {
         ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 64, *tOutK = tIn + 128;
@@ -554,15 +354,14 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                 tInK[c] = rol64(r, (unsigned)(a.k - 1));
             }
         }
-        build_fast_tables(smem + FT, tid, hk, a.k, SYNC);
     }
     const uint32_t region = a.sm_tile + wid * a.sm_ring_bytes;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
     uint8_t *tilebuf = smem + region + 16;
     const uint32_t s_tile = region + 16;
     const uint32_t s_kring = region + a.sm_ring + lane * 8u;
-    const uint8_t *listv = smem + region + a.sm_listv;
-    const uint8_t *listp = smem + region + a.sm_listp;
+    uint64_t *listv = reinterpret_cast<uint64_t *>(smem + region + a.sm_listv);
+    uint8_t *listp = smem + region + a.sm_listp;
     if (lane == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
@@ -571,73 +370,42 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
     uint32_t parity = 0;
-
-    // take a ticket, work out the tile's items and start the copy of its byte range
-    auto fetch = [&](WarpTile &t, Item &it) {
+    for (;;) {
         uint64_t tile = 0;
         if (lane == 0) tile = atomicAdd(a.ticket, 1ULL);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        t.tile = tile;
         const uint64_t item0 = tile * 32ull;
-        t.live = item0 < n_items;
-        t.bytes = 0; t.span_ok = true; t.lo_al = 0;
-        if (!t.live) return;
+        if (item0 >= n_items) break;
         const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_items - item0);
+        Item it;
         item_geometry<MODE>(a, item0 + lane, n_items, it);
         const uint64_t lo = __shfl_sync(0xffffffffu, it.gb0, 0);
         const uint64_t hi = __shfl_sync(0xffffffffu, it.gb0 + it.nb, (int)nvalid - 1);
-        t.lo_al = lo & ~15ULL;
-        const uint64_t span = hi > t.lo_al ? hi - t.lo_al : 0;
-        t.bytes = (uint32_t)((span + 15ULL) & ~15ULL);
-        t.span_ok = t.bytes <= a.sm_tile_bytes;
-        if (lane == 0 && t.bytes && t.span_ok) {
-            fence_proxy_async(); // the previous tile's generic-proxy accesses to this buffer precede the async write
-            mbar_expect_tx(mbar, t.bytes);
-            tma_load_1d(tilebuf, a.bases + t.lo_al, t.bytes, mbar);
+        const uint64_t lo_al = lo & ~15ULL;
+        const uint64_t span = hi > lo_al ? hi - lo_al : 0;
+        const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
+        const bool span_ok = bytes <= a.sm_tile_bytes;
+        if (lane == 0 && bytes && span_ok) {
+            fence_proxy_async(); // the previous tile's generic-proxy writes to this buffer precede the async write
+            mbar_expect_tx(mbar, bytes);
+            tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
         }
-        if (!t.span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
-    };
-
-    WarpTile cur;
-    Item it;
-    fetch(cur, it);
-    while (cur.live) {
-        const uint64_t tile = cur.tile;
+        if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
         if (it.valid && it.first_chunk && a.status) a.status[it.r] = it.status;
-        bool fast = false;
-        if (cur.bytes && cur.span_ok) {
+        if (bytes && span_ok) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
-            // ASCII -> fast bytes, 16 bytes per lane per trip; any byte outside ACGTacgt (alignment slop
-            // included: a false alarm only costs the general path) -> fetch again and write 6-bit codes
-            uint32_t bad = 0;
-            for (uint32_t o = lane * 16u; o < cur.bytes; o += 512u) {
+            // ASCII -> codes, 16 bytes per lane per trip
+            for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
                 uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
-                v.x = fast_word(v.x, bad); v.y = fast_word(v.y, bad);
-                v.z = fast_word(v.z, bad); v.w = fast_word(v.w, bad);
+                const uint32_t orr = v.x | v.y | v.z | v.w, andd = v.x & v.y & v.z & v.w;
+                if ((orr & 0x80808080u) == 0 && (andd & 0x40404040u) == 0x40404040u) {
+                    v.x &= 0x1f1f1f1fu; v.y &= 0x1f1f1f1fu; v.z &= 0x1f1f1f1fu; v.w &= 0x1f1f1f1fu;
+                } else {
+                    v.x = codes_of_word(v.x); v.y = codes_of_word(v.y);
+                    v.z = codes_of_word(v.z); v.w = codes_of_word(v.w);
+                }
                 *reinterpret_cast<uint4 *>(tilebuf + o) = v;
-            }
-            fast = !__any_sync(0xffffffffu, bad != 0);
-            if (!fast) {
-                __syncwarp();
-                if (lane == 0) {
-                    fence_proxy_async();
-                    mbar_expect_tx(mbar, cur.bytes);
-                    tma_load_1d(tilebuf, a.bases + cur.lo_al, cur.bytes, mbar);
-                }
-                mbar_wait(mbar, parity);
-                parity ^= 1u;
-                for (uint32_t o = lane * 16u; o < cur.bytes; o += 512u) {
-                    uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
-                    const uint32_t orr = v.x | v.y | v.z | v.w, andd = v.x & v.y & v.z & v.w;
-                    if ((orr & 0x80808080u) == 0 && (andd & 0x40404040u) == 0x40404040u) {
-                        v.x &= 0x1f1f1f1fu; v.y &= 0x1f1f1f1fu; v.z &= 0x1f1f1f1fu; v.w &= 0x1f1f1f1fu;
-                    } else {
-                        v.x = codes_of_word(v.x); v.y = codes_of_word(v.y);
-                        v.z = codes_of_word(v.z); v.w = codes_of_word(v.w);
-                    }
-                    *reinterpret_cast<uint4 *>(tilebuf + o) = v;
-                }
             }
         }
         __syncwarp();
@@ -645,25 +413,17 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         sink.av = smem_base + region + a.sm_listv + lane * 8u;
         sink.ap = smem_base + region + a.sm_listp + lane;
         sink.cap = a.lcap; sink.cnt = 0;
-        const uint32_t sb = s_tile + (uint32_t)(it.gb0 - cur.lo_al);
-        const bool run = it.valid && it.nstep && cur.span_ok;
+        const uint32_t sb = s_tile + (uint32_t)(it.gb0 - lo_al);
+        const bool run = it.valid && it.nstep && span_ok;
         const int32_t lim0 = (int32_t)(it.end - it.q0);
         const uint32_t halo = it.q0 != it.p0 ? 1u : 0u;
-        const uint32_t nstep = it.nstep, q0 = it.q0;
-        auto walk = [&](auto &snk) {
-            if (SYNC) {
-                if (fast)
-                    syncmer_item_reg<W, true>(smem, sb, nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
-                                              2048u, FT, s_kring, lim0, halo, snk);
-                else
-                    syncmer_item_reg<W, false>(smem, sb, nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
-                                               2048u, FT, s_kring, lim0, halo, snk);
-            } else {
-                if (fast) minimizer_item_reg<W, true>(smem, sb, nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, snk);
-                else minimizer_item_reg<W, false>(smem, sb, nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, snk);
-            }
-        };
-        if (run) walk(sink);
+        if (run) {
+            if (SYNC)
+                syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
+                                    s_kring, lim0, halo, sink);
+            else
+                minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, sink);
+        }
         __syncwarp();
         // a non-first chunk walks one window more (the one before its first own window) to seed the
         // de-duplication; that window always emits first and is dropped here
@@ -679,58 +439,63 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         }
         const uint32_t excl = inc - cnt;
         const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        lookback_publish(a.tile_state, tile, total);
-        // what the flush still needs of this tile's items
-        const bool w_first = it.valid && it.first_chunk, w_last = it.valid && it.last_item;
-        const uint64_t w_read = it.r;
-        WarpTile nxt;
-        Item nit;
-        nxt.live = false;
-        const uint64_t tb = lookback_resolve(a.tile_state, tile, total);
-        // The codes are dead: the next tile's copy overlaps the flush.  (The ticket is taken only now, after
-        // the look-back: a ticket held by a warp that is still waiting for earlier tiles would be a tile
-        // nobody works on, and every later tile waits for it in turn -- a convoy.)
-        if (!any_overflow) fetch(nxt, nit);
+        const uint64_t tb = lookback_exclusive(a.tile_state, tile, total);
         const uint64_t mine = tb + excl;
-        if (w_first) a.out_off[w_read] = a.out_base + mine;
-        if (w_last) a.out_off[a.n_reads] = a.out_base + mine + cnt;
+        if (it.valid && it.first_chunk) a.out_off[it.r] = a.out_base + mine;
+        if (it.valid && it.last_item) a.out_off[a.n_reads] = a.out_base + mine + cnt;
         const bool fits = tb + total <= a.capacity;
         if (!fits && lane == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
         if (fits && total) {
             if (!any_overflow) {
-                // flush: list after list (= item after item, global order), the 32 lanes take consecutive
-                // slots of one list -> every store instruction writes one contiguous run
-                const uint32_t meta = sink.cnt | (skip << 9) | (excl << 10);
-                const bool lean = a.item_first == nullptr && a.lcap <= 32u; // one item per read: q0 = 0, no halo
-                uint64_t *gv = a.out_val + tb;
-                if (!a.out_pos) flush_lists<0>(listv, listp, gv, nullptr, meta, q0, lean, lane);
-                else if (a.pos_width == 1)
-                    flush_lists<1>(listv, listp, gv, reinterpret_cast<uint8_t *>(a.out_pos) + tb, meta, q0, lean, lane);
-                else if (a.pos_width == 2)
-                    flush_lists<2>(listv, listp, gv, reinterpret_cast<uint8_t *>(a.out_pos) + tb * 2, meta, q0, lean, lane);
-                else
-                    flush_lists<4>(listv, listp, gv, reinterpret_cast<uint8_t *>(a.out_pos) + tb * 4, meta, q0, lean, lane);
+                // ordered copy: scatter the staged lists into one contiguous buffer (the codes are dead
+                // now), then stream it out coalesced
+                const uint32_t OB = a.sm_tile_bytes / 12u;
+                uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
+                uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
+                for (uint32_t r0 = 0; r0 < total; r0 += OB) {
+                    uint32_t pos = it.q0 - 1u;
+                    for (uint32_t j = 0; j < sink.cnt; j++) {
+                        pos += listp[j * 32u + lane];
+                        const uint32_t o = excl + j - skip - r0;
+                        if (j >= skip && o < OB) { // unsigned compare also rejects entries before r0
+                            obv[o] = listv[j * 32u + lane];
+                            obp[o] = pos;
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t n = min(OB, total - r0);
+                    uint64_t *gv = a.out_val + tb + r0;
+                    for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
+                    if (a.out_pos)
+                        for (uint32_t i = lane; i < n; i += 32u) store_pos(a.out_pos, a.pos_width, tb + r0 + i, obp[i]);
+                    __syncwarp();
+                }
             } else {
                 // rare (low-complexity reads): some item emitted more than its list holds.  Items that fit
                 // write their lists straight to their final range; the others walk their item again with
                 // the global sink (the codes are still in shared memory).
                 if (!overflow) {
-                    for (uint32_t j = skip; j < sink.cnt; j++) {
-                        a.out_val[mine + j - skip] = *reinterpret_cast<const uint64_t *>(listv + j * LIST_VSTRIDE + lane * 8u);
-                        if (a.out_pos) store_pos(a.out_pos, a.pos_width, mine + j - skip, q0 + listp[j * 32u + lane]);
+                    uint32_t pos = it.q0 - 1u;
+                    for (uint32_t j = 0; j < sink.cnt; j++) {
+                        pos += listp[j * 32u + lane];
+                        if (j >= skip) {
+                            a.out_val[mine + j - skip] = listv[j * 32u + lane];
+                            if (a.out_pos) store_pos(a.out_pos, a.pos_width, mine + j - skip, pos);
+                        }
                     }
                 } else {
                     GlobalSink gs;
                     gs.gv = a.out_val + mine; gs.gp = a.out_pos; gs.gi = mine; gs.pw = a.pos_width;
-                    gs.pos = q0; gs.cnt = 0; gs.skip = skip;
-                    walk(gs);
+                    gs.pos = it.q0 - 1u; gs.cnt = 0; gs.skip = skip;
+                    if (SYNC)
+                        syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
+                                            2048u, s_kring, lim0, halo, gs);
+                    else
+                        minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, gs);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
-        if (any_overflow) fetch(nxt, nit);
-        cur = nxt;
-        it = nit;
     }
 }
 
