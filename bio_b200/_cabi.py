@@ -43,7 +43,21 @@ EXPORTS = (
     "b200sk_check_params", "b200sk_output_bound", "b200sk_run", "b200sk_run_device",
     "b200sk_enqueue_device", "b200sk_strerror", "b200sk_last_error", "b200sk_kernel_launches",
     "b200sk_version", "b200sk_timing_enable", "b200sk_timing_collect",
+    "b200sk_fastx_parse_device", "b200sk_run_fastx", "b200sk_copy_to_host",
 )
+
+FASTX_FASTA, FASTX_FASTQ = 1, 2
+ERR_NOT_FASTX, ERR_BAD_FASTQ = -20, -21
+
+
+class FastxInfo(C.Structure):
+    _fields_ = [
+        ("format", C.c_int32), ("status", C.c_int32), ("n_records", C.c_uint64), ("n_bases", C.c_uint64),
+        ("n_lines", C.c_uint64), ("consumed", C.c_uint64), ("bad_record", C.c_uint64),
+        ("max_read_len", C.c_uint32), ("reserved", C.c_uint32),
+        ("d_bases", C.c_void_p), ("d_read_off", C.c_void_p), ("d_rec_off", C.c_void_p),
+        ("d_qual_off", C.c_void_p), ("d_line_off", C.c_void_p),
+    ]
 
 
 class Params(C.Structure):
@@ -127,6 +141,14 @@ def lib():
     L.b200sk_timing_enable.argtypes = [vp, C.c_int]
     L.b200sk_timing_collect.restype = C.c_int
     L.b200sk_timing_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.b200sk_fastx_parse_device.restype = C.c_int
+    L.b200sk_fastx_parse_device.argtypes = [vp, u8p, C.c_uint64, C.c_int, C.c_int, vp, C.POINTER(FastxInfo)]
+    L.b200sk_copy_to_host.restype = C.c_int
+    L.b200sk_copy_to_host.argtypes = [vp, vp, vp, C.c_uint64]
+    L.b200sk_run_fastx.restype = C.c_int
+    L.b200sk_run_fastx.argtypes = [vp, PP, u8p, C.c_uint64, C.c_int, C.c_int, C.POINTER(FastxInfo),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -243,3 +265,66 @@ class Context:
             flags.data_ptr() if flags is not None else None)
         if rc != 0:
             self._raise(rc)
+
+    # ---- record feeder (seqio/fastx.Reader as a batch operation)
+    def fastx_parse_device(self, d_text, n_bytes=None, fmt=0, final=True, stream=None):
+        """Split a chunk of FASTA/FASTQ text resident in HBM (torch uint8 CUDA tensor, 16-byte aligned, padded
+        to a multiple of 16 bytes) into records.  Returns the FastxInfo (device pointers are library-owned)."""
+        import torch
+        n = d_text.numel() if n_bytes is None else n_bytes
+        st = torch.cuda.current_stream(d_text.device).cuda_stream if stream is None else stream
+        info = FastxInfo()
+        rc = lib().b200sk_fastx_parse_device(self._h, d_text.data_ptr(), n, fmt, int(bool(final)), st, C.byref(info))
+        if rc != 0:
+            e = SketchError(rc, lib().b200sk_last_error(self._h).decode() if rc == ERR_CUDA else "")
+            e.info = info
+            raise e
+        return info
+
+    def fastx_fetch(self, info):
+        """Copy a parse result to the host (tests): dict of numpy arrays."""
+        import numpy as np
+
+        def grab(ptr, count, dt):
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dt)
+            out = np.empty(count, dtype=dt)
+            rc = lib().b200sk_copy_to_host(self._h, out.ctypes.data, ptr, out.nbytes)
+            if rc != 0:
+                self._raise(rc)
+            return out
+
+        n = int(info.n_records)
+        return dict(format=int(info.format), n_records=n, consumed=int(info.consumed),
+                    max_read_len=int(info.max_read_len),
+                    bases=grab(info.d_bases, int(info.n_bases), np.uint8),
+                    read_off=grab(info.d_read_off, n + 1, np.uint64),
+                    rec_off=grab(info.d_rec_off, n + 1, np.uint64),
+                    qual_off=grab(info.d_qual_off, n, np.uint64),
+                    line_off=grab(info.d_line_off, int(info.n_lines) + 1, np.uint64))
+
+    def run_fastx(self, params, text, fmt=0, final=True, copy=True):
+        """Host entry point: FASTA/FASTQ text (bytes / uint8 array) in, the sketches of its records out."""
+        import numpy as np
+        text = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(text, dtype=np.uint8)
+        info = FastxInfo()
+        ov, op, oo, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        total = C.c_uint64(0)
+        rc = lib().b200sk_run_fastx(self._h, C.byref(params), text.ctypes.data if len(text) else None, len(text), fmt,
+                                    int(bool(final)), C.byref(info), C.byref(ov), C.byref(op), C.byref(oo),
+                                    C.byref(st), C.byref(total))
+        if rc != 0:
+            self._raise(rc)
+        t, n = int(total.value), int(info.n_records)
+
+        def view(ptr, count, dt):
+            if not ptr.value or count == 0:
+                return np.zeros(0, dtype=dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dt).itemsize,))
+            a = a.view(dt)
+            return a.copy() if copy else a
+
+        pdt = {1: np.uint8, 2: np.uint16}.get(int(params.pos_width), np.uint32)
+        return dict(val=view(ov, t, np.uint64), pos=view(op, t, pdt) if params.want_pos else None,
+                    off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t, info=info)

@@ -121,11 +121,22 @@ struct b200sk_ctx {
     DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;       // slot 0
     DevBuf d_bases2, d_off2, d_val2, d_pos2, d_ooff2, d_status2; // slot 1
     HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
+    void *fx = nullptr; // record feeder state (b200sk_fastx.cu)
     uint64_t launches = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     std::string last_error;
 };
+
+// hooks for b200sk_fastx.cu
+namespace b200sk {
+void fx_free(void *p);
+int ctx_device(b200sk_ctx *ctx) { return ctx->device; }
+cudaStream_t ctx_stream(b200sk_ctx *ctx) { return ctx->own_stream; }
+void **ctx_fx_slot(b200sk_ctx *ctx) { return &ctx->fx; }
+void ctx_set_error(b200sk_ctx *ctx, const char *msg) { ctx->last_error = msg; }
+void ctx_add_launches(b200sk_ctx *ctx, uint64_t n) { ctx->launches += n; }
+} // namespace b200sk
 
 namespace {
 
@@ -545,6 +556,8 @@ const char *b200sk_strerror(int code) {
     case B200SK_ERR_INVALID_M: return "sketches: invalid m-mer size, should be in range of [4, k]";
     case B200SK_ERR_INVALID_SCALE: return "sketches: invalid scale, should be in range of [1, k-m+1]";
     case B200SK_ERR_K_TOO_LARGE: return "sketches: k-mer size is too large";
+    case B200SK_ERR_NOT_FASTX: return "fastx: invalid FASTA/Q format";
+    case B200SK_ERR_BAD_FASTQ: return "fastx: bad fastq format";
     case B200SK_ERR_CUDA: return "b200sketch: CUDA error";
     case B200SK_ERR_NO_DEVICE: return "b200sketch: no CUDA device (there is no CPU fallback)";
     case B200SK_ERR_UNSUPPORTED: return "b200sketch: parameters outside the implemented range";
@@ -588,6 +601,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
                       &ctx->d_status2})
         b->release();
     for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();
+    b200sk::fx_free(ctx->fx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

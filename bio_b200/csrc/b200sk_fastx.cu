@@ -1,0 +1,587 @@
+// Record feeder: the caller side of the sketching path.  What seqio/fastx.Reader.Read + parseRecord
+// (seqio/fastx/reader.go:233-471) do one record at a time -- find the records of a FASTA/FASTQ text, strip
+// line ends, concatenate each record's sequence lines -- done for a whole chunk of text in HBM, producing
+// directly what the sketching kernels take: the packed bases and read_off[n+1], plus per-record text
+// offsets (record start, quality start) from which the host shim slices Name/ID/Desc/Qual lazily.
+//
+// Reference behaviour kept (reader.go):
+//   * format from the first byte that is not '\n': '>' FASTA, '@' FASTQ, anything else ErrNotFASTXFormat
+//     (:271-304);
+//   * a record starts at a delimiter that follows '\n' (:310-325); '>'/'@' elsewhere in a line is data;
+//   * FASTA: the sequence is every following line up to the next record, each without its '\n' and one
+//     trailing '\r' (:383-393, dropCR :535-541); empty lines contribute nothing;
+//   * FASTQ: the line after the header is the sequence, a non-empty line starting with '+' switches to
+//     quality (:396-412), sequence and quality lengths must agree (:415-417, ErrUnequalSeqAndQual); an '@'
+//     that starts a quality line is not a record start because the record is then not complete (:328-340);
+//   * a last record without a final '\n' is complete (:352-364); empty lines after the last record are not
+//     a record.
+// Scope of this implementation: FASTQ records of exactly four lines (header, sequence, '+', quality -- what
+// every sequencer writes; multi-line FASTQ makes the chunk fail with B200SK_ERR_BAD_FASTQ instead of being
+// mis-parsed) and FASTA with any line structure.  Alphabet guessing / per-letter validation (reader.go:
+// 430-452) stays with the caller.
+//
+// Kernels (all memory-bound, one pass each over what they touch):
+//   k_fx_detect   first record byte and format
+//   k_fx_count    newlines (and line-initial '>') after the first record byte: sizes the tables
+//   k_fx_lines    line-start table L[] in one pass (per-tile newline counts, decoupled look-back)
+//   k_fq_scan     FASTQ: per record validate + sequence length -> read_off / rec_off / qual_off (look-back scan)
+//   k_fa_scan     FASTA: per line header flag + sequence bytes -> out_pos per line, read_off / rec_off per record
+//   k_fq_copy / k_fa_copy   sequence bytes -> packed bases (a warp per record / per line)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/b200sketch.h"
+#include "b200sk_device.cuh"
+
+namespace b200sk {
+
+// internal hooks into the context (b200sk_api.cu)
+int ctx_device(b200sk_ctx *ctx);
+cudaStream_t ctx_stream(b200sk_ctx *ctx);
+void **ctx_fx_slot(b200sk_ctx *ctx);
+void ctx_set_error(b200sk_ctx *ctx, const char *msg);
+void ctx_add_launches(b200sk_ctx *ctx, uint64_t n);
+
+namespace {
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct FxState {
+    Buf meta, lines, outpos, bases, read_off, rec_off, qual_off, state_a, state_b;
+    Buf text;                                   // host path: the chunk in HBM
+    Buf o_val, o_pos, o_off, o_status;          // host path: sketch outputs in HBM
+    PinBuf h_val, h_pos, h_off, h_status, h_meta; // host path: what the caller reads
+};
+
+// meta words (u64): 0 format, 1 start0, 2 newlines, 3 line-initial '>' count, 4 last byte, 5 ticket,
+// 6 error record (min), 7 max sequence length, 8 total bases, 9 records (FASTA), 10 flags, 11 ticket 2
+enum { M_FORMAT = 0, M_START, M_NL, M_HDR, M_LAST, M_TICKET, M_BADREC, M_MAXLEN, M_TOTAL, M_NREC, M_FLAGS, M_TICKET2, M_WORDS = 16 };
+
+// ------------------------------------------------------------------ kernels
+// reader.go:271-304: the first byte that is not '\n' decides
+__global__ void k_fx_detect(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta) {
+    const unsigned lane = threadIdx.x;
+    uint64_t fmt = 0, start = n;
+    for (uint64_t base = 0; base < n && base < (1ull << 20); base += 32) {
+        const uint64_t i = base + lane;
+        const uint8_t b = i < n ? t[i] : (uint8_t)'\n';
+        const unsigned other = __ballot_sync(0xffffffffu, b != '\n');
+        if (other) {
+            const int f = __ffs(other) - 1;
+            const uint8_t c = (uint8_t)__shfl_sync(0xffffffffu, (unsigned)b, f);
+            start = base + f;
+            fmt = c == '>' ? B200SK_FASTX_FASTA : c == '@' ? B200SK_FASTX_FASTQ : 0;
+            break;
+        }
+    }
+    if (lane == 0) {
+        meta[M_FORMAT] = fmt;
+        meta[M_START] = start;
+        meta[M_LAST] = n ? t[n - 1] : '\n';
+    }
+}
+
+// bit j of the result: byte j of the 16-byte vector equals c
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 v, uint32_t c4) {
+    const uint32_t a = __vcmpeq4(v.x, c4) & 0x01010101u, b = __vcmpeq4(v.y, c4) & 0x01010101u;
+    const uint32_t c = __vcmpeq4(v.z, c4) & 0x01010101u, d = __vcmpeq4(v.w, c4) & 0x01010101u;
+    // gather the four flag bits of a word into a nibble: bits 0,8,16,24 -> 0,1,2,3
+    auto nib = [](uint32_t x) { return (x * 0x00204081u) >> 21 & 0xfu; }; // (1 + 2^7 + 2^14 + 2^21) spreads, top nibble collects
+    return nib(a) | (nib(b) << 4) | (nib(c) << 8) | (nib(d) << 12);
+}
+__device__ __forceinline__ uint32_t range_mask16(uint64_t pos, uint64_t lo, uint64_t hi) { // bytes pos+j in [lo, hi)
+    uint32_t m = 0xffffu;
+    if (pos < lo) m &= lo - pos >= 16 ? 0u : (0xffffu << (uint32_t)(lo - pos));
+    if (pos + 16 > hi) m &= hi <= pos ? 0u : (0xffffu >> (uint32_t)(pos + 16 - hi));
+    return m & 0xffffu;
+}
+
+// newlines at positions >= start0, and '>' that start a line (FASTA records) -- sizes the tables
+__global__ void __launch_bounds__(256) k_fx_count(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta) {
+    const uint64_t start0 = meta[M_START];
+    const uint64_t nvec = (n + 15) / 16;
+    unsigned long long nl = 0, hd = 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t pos = v * 16;
+        if (pos + 16 <= start0) continue;
+        const uint4 x = reinterpret_cast<const uint4 *>(t)[v];
+        const uint32_t rm = range_mask16(pos, start0, n);
+        const uint32_t m = eq_mask16(x, 0x0a0a0a0au) & rm;
+        nl += __popc(m);
+        // '>' preceded by '\n' (the byte before the vector decides for bit 0); the first record byte counts too
+        uint32_t g = eq_mask16(x, 0x3e3e3e3eu) & rm;
+        if (g) {
+            uint32_t prev_nl = (eq_mask16(x, 0x0a0a0a0au) << 1) & 0xffffu;
+            if (pos > 0 && t[pos - 1] == '\n') prev_nl |= 1u;
+            if (start0 >= pos && start0 < pos + 16) prev_nl |= 1u << (uint32_t)(start0 - pos);
+            hd += __popc(g & prev_nl);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nl += __shfl_xor_sync(0xffffffffu, nl, o);
+        hd += __shfl_xor_sync(0xffffffffu, hd, o);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (nl) atomicAdd(meta + M_NL, nl);
+        if (hd) atomicAdd(meta + M_HDR, hd);
+    }
+}
+
+// L[i] = start of line i: L[0] = start0, L[i] = position after the i-th newline at or after start0.
+// One pass: tiles of 4 KB, per-tile counts ordered by a decoupled look-back.
+__global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta,
+                                                  uint64_t *tile_state, uint64_t *__restrict__ L) {
+    __shared__ uint32_t warp_sums[34];
+    __shared__ uint64_t s_tile, s_base;
+    const uint64_t start0 = meta[M_START];
+    const uint64_t ntiles = (n + 4095) / 4096;
+    const uint32_t tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(meta + M_TICKET, 1ULL);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const uint64_t pos = tile * 4096 + (uint64_t)tid * 16;
+        uint32_t m = 0;
+        if (pos < n && pos + 16 > start0) {
+            const uint4 x = reinterpret_cast<const uint4 *>(t)[pos / 16];
+            m = eq_mask16(x, 0x0a0a0a0au) & range_mask16(pos, start0, n);
+        }
+        uint32_t total;
+        const uint32_t excl = block_excl_scan((uint32_t)__popc(m), warp_sums, &total);
+        if (tid < 32) {
+            const uint64_t b = lookback_exclusive(tile_state, tile, total);
+            if (tid == 0) s_base = b;
+        }
+        __syncthreads();
+        uint64_t idx = s_base + excl + 1; // line index the next newline of this thread opens
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            L[idx++] = pos + j + 1;
+        }
+        __syncthreads();
+    }
+}
+// the two ends of the table
+__global__ void k_fx_lines_finish(uint64_t n, const unsigned long long *meta, uint64_t nl, uint64_t *L) {
+    const uint64_t start0 = meta[M_START];
+    L[0] = start0;
+    // a last line without '\n': its (virtual) newline sits at n, so the "next line" starts at n + 1
+    if (n > start0 && meta[M_LAST] != '\n') L[nl + 1] = n + 1;
+}
+
+__device__ __forceinline__ uint32_t line_len(const uint8_t *t, uint64_t s, uint64_t next) { // without '\n' and one '\r'
+    const uint64_t e = next - 1; // position of the newline
+    uint32_t len = (uint32_t)(e - s);
+    if (len && t[e - 1] == '\r') len--; // dropCR, reader.go:535-541
+    return len;
+}
+
+// FASTQ, one thread per record of four lines (reader.go:396-417)
+__global__ void __launch_bounds__(256) k_fq_scan(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
+                                                 uint64_t nrec, uint64_t nlines, int final, unsigned long long *meta,
+                                                 uint64_t *tile_state, uint64_t *read_off, uint64_t *rec_off,
+                                                 uint64_t *qual_off) {
+    __shared__ uint32_t warp_sums[34];
+    __shared__ uint64_t s_tile, s_base;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t ntiles = (nrec + 255) / 256;
+    if (blockIdx.x == 0 && tid == 0) {
+        // lines after the last whole record: only empty ones are not an error, and only at the end of the text
+        for (uint64_t i = 4 * nrec; i < nlines; i++)
+            if (!final || line_len(t, L[i], L[i + 1]) != 0) atomicMin(meta + M_BADREC, (unsigned long long)nrec);
+        if (nrec == 0) read_off[0] = 0;
+    }
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(meta + M_TICKET2, 1ULL);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const uint64_t r = tile * 256 + tid;
+        uint32_t len = 0;
+        if (r < nrec) {
+            const uint64_t h = L[4 * r], s = L[4 * r + 1], p = L[4 * r + 2], q = L[4 * r + 3], e = L[4 * r + 4];
+            len = line_len(t, s, p);
+            const uint32_t qlen = line_len(t, q, e);
+            // header '@'; a NON-EMPTY line starting with '+' (reader.go:399); equal lengths (:415)
+            const bool ok = t[h] == '@' && p + 1 < q && t[p] == '+' && len == qlen;
+            if (!ok) atomicMin(meta + M_BADREC, (unsigned long long)r);
+            rec_off[r] = h;
+            qual_off[r] = q;
+        }
+        uint32_t total;
+        const uint32_t excl = block_excl_scan(len, warp_sums, &total);
+        uint32_t mx = len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31u) == 0 && mx) atomicMax(meta + M_MAXLEN, (unsigned long long)mx);
+        if (tid < 32) {
+            const uint64_t b = lookback_exclusive(tile_state, tile, total);
+            if (tid == 0) s_base = b;
+        }
+        __syncthreads();
+        if (r < nrec) {
+            read_off[r] = s_base + excl;
+            if (r + 1 == nrec) {
+                read_off[nrec] = s_base + excl + len;
+                meta[M_TOTAL] = s_base + excl + len;
+            }
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_fq_copy(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
+                                                 const uint64_t *__restrict__ read_off, uint64_t nrec,
+                                                 uint8_t *__restrict__ bases) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nwarp = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrec; r += nwarp) {
+        const uint64_t s = L[4 * r + 1], d = read_off[r];
+        const uint32_t len = (uint32_t)(read_off[r + 1] - d);
+        for (uint32_t i = lane; i < len; i += 32u) bases[d + i] = t[s + i];
+    }
+}
+
+// FASTA, one thread per line (reader.go:383-393): header lines open a record, every other line adds its
+// bytes to the current record.  Two ordered sums: sequence bytes and header count.
+__global__ void __launch_bounds__(256) k_fa_scan(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
+                                                 uint64_t nlines, unsigned long long *meta, uint64_t *state_len,
+                                                 uint64_t *state_hdr, uint64_t *outpos, uint64_t *read_off,
+                                                 uint64_t *rec_off) {
+    __shared__ uint32_t warp_sums[34];
+    __shared__ uint64_t s_tile, s_base_len, s_base_hdr;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t ntiles = (nlines + 255) / 256;
+    if (blockIdx.x == 0 && tid == 0 && nlines == 0) { read_off[0] = 0; meta[M_NREC] = 0; meta[M_TOTAL] = 0; }
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(meta + M_TICKET2, 1ULL);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const uint64_t i = tile * 256 + tid;
+        uint32_t len = 0, hdr = 0;
+        uint64_t s = 0;
+        if (i < nlines) {
+            s = L[i];
+            const uint64_t nx = L[i + 1];
+            hdr = (nx - 1 > s && t[s] == '>') ? 1u : 0u; // an empty line is not a header
+            len = hdr ? 0u : line_len(t, s, nx);
+        }
+        uint32_t total_len, total_hdr;
+        const uint32_t excl_len = block_excl_scan(len, warp_sums, &total_len);
+        const uint32_t excl_hdr = block_excl_scan(hdr, warp_sums, &total_hdr);
+        if (tid < 32) {
+            const uint64_t b = lookback_exclusive(state_len, tile, total_len);
+            const uint64_t c = lookback_exclusive(state_hdr, tile, total_hdr);
+            if (tid == 0) { s_base_len = b; s_base_hdr = c; }
+        }
+        __syncthreads();
+        if (i < nlines) {
+            const uint64_t op = s_base_len + excl_len;
+            outpos[i] = op;
+            if (hdr) {
+                const uint64_t r = s_base_hdr + excl_hdr;
+                read_off[r] = op;
+                rec_off[r] = s;
+            }
+            if (i + 1 == nlines) {
+                const uint64_t nrec = s_base_hdr + excl_hdr + hdr;
+                read_off[nrec] = op + len;
+                meta[M_NREC] = nrec;
+                meta[M_TOTAL] = op + len;
+            }
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_fa_copy(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
+                                                 const uint64_t *__restrict__ outpos, uint64_t nlines, uint64_t limit,
+                                                 uint8_t *__restrict__ bases) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nwarp = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nlines; i += nwarp) {
+        const uint64_t s = L[i], nx = L[i + 1];
+        if (s >= limit) continue;                   // lines of a record that is not complete in this chunk
+        if (nx - 1 > s && t[s] == '>') continue;    // header
+        const uint32_t len = line_len(t, s, nx);
+        const uint64_t d = outpos[i];
+        for (uint32_t j = lane; j < len; j += 32u) bases[d + j] = t[s + j];
+    }
+}
+
+int fail(b200sk_ctx *ctx, cudaError_t e, const char *what) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    ctx_set_error(ctx, buf);
+    return B200SK_ERR_CUDA;
+}
+#define FCK(call)                                          \
+    do {                                                   \
+        cudaError_t _e = (call);                           \
+        if (_e != cudaSuccess) return fail(ctx, _e, #call); \
+    } while (0)
+
+FxState *state_of(b200sk_ctx *ctx) {
+    void **slot = ctx_fx_slot(ctx);
+    if (!*slot) *slot = new FxState();
+    return static_cast<FxState *>(*slot);
+}
+
+} // namespace
+
+void fx_free(void *p) {
+    FxState *s = static_cast<FxState *>(p);
+    if (!s) return;
+    for (Buf *b : {&s->meta, &s->lines, &s->outpos, &s->bases, &s->read_off, &s->rec_off, &s->qual_off, &s->state_a,
+                   &s->state_b, &s->text, &s->o_val, &s->o_pos, &s->o_off, &s->o_status})
+        b->release();
+    for (PinBuf *b : {&s->h_val, &s->h_pos, &s->h_off, &s->h_status, &s->h_meta}) b->release();
+    delete s;
+}
+
+} // namespace b200sk
+
+using namespace b200sk;
+
+extern "C" {
+
+int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n_bytes, int format, int final,
+                              void *stream, b200sk_fastx_info *info) {
+    if (!ctx || !info || (n_bytes && !d_text)) return B200SK_ERR_BAD_ARG;
+    if (((uintptr_t)d_text & 15u) != 0) return B200SK_ERR_BAD_ARG;
+    if (format != 0 && format != B200SK_FASTX_FASTA && format != B200SK_FASTX_FASTQ) return B200SK_ERR_BAD_ARG;
+    memset(info, 0, sizeof(*info));
+    FCK(cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx_stream(ctx);
+    FxState *fx = state_of(ctx);
+    FCK(fx->meta.reserve(M_WORDS * 8));
+    unsigned long long *meta = (unsigned long long *)fx->meta.p;
+    unsigned long long hm[M_WORDS];
+    FCK(cudaMemsetAsync(meta, 0, M_WORDS * 8, st));
+    if (n_bytes == 0) {
+        info->format = format;
+        return 0;
+    }
+    k_fx_detect<<<1, 32, 0, st>>>(d_text, n_bytes, meta);
+    {
+        const uint64_t nvec = (n_bytes + 15) / 16;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((nvec + 255) / 256, 148ull * 16);
+        k_fx_count<<<blocks, 256, 0, st>>>(d_text, n_bytes, meta);
+    }
+    ctx_add_launches(ctx, 2);
+    FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
+    FCK(cudaStreamSynchronize(st));
+    const int detected = (int)hm[M_FORMAT];
+    if (hm[M_START] >= n_bytes) { // only newlines: nothing to parse
+        info->format = format;
+        info->consumed = final ? n_bytes : 0;
+        return 0;
+    }
+    if (detected == 0 || (format != 0 && format != detected)) {
+        info->status = B200SK_ERR_NOT_FASTX;
+        return B200SK_ERR_NOT_FASTX;
+    }
+    info->format = detected;
+    const uint64_t nl = hm[M_NL];
+    const bool tail = hm[M_LAST] != '\n'; // a last line without its newline
+    // lines the parse may use: without `final` an unterminated last line is not complete
+    const uint64_t nlines = nl + ((tail && final) ? 1 : 0);
+    FCK(fx->lines.reserve((nl + 3) * 8));
+    uint64_t *L = (uint64_t *)fx->lines.p;
+    {
+        const uint64_t ntiles = (n_bytes + 4095) / 4096;
+        FCK(fx->state_a.reserve((ntiles + 1) * 8));
+        FCK(cudaMemsetAsync(fx->state_a.p, 0, (ntiles + 1) * 8, st));
+        const unsigned blocks = (unsigned)std::min<uint64_t>(ntiles, 148ull * 8);
+        k_fx_lines<<<blocks, 256, 0, st>>>(d_text, n_bytes, meta, (uint64_t *)fx->state_a.p, L);
+        k_fx_lines_finish<<<1, 1, 0, st>>>(n_bytes, meta, nl, L);
+        ctx_add_launches(ctx, 2);
+    }
+    uint64_t nrec = 0;
+    if (detected == B200SK_FASTX_FASTQ) {
+        nrec = nlines / 4;
+        FCK(fx->read_off.reserve((nrec + 2) * 8));
+        FCK(fx->rec_off.reserve((nrec + 2) * 8));
+        FCK(fx->qual_off.reserve((nrec + 2) * 8));
+        const uint64_t ntiles = (nrec + 255) / 256;
+        FCK(fx->state_b.reserve((ntiles + 1) * 8));
+        FCK(cudaMemsetAsync(fx->state_b.p, 0, (ntiles + 1) * 8, st));
+        const unsigned long long none = ~0ULL;
+        FCK(cudaMemcpyAsync(meta + M_BADREC, &none, 8, cudaMemcpyHostToDevice, st));
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ntiles, 148ull * 8));
+        // without `final` the lines after the last whole record simply stay for the next chunk
+        k_fq_scan<<<blocks, 256, 0, st>>>(d_text, L, nrec, final ? nlines : 4 * nrec, final, meta,
+                                          (uint64_t *)fx->state_b.p, (uint64_t *)fx->read_off.p,
+                                          (uint64_t *)fx->rec_off.p, (uint64_t *)fx->qual_off.p);
+        ctx_add_launches(ctx, 1);
+        FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
+        FCK(cudaStreamSynchronize(st));
+        if (hm[M_BADREC] != ~0ULL) {
+            info->status = B200SK_ERR_BAD_FASTQ;
+            info->bad_record = hm[M_BADREC];
+            return B200SK_ERR_BAD_FASTQ;
+        }
+        const uint64_t total = nrec ? hm[M_TOTAL] : 0;
+        FCK(fx->bases.reserve(total + 64));
+        if (nrec) {
+            const unsigned cb = (unsigned)std::min<uint64_t>((nrec + 7) / 8, 148ull * 16);
+            k_fq_copy<<<cb, 256, 0, st>>>(d_text, L, (const uint64_t *)fx->read_off.p, nrec, (uint8_t *)fx->bases.p);
+            ctx_add_launches(ctx, 1);
+        }
+        info->n_records = nrec;
+        info->n_bases = total;
+        info->max_read_len = (uint32_t)hm[M_MAXLEN];
+        if (final) info->consumed = n_bytes;
+        else {
+            uint64_t c = 0;
+            if (nrec) {
+                FCK(cudaMemcpyAsync(&c, L + 4 * nrec, 8, cudaMemcpyDeviceToHost, st));
+                FCK(cudaStreamSynchronize(st));
+            } else c = hm[M_START];
+            info->consumed = std::min<uint64_t>(c, n_bytes);
+        }
+        info->d_qual_off = (uint64_t *)fx->qual_off.p;
+    } else {
+        const uint64_t maxrec = hm[M_HDR];
+        FCK(fx->read_off.reserve((maxrec + 2) * 8));
+        FCK(fx->rec_off.reserve((maxrec + 2) * 8));
+        FCK(fx->outpos.reserve((nlines + 2) * 8));
+        const uint64_t ntiles = (nlines + 255) / 256;
+        FCK(fx->state_a.reserve((ntiles + 1) * 8));
+        FCK(fx->state_b.reserve((ntiles + 1) * 8));
+        FCK(cudaMemsetAsync(fx->state_a.p, 0, (ntiles + 1) * 8, st));
+        FCK(cudaMemsetAsync(fx->state_b.p, 0, (ntiles + 1) * 8, st));
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ntiles, 148ull * 8));
+        k_fa_scan<<<blocks, 256, 0, st>>>(d_text, L, nlines, meta, (uint64_t *)fx->state_a.p,
+                                          (uint64_t *)fx->state_b.p, (uint64_t *)fx->outpos.p,
+                                          (uint64_t *)fx->read_off.p, (uint64_t *)fx->rec_off.p);
+        ctx_add_launches(ctx, 1);
+        FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
+        FCK(cudaStreamSynchronize(st));
+        uint64_t found = hm[M_NREC];
+        // without `final` the last record may continue in the next chunk: it stays
+        nrec = final ? found : (found ? found - 1 : 0);
+        uint64_t ro[2] = {0, 0};
+        uint64_t limit = n_bytes + 2, total = hm[M_TOTAL];
+        if (!final) {
+            if (found) {
+                FCK(cudaMemcpyAsync(&ro[0], (uint64_t *)fx->read_off.p + nrec, 8, cudaMemcpyDeviceToHost, st));
+                FCK(cudaMemcpyAsync(&ro[1], (uint64_t *)fx->rec_off.p + nrec, 8, cudaMemcpyDeviceToHost, st));
+                FCK(cudaStreamSynchronize(st));
+                total = ro[0];
+                limit = ro[1];
+            } else { total = 0; limit = hm[M_START]; }
+        }
+        FCK(fx->bases.reserve(total + 64));
+        if (nlines && total) {
+            const unsigned cb = (unsigned)std::min<uint64_t>((nlines + 7) / 8, 148ull * 16);
+            k_fa_copy<<<cb, 256, 0, st>>>(d_text, L, (const uint64_t *)fx->outpos.p, nlines, limit, (uint8_t *)fx->bases.p);
+            ctx_add_launches(ctx, 1);
+        }
+        info->n_records = nrec;
+        info->n_bases = total;
+        info->max_read_len = 0; // unknown: the sketching entry points measure it
+        info->consumed = final ? n_bytes : std::min<uint64_t>(limit, n_bytes);
+        info->d_qual_off = nullptr;
+    }
+    FCK(cudaMemcpyAsync((uint64_t *)fx->rec_off.p + info->n_records, &info->consumed, 8, cudaMemcpyHostToDevice, st));
+    FCK(cudaStreamSynchronize(st));
+    info->n_lines = nlines;
+    info->d_bases = (uint8_t *)fx->bases.p;
+    info->d_read_off = (uint64_t *)fx->read_off.p;
+    info->d_rec_off = (uint64_t *)fx->rec_off.p;
+    info->d_line_off = L;
+    info->status = B200SK_OK;
+    return 0;
+}
+
+int b200sk_copy_to_host(b200sk_ctx *ctx, void *dst, const void *d_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!dst || !d_src))) return B200SK_ERR_BAD_ARG;
+    FCK(cudaSetDevice(ctx_device(ctx)));
+    FCK(cudaDeviceSynchronize());
+    if (bytes) FCK(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *text, uint64_t n_bytes, int format,
+                     int final, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+                     int32_t **read_status, uint64_t *n_out) {
+    if (!ctx || !p || !info || (n_bytes && !text)) return B200SK_ERR_BAD_ARG;
+    int rc = b200sk_check_params(p);
+    if (rc) return rc;
+    FCK(cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t st = ctx_stream(ctx);
+    FxState *fx = state_of(ctx);
+    FCK(fx->text.reserve(((n_bytes + 15) & ~15ull) + 16));
+    if (n_bytes) FCK(cudaMemcpyAsync(fx->text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = b200sk_fastx_parse_device(ctx, (const uint8_t *)fx->text.p, n_bytes, format, final, st, info))) return rc;
+    const uint64_t nrec = info->n_records;
+    b200sk_params q = *p;
+    if (q.max_read_len == 0) q.max_read_len = info->max_read_len; // FASTQ: measured by the parse
+    const uint32_t pw = q.pos_width == 1 ? 1u : q.pos_width == 2 ? 2u : 4u;
+    uint64_t cap = b200sk_output_bound(&q, info->n_bases, nrec, 0);
+    uint64_t got = 0;
+    FCK(fx->o_off.reserve((nrec + 1) * 8));
+    FCK(fx->o_status.reserve((nrec + 1) * 4));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        FCK(fx->o_val.reserve(cap * 8 + 64));
+        if (q.want_pos) FCK(fx->o_pos.reserve(cap * pw + 64));
+        rc = b200sk_run_device(ctx, &q, info->d_bases, info->d_read_off, nrec, info->n_bases, (uint64_t *)fx->o_val.p,
+                               q.want_pos ? (uint32_t *)fx->o_pos.p : nullptr, (uint64_t *)fx->o_off.p,
+                               (int32_t *)fx->o_status.p, cap, st, &got);
+        if (rc != B200SK_ERR_CAPACITY) break;
+        cap = got;
+    }
+    if (rc) return rc;
+    FCK(fx->h_val.reserve(got * 8 + 8));
+    FCK(fx->h_off.reserve((nrec + 1) * 8));
+    FCK(fx->h_status.reserve((nrec + 1) * 4));
+    if (q.want_pos) FCK(fx->h_pos.reserve(got * pw + 8));
+    if (got) FCK(cudaMemcpyAsync(fx->h_val.p, fx->o_val.p, got * 8, cudaMemcpyDeviceToHost, st));
+    if (got && q.want_pos) FCK(cudaMemcpyAsync(fx->h_pos.p, fx->o_pos.p, got * pw, cudaMemcpyDeviceToHost, st));
+    FCK(cudaMemcpyAsync(fx->h_off.p, fx->o_off.p, (nrec + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (nrec) FCK(cudaMemcpyAsync(fx->h_status.p, fx->o_status.p, nrec * 4, cudaMemcpyDeviceToHost, st));
+    FCK(cudaStreamSynchronize(st));
+    if (out_val) *out_val = (uint64_t *)fx->h_val.p;
+    if (out_pos) *out_pos = q.want_pos ? (uint32_t *)fx->h_pos.p : nullptr;
+    if (out_off) *out_off = (uint64_t *)fx->h_off.p;
+    if (read_status) *read_status = (int32_t *)fx->h_status.p;
+    if (n_out) *n_out = got;
+    return 0;
+}
+
+} // extern "C"

@@ -45,6 +45,8 @@ extern "C" {
 #define B200SK_ERR_INVALID_M (-11)      /* sketches/iterator.go:50  ErrInvalidM     */
 #define B200SK_ERR_INVALID_SCALE (-12)  /* sketches/iterator.go:53  ErrInvalidScale */
 #define B200SK_ERR_K_TOO_LARGE (-13)    /* sketches/iterator.go:47  ErrKTooLarge (k >= 65535) */
+#define B200SK_ERR_NOT_FASTX (-20)      /* seqio/fastx/reader.go:37  ErrNotFASTXFormat                      */
+#define B200SK_ERR_BAD_FASTQ (-21)      /* seqio/fastx/reader.go:40,43 ErrBadFASTQFormat / ErrUnequalSeqAndQual */
 /* library-level conditions (no reference counterpart) */
 #define B200SK_ERR_CUDA (-100)          /* a CUDA runtime call failed; see b200sk_last_error */
 #define B200SK_ERR_NO_DEVICE (-101)     /* no CUDA device: there is NO CPU fallback */
@@ -151,6 +153,53 @@ int b200sk_enqueue_device(b200sk_ctx *ctx, const b200sk_params *p,
                           uint64_t *d_out_val, uint32_t *d_out_pos, uint64_t *d_out_off,
                           int32_t *d_read_status, uint64_t capacity, void *stream,
                           uint32_t *d_flags);
+
+/* ---- record feeder: seqio/fastx.Reader.Read (seqio/fastx/reader.go:233-471) as a batch operation ----------
+ * The caller side of the path.  The reference reads one record per Read() call: finds the
+ * next delimiter that follows a newline, strips line ends, joins the sequence lines (parseRecord,
+ * reader.go:372-471).  Here a whole chunk of FASTA/FASTQ text is split into records on the device and its
+ * sequences land packed in HBM in exactly the layout b200sk_run_device takes (bases + read_off), so a
+ * chunk goes text -> records -> sketches without the bases ever visiting the host.
+ * Supported: FASTA with any line structure; FASTQ records of four lines (B200SK_ERR_BAD_FASTQ otherwise);
+ * LF or CRLF line ends; leading blank lines; a last line without newline.  Alphabet guessing and per-letter
+ * validation (reader.go:430-452) are not done here. */
+#define B200SK_FASTX_FASTA 1
+#define B200SK_FASTX_FASTQ 2
+typedef struct b200sk_fastx_info {
+    int32_t format;        /* B200SK_FASTX_FASTA / _FASTQ (reader.go:271-304: first byte that is not a newline) */
+    int32_t status;        /* B200SK_OK or the error also returned                                              */
+    uint64_t n_records;    /* complete records found                                                            */
+    uint64_t n_bases;      /* bytes in d_bases = d_read_off[n_records]                                          */
+    uint64_t n_lines;      /* lines looked at                                                                   */
+    uint64_t consumed;     /* text bytes the records cover: feed text[consumed:] + the next chunk next time     */
+    uint64_t bad_record;   /* B200SK_ERR_BAD_FASTQ: index of the first record that is not header/seq/+/qual     */
+    uint32_t max_read_len; /* FASTQ: longest sequence (the max_read_len hint of b200sk_params); FASTA: 0        */
+    uint32_t reserved;
+    /* library-owned device arrays, valid until the next feeder call on this ctx */
+    uint8_t *d_bases;      /* record.Seq.Seq of every record, concatenated                                      */
+    uint64_t *d_read_off;  /* [n_records+1] offsets into d_bases                                                */
+    uint64_t *d_rec_off;   /* [n_records+1] text offset of each record's delimiter; [n_records] = consumed      */
+    uint64_t *d_qual_off;  /* FASTQ: [n_records] text offset of the quality line; FASTA: NULL                   */
+    uint64_t *d_line_off;  /* [n_lines+1] text offset of every line start                                       */
+} b200sk_fastx_info;
+
+/* d_text: the chunk in HBM, 16-byte aligned, readable up to the next 16-byte boundary past n_bytes.
+ * format: 0 = detect, else B200SK_FASTX_* (a chunk that continues a file starts at a record and passes
+ * the file's format).  final: 1 = the text ends here (the last record is complete), 0 = more follows (the
+ * last, possibly cut, record is left for the next call: see consumed). */
+int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n_bytes, int format, int final,
+                              void *stream, b200sk_fastx_info *info);
+
+/* Host entry point for the whole front of the path: replaces
+ *     for { record, err := reader.Read(); it, _ := sketches.NewXxx(record.Seq, ...); for it.Next() ... }
+ * over one chunk of FASTA/FASTQ text in host memory (pinned for full copy speed): copy to the device,
+ * split into records, sketch, copy the sketches back.  Outputs as b200sk_run. */
+int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *text, uint64_t n_bytes, int format,
+                     int final, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+                     int32_t **read_status, uint64_t *n_out);
+
+/* Synchronous copy of a library-owned device array (the feeder's tables) into host memory. */
+int b200sk_copy_to_host(b200sk_ctx *ctx, void *dst, const void *d_src, uint64_t bytes);
 
 /* Error text: the reference's error strings for the codes that mirror them
  * (iterator.go:34-53, sketch.go:32-42), library text otherwise. */

@@ -51,9 +51,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        src = os.path.join(_HERE, "sketch_oracle.c")
+        srcs = [os.path.join(_HERE, f) for f in ("sketch_oracle.c", "fastx_oracle.c")]
         if (not os.path.exists(_LIB_PATH)
-                or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)):
+                or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)):
             build()
         L = C.CDLL(_LIB_PATH)
         u8p, u64p, i64p, ip = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint64),
@@ -250,3 +250,39 @@ def run_batch(bases, off, mode, k, w=0, s=0, canonical=True, circular=False, cod
                         _p(pos, C.c_uint32) if want_pos else None, None)
         res.update(off=out_off, val=val[:total], pos=pos[:total] if want_pos else None)
     return res
+
+
+# ---------------------------------------------------------------- record feeder oracle (fastx_oracle.c)
+FASTX_FASTA, FASTX_FASTQ = 1, 2
+ERR_NOT_FASTX, ERR_BAD_FASTQ = -20, -21
+
+
+def fastx_parse(text):
+    """seqio/fastx.Reader.Read until EOF over `text` (bytes): the records' sequences packed, their offsets,
+    the text offset of every record delimiter / quality line, and the header length."""
+    L = lib()
+    u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+    f = L.ora_fastx_parse
+    f.restype = C.c_int
+    f.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_int), u64p, u64p, C.POINTER(u8p), C.POINTER(u64p),
+                  C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p)]
+    L.ora_fastx_free.argtypes = [C.c_void_p]
+    fmt = C.c_int(0)
+    n_rec, n_bases = C.c_uint64(0), C.c_uint64(0)
+    bases = u8p()
+    ro, rc, qo, nl = u64p(), u64p(), u64p(), u64p()
+    text = bytes(text)
+    st = f(text, len(text), C.byref(fmt), C.byref(n_rec), C.byref(n_bases), C.byref(bases), C.byref(ro),
+           C.byref(rc), C.byref(qo), C.byref(nl))
+    n, nb = n_rec.value, n_bases.value
+    out = {
+        "status": st, "format": fmt.value, "n_records": n,
+        "bases": np.ctypeslib.as_array(bases, shape=(max(nb, 1),))[:nb].copy(),
+        "read_off": np.ctypeslib.as_array(ro, shape=(n + 1,)).copy(),
+        "rec_off": np.ctypeslib.as_array(rc, shape=(n + 1,))[:n].copy(),
+        "qual_off": np.ctypeslib.as_array(qo, shape=(n + 1,))[:n].copy(),
+        "name_len": np.ctypeslib.as_array(nl, shape=(n + 1,))[:n].copy(),
+    }
+    for p in (bases, ro, rc, qo, nl):
+        L.ora_fastx_free(C.cast(p, C.c_void_p))
+    return out

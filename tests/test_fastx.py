@@ -1,0 +1,226 @@
+"""Record feeder: oracle = literal restatement of seqio/fastx.Reader.Read/parseRecord
+(oracle/fastx_oracle.c); GPU = b200sk_fastx_parse_device / b200sk_run_fastx through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+REF = "/root/reference/seqio/fastx"
+
+
+def make_fastq(n, read_len, seed, crlf=False, at_quals=False, tail_newline=True, lower=False):
+    rng = np.random.default_rng(seed)
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    seqs = []
+    for i in range(n):
+        L = int(read_len if np.isscalar(read_len) else read_len[i])
+        s = bytes(np.frombuffer(b"acgtn" if lower else b"ACGTN", dtype=np.uint8)[rng.integers(0, 5 if i % 7 == 0 else 4, size=L)])
+        q = bytearray(rng.integers(33, 74, size=L, dtype=np.uint8).tobytes())
+        if at_quals and L and i % 3 == 0:
+            q[0] = ord("@")
+        seqs.append(s)
+        out.append(b"@r%d desc %d" % (i, i) + nl + s + nl + b"+" + nl + bytes(q) + nl)
+    text = b"".join(out)
+    if not tail_newline and text:
+        text = text[:-len(nl)]
+    return text, seqs
+
+
+def make_fasta(n, seed, width=60, crlf=False, blank_lines=False):
+    rng = np.random.default_rng(seed)
+    nl = b"\r\n" if crlf else b"\n"
+    out, seqs = [], []
+    for i in range(n):
+        L = int(rng.integers(0, 700))
+        s = bytes(np.frombuffer(b"ACGTacgtN>@", dtype=np.uint8)[rng.integers(0, 9 if i % 5 else 11, size=L)])
+        # a '>' or '@' inside a line is data, but never at a line start
+        rows = [s[j:j + width] for j in range(0, L, width)]
+        rows = [(b"A" + r[1:]) if r[:1] in (b">", b"@") else r for r in rows]
+        seqs.append(b"".join(rows))
+        out.append(b">seq%d some description" % i + nl)
+        for r in rows:
+            out.append(r + nl)
+            if blank_lines and rng.integers(0, 6) == 0:
+                out.append(nl)
+    return b"".join(out), seqs
+
+
+# ------------------------------------------------------------------ oracle (CPU)
+def test_oracle_pinned_by_reference_fixtures():
+    """reader_test.go:84,105,125,130-158: record counts of the reference's own fixtures."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present (GPU box)")
+    want = {"test.fa": 6, "test.fq": 8, "test2.fq": 5, "test3.fq": 3}
+    for name, n in want.items():
+        r = oracle.fastx_parse(open(os.path.join(REF, name), "rb").read())
+        assert r["status"] == 0 and r["n_records"] == n, name
+    r = oracle.fastx_parse(open(os.path.join(REF, "test3.fq"), "rb").read())
+    lens = np.diff(r["read_off"].astype(np.int64))
+    assert len(set(lens.tolist())) == 1  # reader_test.go:130-158: equal-length records, '@'-leading quality lines
+
+
+def test_oracle_rules():
+    r = oracle.fastx_parse(b"\n\n@r1 d\nACGT\n+\n@III\n@r2\nAC\r\n+\r\nII\r\n")
+    assert r["status"] == 0 and r["format"] == oracle.FASTX_FASTQ and r["n_records"] == 2
+    assert bytes(r["bases"]) == b"ACGTAC" and r["read_off"].tolist() == [0, 4, 6]
+    assert r["rec_off"].tolist() == [2, 20] and r["qual_off"].tolist() == [15, 31]
+    r = oracle.fastx_parse(b">a b\nAC\nGT\n\n>b\nTT>A\nC")
+    assert r["n_records"] == 2 and bytes(r["bases"]) == b"ACGTTT>AC" and r["name_len"].tolist() == [3, 1]
+    assert oracle.fastx_parse(b"hello\n")["status"] == oracle.ERR_NOT_FASTX
+    assert oracle.fastx_parse(b"\r\n>a\nAC\n")["status"] == oracle.ERR_NOT_FASTX  # only '\n' may lead (reader.go:286)
+    assert oracle.fastx_parse(b"@r\nACGT\n+\nII\n")["status"] == oracle.ERR_BAD_FASTQ
+    # multi-line FASTQ is legal for the reference (reader.go:396-412)
+    r = oracle.fastx_parse(b"@r\nAC\nGT\n+\nII\nII\n@s\nA\n+\nI\n")
+    assert r["status"] == 0 and r["n_records"] == 2 and bytes(r["bases"]) == b"ACGTA"
+    text, seqs = make_fastq(50, 37, 3, at_quals=True)
+    r = oracle.fastx_parse(text)
+    assert r["n_records"] == 50 and bytes(r["bases"]) == b"".join(seqs)
+    text, seqs = make_fasta(40, 4, blank_lines=True, crlf=True)
+    r = oracle.fastx_parse(text)
+    assert r["n_records"] == 40 and bytes(r["bases"]) == b"".join(seqs)
+
+
+def test_head_id_desc():
+    from bio_b200.fastx import parse_head_id_and_desc as f
+    assert f(b"id desc more") == (b"id", b"desc more")
+    assert f(b"id\t  desc") == (b"id", b"desc")
+    assert f(b"id") == (b"id", b"")
+    assert f(b"id   ") == (b"id", b"")
+
+
+# ------------------------------------------------------------------ GPU parity
+def _ctx():
+    from bio_b200 import _cabi as cabi
+    return cabi, cabi.Context(0)
+
+
+def _parse_gpu(ctx, text, fmt=0, final=True):
+    import torch
+    n = len(text)
+    host = np.zeros((n + 15) // 16 * 16 + 16, dtype=np.uint8)
+    host[:n] = np.frombuffer(text, dtype=np.uint8)
+    d = torch.from_numpy(host).cuda()
+    info = ctx.fastx_parse_device(d, n, fmt, final)
+    return info, ctx.fastx_fetch(info)
+
+
+def _same(g, o, fastq):
+    assert g["n_records"] == o["n_records"]
+    assert np.array_equal(g["read_off"], o["read_off"])
+    assert np.array_equal(g["bases"], o["bases"])
+    assert np.array_equal(g["rec_off"][:-1], o["rec_off"])
+    if fastq:
+        assert np.array_equal(g["qual_off"], o["qual_off"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(crlf=True), dict(at_quals=True), dict(tail_newline=False),
+                                dict(lower=True, at_quals=True, crlf=True)])
+def test_fastq_parity(kw):
+    cabi, ctx = _ctx()
+    for n, L, seed in ((1, 150, 1), (1000, 150, 2), (333, 1, 3), (5000, 151, 4)):
+        text, seqs = make_fastq(n, L, seed, **kw)
+        for lead in (b"", b"\n\n\n"):
+            info, g = _parse_gpu(ctx, lead + text)
+            o = oracle.fastx_parse(lead + text)
+            assert o["status"] == 0 and g["format"] == cabi.FASTX_FASTQ
+            _same(g, o, True)
+            assert g["consumed"] == len(lead + text) and g["max_read_len"] == L
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_fastq_ragged_and_long():
+    cabi, ctx = _ctx()
+    rng = np.random.default_rng(9)
+    lens = rng.integers(0, 3000, size=400)
+    lens[5] = 70000
+    text, seqs = make_fastq(len(lens), lens, 11, at_quals=True)
+    info, g = _parse_gpu(ctx, text + b"\n\n")  # trailing blank lines are not a record
+    o = oracle.fastx_parse(text + b"\n\n")
+    _same(g, o, True)
+    assert bytes(g["bases"]) == b"".join(seqs)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(crlf=True), dict(blank_lines=True), dict(width=7), dict(width=100000)])
+def test_fasta_parity(kw):
+    cabi, ctx = _ctx()
+    for n, seed in ((1, 1), (300, 2), (2000, 3)):
+        text, seqs = make_fasta(n, seed, **kw)
+        for tail in (b"", b"\n"):
+            t = (text + tail) if tail else text[:-1] if text.endswith(b"\n") and not kw.get("crlf") else text
+            info, g = _parse_gpu(ctx, t)
+            o = oracle.fastx_parse(t)
+            assert o["status"] == 0 and g["format"] == cabi.FASTX_FASTA
+            _same(g, o, False)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_errors_and_edges():
+    cabi, ctx = _ctx()
+    for bad in (b"hello\n", b"\r\n>a\nAC\n"):
+        with pytest.raises(cabi.SketchError) as e:
+            _parse_gpu(ctx, bad)
+        assert e.value.code == cabi.ERR_NOT_FASTX
+    for bad in (b"@r\nACGT\n+\nII\n", b"@r\nAC\nGT\n+\nII\nII\n", b"@r\nACGT\n+\nIIII\n@s\nAC\n"):
+        with pytest.raises(cabi.SketchError) as e:
+            _parse_gpu(ctx, bad)
+        assert e.value.code == cabi.ERR_BAD_FASTQ
+    info, g = _parse_gpu(ctx, b"\n\n\n")
+    assert g["n_records"] == 0
+    info, g = _parse_gpu(ctx, b">only header")
+    o = oracle.fastx_parse(b">only header")
+    assert g["n_records"] == o["n_records"] == 1 and g["read_off"].tolist() == [0, 0]
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_streaming_chunks_and_reader():
+    """A text cut at arbitrary places: consumed/carry-over reproduces the whole-file parse; Reader.Read()
+    yields the reference's Record fields."""
+    from bio_b200 import fastx
+    cabi, ctx = _ctx()
+    for text, seqs, fq in (make_fastq(700, 150, 5, at_quals=True) + (True,), make_fasta(300, 6, blank_lines=True) + (False,)):
+        o = oracle.fastx_parse(text)
+        rd = fastx.Reader(text, ctx=ctx, chunk_bytes=10007)
+        recs = list(rd)
+        assert len(recs) == o["n_records"] and rd.IsFastq == fq
+        assert [r.Seq for r in recs] == seqs
+        for i in (0, len(recs) // 2, len(recs) - 1):
+            start = int(o["rec_off"][i])
+            name = text[start + 1:start + 1 + int(o["name_len"][i])]
+            assert recs[i].Name == name and recs[i].ID == name.split(b" ")[0]
+            if fq:
+                q = int(o["qual_off"][i])
+                assert recs[i].Qual == text[q:q + len(seqs[i])]
+    if os.path.isdir(REF):
+        for name, n in {"test.fa": 6, "test.fq": 8, "test2.fq": 5, "test3.fq": 3}.items():
+            assert len(list(fastx.Reader(os.path.join(REF, name), ctx=ctx))) == n
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_run_fastx_matches_sketch_of_oracle_records():
+    """text -> records -> minimizers in one C-ABI call == oracle parse + oracle NextMinimizer."""
+    cabi, ctx = _ctx()
+    text, seqs = make_fastq(3000, 150, 21)
+    o = oracle.fastx_parse(text)
+    for mode, omode, kw in ((cabi.MODE_MINIMIZER, oracle.MODE_MINIMIZER, dict(k=21, w=11)),
+                            (cabi.MODE_NTHASH, oracle.MODE_NTHASH, dict(k=21)),
+                            (cabi.MODE_SYNCMER, oracle.MODE_SYNCMER, dict(k=21, s=11))):
+        res = ctx.run_fastx(cabi.make_params(mode, **kw), text)
+        ref = oracle.run_batch(o["bases"], o["read_off"], omode, threads=4, **kw)
+        assert np.array_equal(res["val"], ref["val"]) and np.array_equal(res["off"], ref["off"])
+        assert np.array_equal(res["pos"], ref["pos"]) and np.array_equal(res["status"], ref["status"])
+    text, seqs = make_fasta(200, 8)
+    o = oracle.fastx_parse(text)
+    res = ctx.run_fastx(cabi.make_params(cabi.MODE_MINIMIZER, k=21, w=11), text)
+    ref = oracle.run_batch(o["bases"], o["read_off"], oracle.MODE_MINIMIZER, threads=4, k=21, w=11)
+    assert np.array_equal(res["val"], ref["val"]) and np.array_equal(res["off"], ref["off"])
+    ctx.close()
