@@ -24,9 +24,10 @@
 //   k_fx_detect   first record byte and format
 //   k_fx_count    newlines (and line-initial '>') after the first record byte: sizes the tables
 //   k_fx_lines    line-start table L[] in one pass (per-tile newline counts, decoupled look-back)
-//   k_fq_scan     FASTQ: per record validate + sequence length -> read_off / rec_off / qual_off (look-back scan)
+//   k_fq_scan     FASTQ: per record validate + sequence length -> read_off / rec_off / qual_off (look-back scan),
+//                 then the sequence lines -> packed bases in the same pass
 //   k_fa_scan     FASTA: per line header flag + sequence bytes -> out_pos per line, read_off / rec_off per record
-//   k_fq_copy / k_fa_copy   sequence bytes -> packed bases (a warp per record / per line)
+//   k_fa_copy     FASTA sequence lines -> packed bases (a warp per line)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -113,6 +114,11 @@ __global__ void k_fx_detect(const uint8_t *__restrict__ t, uint64_t n, unsigned 
     }
 }
 
+// bit 7 of every byte of w that equals the byte replicated in c4 (exact: no borrow between bytes)
+__device__ __forceinline__ uint32_t eq_msb(uint32_t w, uint32_t c4) {
+    const uint32_t x = w ^ c4;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
 // bit j of the result: byte j of the 16-byte vector equals c
 __device__ __forceinline__ uint32_t eq_mask16(const uint4 v, uint32_t c4) {
     const uint32_t a = __vcmpeq4(v.x, c4) & 0x01010101u, b = __vcmpeq4(v.y, c4) & 0x01010101u;
@@ -131,22 +137,39 @@ __device__ __forceinline__ uint32_t range_mask16(uint64_t pos, uint64_t lo, uint
 // newlines at positions >= start0, and '>' that start a line (FASTA records) -- sizes the tables
 __global__ void __launch_bounds__(256) k_fx_count(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta) {
     const uint64_t start0 = meta[M_START];
+    const bool fasta = meta[M_FORMAT] == B200SK_FASTX_FASTA;
     const uint64_t nvec = (n + 15) / 16;
     unsigned long long nl = 0, hd = 0;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t pos = v * 16;
-        if (pos + 16 <= start0) continue;
-        const uint4 x = reinterpret_cast<const uint4 *>(t)[v];
-        const uint32_t rm = range_mask16(pos, start0, n);
-        const uint32_t m = eq_mask16(x, 0x0a0a0a0au) & rm;
-        nl += __popc(m);
-        // '>' preceded by '\n' (the byte before the vector decides for bit 0); the first record byte counts too
-        uint32_t g = eq_mask16(x, 0x3e3e3e3eu) & rm;
-        if (g) {
-            uint32_t prev_nl = (eq_mask16(x, 0x0a0a0a0au) << 1) & 0xffffu;
-            if (pos > 0 && t[pos - 1] == '\n') prev_nl |= 1u;
-            if (start0 >= pos && start0 < pos + 16) prev_nl |= 1u << (uint32_t)(start0 - pos);
-            hd += __popc(g & prev_nl);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += 4 * stride) {
+        uint4 xs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { // four independent 16-byte loads in flight
+            const uint64_t v = v0 + u * stride;
+            xs[u] = v < nvec ? reinterpret_cast<const uint4 *>(t)[v] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t v = v0 + u * stride;
+            const uint64_t pos = v * 16;
+            if (v >= nvec || pos + 16 <= start0) continue;
+            const uint4 x = xs[u];
+            if (pos >= start0 && pos + 16 <= n && !fasta) { // interior vector, FASTQ: only the newline count matters
+                nl += __popc(eq_msb(x.x, 0x0a0a0a0au)) + __popc(eq_msb(x.y, 0x0a0a0a0au)) +
+                      __popc(eq_msb(x.z, 0x0a0a0a0au)) + __popc(eq_msb(x.w, 0x0a0a0a0au));
+                continue;
+            }
+            const uint32_t rm = range_mask16(pos, start0, n);
+            const uint32_t nlm = eq_mask16(x, 0x0a0a0a0au);
+            nl += __popc(nlm & rm);
+            // '>' preceded by '\n' (the byte before the vector decides for bit 0); the first record byte counts too
+            const uint32_t g = fasta ? (eq_mask16(x, 0x3e3e3e3eu) & rm) : 0u;
+            if (g) {
+                uint32_t prev_nl = (nlm << 1) & 0xffffu;
+                if (pos > 0 && t[pos - 1] == '\n') prev_nl |= 1u;
+                if (start0 >= pos && start0 < pos + 16) prev_nl |= 1u << (uint32_t)(start0 - pos);
+                hd += __popc(g & prev_nl);
+            }
         }
     }
 #pragma unroll
@@ -161,37 +184,58 @@ __global__ void __launch_bounds__(256) k_fx_count(const uint8_t *__restrict__ t,
 }
 
 // L[i] = start of line i: L[0] = start0, L[i] = position after the i-th newline at or after start0.
-// One pass: tiles of 4 KB, per-tile counts ordered by a decoupled look-back.
+// One pass: tiles of 32 KB (128 contiguous bytes per thread, eight 16-byte loads in flight), per-tile newline
+// counts ordered by a decoupled look-back.
+#define FX_TILE 32768ull
 __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta,
                                                   uint64_t *tile_state, uint64_t *__restrict__ L) {
     __shared__ uint32_t warp_sums[34];
     __shared__ uint64_t s_tile, s_base;
     const uint64_t start0 = meta[M_START];
-    const uint64_t ntiles = (n + 4095) / 4096;
+    const uint64_t ntiles = (n + FX_TILE - 1) / FX_TILE;
     const uint32_t tid = threadIdx.x;
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(meta + M_TICKET, 1ULL);
         __syncthreads();
         const uint64_t tile = s_tile;
         if (tile >= ntiles) break;
-        const uint64_t pos = tile * 4096 + (uint64_t)tid * 16;
-        uint32_t m = 0;
-        if (pos < n && pos + 16 > start0) {
-            const uint4 x = reinterpret_cast<const uint4 *>(t)[pos / 16];
-            m = eq_mask16(x, 0x0a0a0a0au) & range_mask16(pos, start0, n);
+        const uint64_t pos0 = tile * FX_TILE + (uint64_t)tid * 128;
+        uint4 xs[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint64_t pos = pos0 + u * 16;
+            xs[u] = (pos < n && pos + 16 > start0) ? reinterpret_cast<const uint4 *>(t)[pos / 16] : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t m[8], cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint64_t pos = pos0 + u * 16;
+            m[u] = 0;
+            if (pos >= start0 && pos + 16 <= n) { // interior: count first, positions only where there is a newline
+                const uint32_t a = eq_msb(xs[u].x, 0x0a0a0a0au), b = eq_msb(xs[u].y, 0x0a0a0a0au);
+                const uint32_t c = eq_msb(xs[u].z, 0x0a0a0a0au), d = eq_msb(xs[u].w, 0x0a0a0a0au);
+                if (a | b | c | d) m[u] = eq_mask16(xs[u], 0x0a0a0a0au);
+            } else if (pos < n && pos + 16 > start0) {
+                m[u] = eq_mask16(xs[u], 0x0a0a0a0au) & range_mask16(pos, start0, n);
+            }
+            cnt += __popc(m[u]);
         }
         uint32_t total;
-        const uint32_t excl = block_excl_scan((uint32_t)__popc(m), warp_sums, &total);
+        const uint32_t excl = block_excl_scan(cnt, warp_sums, &total);
         if (tid < 32) {
             const uint64_t b = lookback_exclusive(tile_state, tile, total);
             if (tid == 0) s_base = b;
         }
         __syncthreads();
         uint64_t idx = s_base + excl + 1; // line index the next newline of this thread opens
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            L[idx++] = pos + j + 1;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            uint32_t mm = m[u];
+            while (mm) {
+                const int j = __ffs(mm) - 1;
+                mm &= mm - 1;
+                L[idx++] = pos0 + u * 16 + j + 1;
+            }
         }
         __syncthreads();
     }
@@ -215,7 +259,7 @@ __device__ __forceinline__ uint32_t line_len(const uint8_t *t, uint64_t s, uint6
 __global__ void __launch_bounds__(256) k_fq_scan(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
                                                  uint64_t nrec, uint64_t nlines, int final, unsigned long long *meta,
                                                  uint64_t *tile_state, uint64_t *read_off, uint64_t *rec_off,
-                                                 uint64_t *qual_off) {
+                                                 uint64_t *qual_off, uint8_t *__restrict__ bases) {
     __shared__ uint32_t warp_sums[34];
     __shared__ uint64_t s_tile, s_base;
     const uint32_t tid = threadIdx.x;
@@ -233,8 +277,10 @@ __global__ void __launch_bounds__(256) k_fq_scan(const uint8_t *__restrict__ t, 
         if (tile >= ntiles) break;
         const uint64_t r = tile * 256 + tid;
         uint32_t len = 0;
+        uint64_t s = 0;
         if (r < nrec) {
-            const uint64_t h = L[4 * r], s = L[4 * r + 1], p = L[4 * r + 2], q = L[4 * r + 3], e = L[4 * r + 4];
+            const uint64_t h = L[4 * r], p = L[4 * r + 2], q = L[4 * r + 3], e = L[4 * r + 4];
+            s = L[4 * r + 1];
             len = line_len(t, s, p);
             const uint32_t qlen = line_len(t, q, e);
             // header '@'; a NON-EMPTY line starting with '+' (reader.go:399); equal lengths (:415)
@@ -254,28 +300,23 @@ __global__ void __launch_bounds__(256) k_fq_scan(const uint8_t *__restrict__ t, 
             if (tid == 0) s_base = b;
         }
         __syncthreads();
+        const uint64_t dst = s_base + excl;
         if (r < nrec) {
-            read_off[r] = s_base + excl;
+            read_off[r] = dst;
             if (r + 1 == nrec) {
-                read_off[nrec] = s_base + excl + len;
-                meta[M_TOTAL] = s_base + excl + len;
+                read_off[nrec] = dst + len;
+                meta[M_TOTAL] = dst + len;
             }
+        }
+        // the sequence lines of the warp's 32 records -> packed bases, record after record
+        for (int i = 0; i < 32; i++) {
+            const uint64_t si = __shfl_sync(0xffffffffu, s, i), di = __shfl_sync(0xffffffffu, dst, i);
+            const uint32_t li = __shfl_sync(0xffffffffu, len, i);
+            for (uint32_t j = tid & 31u; j < li; j += 32u) bases[di + j] = t[si + j];
         }
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256) k_fq_copy(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
-                                                 const uint64_t *__restrict__ read_off, uint64_t nrec,
-                                                 uint8_t *__restrict__ bases) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t nwarp = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrec; r += nwarp) {
-        const uint64_t s = L[4 * r + 1], d = read_off[r];
-        const uint32_t len = (uint32_t)(read_off[r + 1] - d);
-        for (uint32_t i = lane; i < len; i += 32u) bases[d + i] = t[s + i];
-    }
-}
-
 // FASTA, one thread per line (reader.go:383-393): header lines open a record, every other line adds its
 // bytes to the current record.  Two ordered sums: sequence bytes and header count.
 __global__ void __launch_bounds__(256) k_fa_scan(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
@@ -423,7 +464,7 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
     FCK(fx->lines.reserve((nl + 3) * 8));
     uint64_t *L = (uint64_t *)fx->lines.p;
     {
-        const uint64_t ntiles = (n_bytes + 4095) / 4096;
+        const uint64_t ntiles = (n_bytes + FX_TILE - 1) / FX_TILE;
         FCK(fx->state_a.reserve((ntiles + 1) * 8));
         FCK(cudaMemsetAsync(fx->state_a.p, 0, (ntiles + 1) * 8, st));
         const unsigned blocks = (unsigned)std::min<uint64_t>(ntiles, 148ull * 8);
@@ -444,9 +485,10 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         FCK(cudaMemcpyAsync(meta + M_BADREC, &none, 8, cudaMemcpyHostToDevice, st));
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ntiles, 148ull * 8));
         // without `final` the lines after the last whole record simply stay for the next chunk
+        FCK(fx->bases.reserve(n_bytes / 2 + 64)); // sequence and quality are equally long: at most half the text
         k_fq_scan<<<blocks, 256, 0, st>>>(d_text, L, nrec, final ? nlines : 4 * nrec, final, meta,
                                           (uint64_t *)fx->state_b.p, (uint64_t *)fx->read_off.p,
-                                          (uint64_t *)fx->rec_off.p, (uint64_t *)fx->qual_off.p);
+                                          (uint64_t *)fx->rec_off.p, (uint64_t *)fx->qual_off.p, (uint8_t *)fx->bases.p);
         ctx_add_launches(ctx, 1);
         FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
         FCK(cudaStreamSynchronize(st));
@@ -456,12 +498,6 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
             return B200SK_ERR_BAD_FASTQ;
         }
         const uint64_t total = nrec ? hm[M_TOTAL] : 0;
-        FCK(fx->bases.reserve(total + 64));
-        if (nrec) {
-            const unsigned cb = (unsigned)std::min<uint64_t>((nrec + 7) / 8, 148ull * 16);
-            k_fq_copy<<<cb, 256, 0, st>>>(d_text, L, (const uint64_t *)fx->read_off.p, nrec, (uint8_t *)fx->bases.p);
-            ctx_add_launches(ctx, 1);
-        }
         info->n_records = nrec;
         info->n_bases = total;
         info->max_read_len = (uint32_t)hm[M_MAXLEN];
