@@ -22,8 +22,8 @@
 //
 // Kernels (all memory-bound, one pass each over what they touch):
 //   k_fx_detect   first record byte and format
-//   k_fx_count    newlines (and line-initial '>') after the first record byte: sizes the tables
-//   k_fx_lines    line-start table L[] in one pass (per-tile newline counts, decoupled look-back)
+//   k_fx_lines    line-start table L[] in one pass (per-tile newline counts, decoupled look-back); the table is
+//                 sized from a bound, the pass also counts the lines and the FASTA record delimiters
 //   k_fq_scan     FASTQ: per record validate + sequence length -> read_off / rec_off / qual_off (look-back scan),
 //                 then the sequence lines -> packed bases in the same pass
 //   k_fa_scan     FASTA: per line header flag + sequence bytes -> out_pos per line, read_off / rec_off per record
@@ -134,66 +134,19 @@ __device__ __forceinline__ uint32_t range_mask16(uint64_t pos, uint64_t lo, uint
     return m & 0xffffu;
 }
 
-// newlines at positions >= start0, and '>' that start a line (FASTA records) -- sizes the tables
-__global__ void __launch_bounds__(256) k_fx_count(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta) {
-    const uint64_t start0 = meta[M_START];
-    const bool fasta = meta[M_FORMAT] == B200SK_FASTX_FASTA;
-    const uint64_t nvec = (n + 15) / 16;
-    unsigned long long nl = 0, hd = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += 4 * stride) {
-        uint4 xs[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { // four independent 16-byte loads in flight
-            const uint64_t v = v0 + u * stride;
-            xs[u] = v < nvec ? reinterpret_cast<const uint4 *>(t)[v] : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint64_t v = v0 + u * stride;
-            const uint64_t pos = v * 16;
-            if (v >= nvec || pos + 16 <= start0) continue;
-            const uint4 x = xs[u];
-            if (pos >= start0 && pos + 16 <= n && !fasta) { // interior vector, FASTQ: only the newline count matters
-                nl += __popc(eq_msb(x.x, 0x0a0a0a0au)) + __popc(eq_msb(x.y, 0x0a0a0a0au)) +
-                      __popc(eq_msb(x.z, 0x0a0a0a0au)) + __popc(eq_msb(x.w, 0x0a0a0a0au));
-                continue;
-            }
-            const uint32_t rm = range_mask16(pos, start0, n);
-            const uint32_t nlm = eq_mask16(x, 0x0a0a0a0au);
-            nl += __popc(nlm & rm);
-            // '>' preceded by '\n' (the byte before the vector decides for bit 0); the first record byte counts too
-            const uint32_t g = fasta ? (eq_mask16(x, 0x3e3e3e3eu) & rm) : 0u;
-            if (g) {
-                uint32_t prev_nl = (nlm << 1) & 0xffffu;
-                if (pos > 0 && t[pos - 1] == '\n') prev_nl |= 1u;
-                if (start0 >= pos && start0 < pos + 16) prev_nl |= 1u << (uint32_t)(start0 - pos);
-                hd += __popc(g & prev_nl);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        nl += __shfl_xor_sync(0xffffffffu, nl, o);
-        hd += __shfl_xor_sync(0xffffffffu, hd, o);
-    }
-    if ((threadIdx.x & 31u) == 0) {
-        if (nl) atomicAdd(meta + M_NL, nl);
-        if (hd) atomicAdd(meta + M_HDR, hd);
-    }
-}
-
 // L[i] = start of line i: L[0] = start0, L[i] = position after the i-th newline at or after start0.
 // One pass: tiles of 32 KB (128 contiguous bytes per thread, eight 16-byte loads in flight), per-tile newline
 // counts ordered by a decoupled look-back.
 #define FX_TILE 32768ull
 __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta,
-                                                  uint64_t *tile_state, uint64_t *__restrict__ L) {
+                                                  uint64_t *tile_state, uint64_t *__restrict__ L, uint64_t cap) {
     __shared__ uint32_t warp_sums[34];
     __shared__ uint64_t s_tile, s_base;
     const uint64_t start0 = meta[M_START];
+    const bool fasta = meta[M_FORMAT] == B200SK_FASTX_FASTA;
     const uint64_t ntiles = (n + FX_TILE - 1) / FX_TILE;
     const uint32_t tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0 && fasta && start0 < n) atomicAdd(meta + M_HDR, 1ULL); // the first record
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(meta + M_TICKET, 1ULL);
         __syncthreads();
@@ -227,25 +180,35 @@ __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t,
             if (tid == 0) s_base = b;
         }
         __syncthreads();
+        if (tid == 0 && tile + 1 == ntiles) meta[M_NL] = s_base + total; // all newlines of the text
         uint64_t idx = s_base + excl + 1; // line index the next newline of this thread opens
+        uint32_t hd = 0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             uint32_t mm = m[u];
             while (mm) {
                 const int j = __ffs(mm) - 1;
                 mm &= mm - 1;
-                L[idx++] = pos0 + u * 16 + j + 1;
+                const uint64_t ls = pos0 + u * 16 + j + 1;
+                if (idx < cap) L[idx] = ls; // a table sized from a bound: the host re-runs with the exact size
+                idx++;
+                if (fasta && ls < n && t[ls] == '>') hd++; // a record delimiter: '>' right after a newline
             }
+        }
+        if (fasta) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hd += __shfl_xor_sync(0xffffffffu, hd, o);
+            if ((tid & 31u) == 0 && hd) atomicAdd(meta + M_HDR, (unsigned long long)hd);
         }
         __syncthreads();
     }
 }
 // the two ends of the table
-__global__ void k_fx_lines_finish(uint64_t n, const unsigned long long *meta, uint64_t nl, uint64_t *L) {
-    const uint64_t start0 = meta[M_START];
+__global__ void k_fx_lines_finish(uint64_t n, const unsigned long long *meta, uint64_t *L, uint64_t cap) {
+    const uint64_t start0 = meta[M_START], nl = meta[M_NL];
     L[0] = start0;
     // a last line without '\n': its (virtual) newline sits at n, so the "next line" starts at n + 1
-    if (n > start0 && meta[M_LAST] != '\n') L[nl + 1] = n + 1;
+    if (n > start0 && meta[M_LAST] != '\n' && nl + 1 < cap) L[nl + 1] = n + 1;
 }
 
 __device__ __forceinline__ uint32_t line_len(const uint8_t *t, uint64_t s, uint64_t next) { // without '\n' and one '\r'
@@ -438,14 +401,26 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         return 0;
     }
     k_fx_detect<<<1, 32, 0, st>>>(d_text, n_bytes, meta);
-    {
-        const uint64_t nvec = (n_bytes + 15) / 16;
-        const unsigned blocks = (unsigned)std::min<uint64_t>((nvec + 255) / 256, 148ull * 16);
-        k_fx_count<<<blocks, 256, 0, st>>>(d_text, n_bytes, meta);
+    ctx_add_launches(ctx, 1);
+    // The line table is sized from a bound (a line per 32 bytes of text) and filled in the same pass that
+    // counts the lines; only a text with shorter lines on average pays a second pass with the exact size.
+    const uint64_t ntiles_l = (n_bytes + FX_TILE - 1) / FX_TILE;
+    FCK(fx->state_a.reserve((ntiles_l + 1) * 8));
+    uint64_t cap = n_bytes / 32 + 4096;
+    for (int attempt = 0;; attempt++) {
+        FCK(fx->lines.reserve(cap * 8));
+        FCK(cudaMemsetAsync(fx->state_a.p, 0, (ntiles_l + 1) * 8, st));
+        FCK(cudaMemsetAsync(meta + M_NL, 0, 16, st));     // newline and header counts
+        FCK(cudaMemsetAsync(meta + M_TICKET, 0, 8, st));
+        const unsigned blocks = (unsigned)std::min<uint64_t>(ntiles_l, 148ull * 8);
+        k_fx_lines<<<blocks, 256, 0, st>>>(d_text, n_bytes, meta, (uint64_t *)fx->state_a.p, (uint64_t *)fx->lines.p, cap);
+        k_fx_lines_finish<<<1, 1, 0, st>>>(n_bytes, meta, (uint64_t *)fx->lines.p, cap);
+        ctx_add_launches(ctx, 2);
+        FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
+        FCK(cudaStreamSynchronize(st));
+        if (hm[M_NL] + 3 <= cap || attempt) break;
+        cap = hm[M_NL] + 3;
     }
-    ctx_add_launches(ctx, 2);
-    FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
-    FCK(cudaStreamSynchronize(st));
     const int detected = (int)hm[M_FORMAT];
     if (hm[M_START] >= n_bytes) { // only newlines: nothing to parse
         info->format = format;
@@ -461,17 +436,7 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
     const bool tail = hm[M_LAST] != '\n'; // a last line without its newline
     // lines the parse may use: without `final` an unterminated last line is not complete
     const uint64_t nlines = nl + ((tail && final) ? 1 : 0);
-    FCK(fx->lines.reserve((nl + 3) * 8));
     uint64_t *L = (uint64_t *)fx->lines.p;
-    {
-        const uint64_t ntiles = (n_bytes + FX_TILE - 1) / FX_TILE;
-        FCK(fx->state_a.reserve((ntiles + 1) * 8));
-        FCK(cudaMemsetAsync(fx->state_a.p, 0, (ntiles + 1) * 8, st));
-        const unsigned blocks = (unsigned)std::min<uint64_t>(ntiles, 148ull * 8);
-        k_fx_lines<<<blocks, 256, 0, st>>>(d_text, n_bytes, meta, (uint64_t *)fx->state_a.p, L);
-        k_fx_lines_finish<<<1, 1, 0, st>>>(n_bytes, meta, nl, L);
-        ctx_add_launches(ctx, 2);
-    }
     uint64_t nrec = 0;
     if (detected == B200SK_FASTX_FASTQ) {
         nrec = nlines / 4;
