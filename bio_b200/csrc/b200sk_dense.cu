@@ -669,9 +669,15 @@ static cudaError_t launch_dense_mode(const KArgs &a, int threads, int blocks, cu
     return cudaGetLastError();
 }
 
+cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ); // b200sk_nthash.cu
+bool nthash_warp_fits(uint32_t span_max);
+
 cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
     switch (a.mode) {
-    case B200SK_MODE_NTHASH: return launch_dense_mode<B200SK_MODE_NTHASH>(a, threads, blocks, st, occ);
+    case B200SK_MODE_NTHASH:
+        // values only (no Index() array): the warp-tile kernel; with positions: the generic dense kernel
+        if (!a.out_pos && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
+        return launch_dense_mode<B200SK_MODE_NTHASH>(a, threads, blocks, st, occ);
     case B200SK_MODE_KMER: return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
     case B200SK_MODE_PROTEIN: return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
     case B200SK_MODE_SIMHASH: { // counter planes: enough bits for n = k-m+1 (a.w carries m)

@@ -1,0 +1,347 @@
+// NextHash (sketches/iterator.go:615-665; ntHash-1 of will-rowe/nthash v0.4.0) for batches that want the
+// values only: one tile of 32 items per WARP, no block-wide barrier, no ordering between tiles (the output
+// offsets of a dense mode follow from the read lengths: k_scan_reads wrote out_off before this kernel runs).
+//
+// Per tile:
+//   1. one 1-D TMA bulk copy brings the tile's byte range into the warp's shared-memory buffer;
+//   2. if every byte is one of ACGTacgt the tile is rewritten as cls * 40 (cls = (byte >> 1) & 3), so that
+//      (in & 0x18) | (out & 0x60) is the byte offset into 16-entry pair tables
+//          X[in, out] = A[in] ^ rol(A[out], k),   Y[in, out] = rol(B[in], k-1) ^ ror(B[out], 1)
+//      and a rolling step is one PRMT, two conflict-free LDS.64 and one three-input XOR per 32-bit half; the
+//      first k-1 bases fold two at a time through F2X / F2Y.  Any other byte: the tile is fetched again and
+//      walks the general 256-entry tables (forward seed by byte, reverse seed by byte & 7);
+//   3. every lane walks its item 16 steps at a time into its row of the staging area (row stride 136 B: the
+//      lanes' 8-byte stores and the half-warp row reads below are both 2 wavefronts, the minimum for 64-bit
+//      accesses); whole blocks run as straight-line code so that the table loads of all 16 steps are in
+//      flight together;
+//   4. the 32 rows leave two per store instruction -- lanes 0-15 one row, lanes 16-31 the next, each a
+//      contiguous 128-byte run of out_val.
+// (Tried: one cp.async.bulk shared -> global per lane and row instead of step 4.  The TMA engine takes such
+// 128-byte stores at the full HBM write bandwidth -- scripts/ubench/bulkstore.cu: 6.4 TB/s -- but UBLKCP is a
+// uniform-datapath instruction: with per-lane addresses the compiler emits a loop over the 32 lanes, 12
+// instructions per row against 6 per warp-step here.)
+#include "b200sk_tile.cuh"
+
+namespace b200sk {
+
+namespace {
+
+#define NH_ROW 136u              // staging row stride (16 values + 8 B of padding)
+#define NH_STAGE (32u * NH_ROW)  // per warp
+#define NH_DESC 256u             // 32 row destinations (8 B each)
+#define NH_TAB_GENERAL 8192u     // tIn[256], tOut[256] (16 B entries)
+#define NH_TAB_FAST 8192u        // fast tables start here (640 B used)
+#define NH_TABLES (8192u + 1024u)
+// fast-table offsets: X 0, Y 128, F2X 256, F2Y 384, F1X 512, F1Y 544
+
+__device__ __forceinline__ uint64_t lds64(const uint8_t *sm, uint32_t o) { return *reinterpret_cast<const uint64_t *>(sm + o); }
+__device__ __forceinline__ uint32_t lds8(const uint8_t *sm, uint32_t o) { return sm[o]; }
+
+__device__ __forceinline__ uint32_t fast_word(uint32_t w, uint32_t &bad) {
+    const uint32_t x = w | 0x20202020u;                // lower case
+    const uint32_t t = (x >> 1) & 0x03030303u;         // class of every byte: a=0 c=1 t=2 g=3
+    const uint32_t u2 = t | (t >> 4);                  // nibble pairs in bytes 0 and 2
+    const uint32_t sel = __byte_perm(u2, 0u, 0x4420u); // four nibbles = PRMT selector
+    bad |= x ^ __byte_perm(0x67746361u, 0u, sel);      // 'a','c','t','g' by class
+    return t * 40u;                                    // (cls << 3) | (cls << 5)
+}
+
+// 16 consecutive bytes from an arbitrary shared-memory offset, as aligned words lined up with PRMT
+struct Bytes16 {
+    uint32_t x[4];
+    __device__ __forceinline__ void load(const uint8_t *sm, uint32_t p) {
+        const uint32_t a = p & ~3u, sel = 0x3210u + 0x1111u * (p & 3u);
+        uint32_t w[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) w[i] = *reinterpret_cast<const uint32_t *>(sm + a + 4u * i);
+#pragma unroll
+        for (int g = 0; g < 4; g++) x[g] = __byte_perm(w[g], w[g + 1], sel);
+    }
+    __device__ __forceinline__ uint32_t byte(const int j) const { return __byte_perm(x[j >> 2], 0u, 0x4440u | (j & 3)); }
+};
+
+// 16 virtual steps of one lane into its staging row (slot e = virtual step v0 + e).  FAST: pair tables over
+// fast bytes, else the general tables over the original bytes.  FULL: every slot is a real step, and slot 0 is
+// the item's first k-mer (no outgoing base) iff FIRST0; otherwise slots [lo, hi) are real and slot `first`
+// (16 = none) is the first k-mer.
+template <bool CANON, bool FAST, bool FULL, bool FIRST0>
+__device__ __forceinline__ void block16(uint8_t *smem, uint32_t FT, const Bytes16 &win, const Bytes16 &wout, uint32_t lo,
+                                        uint32_t hi, uint32_t first, uint32_t s_row, uint64_t &fh, uint64_t &rh) {
+    uint32_t po[4];
+    if (FAST) {
+#pragma unroll
+        for (int gq = 0; gq < 4; gq++) po[gq] = (win.x[gq] & 0x18181818u) | (wout.x[gq] & 0x60606060u);
+    }
+    const ulonglong2 *tIn = reinterpret_cast<const ulonglong2 *>(smem), *tOut = tIn + 256;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        if (FULL || ((uint32_t)e >= lo && (uint32_t)e < hi)) {
+            const bool is_first = FULL ? (FIRST0 && e == 0) : ((uint32_t)e == first);
+            if (FAST) {
+                const uint32_t o = __byte_perm(po[e >> 2], 0u, 0x4440u | (e & 3));
+                if (is_first) {
+                    fh = rol1(fh) ^ lds64(smem, FT + 512u + (o & 0x18u));
+                    rh = ror1(rh) ^ lds64(smem, FT + 544u + (o & 0x18u));
+                } else {
+                    fh = rol1(fh) ^ lds64(smem, FT + o);
+                    rh = ror1(rh) ^ lds64(smem, FT + 128u + o);
+                }
+            } else {
+                const ulonglong2 in = tIn[win.byte(e)];
+                ulonglong2 o = make_ulonglong2(0, 0);
+                if (!is_first) o = tOut[wout.byte(e)];
+                fh = rol1(fh) ^ o.x ^ in.x;
+                rh = ror1(rh) ^ o.y ^ in.y;
+            }
+            *reinterpret_cast<uint64_t *>(smem + s_row + e * 8) = (CANON && rh < fh) ? rh : fh; // iterator.go:659
+        }
+    }
+}
+
+struct NItem {
+    uint64_t gb0, obase;
+    uint32_t nb, nstep;
+};
+
+__device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, uint64_t item, uint64_t n_items, NItem &it) {
+    it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0;
+    if (item >= n_items) return;
+    uint64_t r = item;
+    uint32_t c = 0;
+    if (a.item_first) {
+        uint64_t lo = 0, hi = a.n_reads; // largest r with item_first[r] <= item
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (a.item_first[mid] <= item) lo = mid; else hi = mid;
+        }
+        r = lo;
+        c = (uint32_t)(item - a.item_first[r]);
+    }
+    const uint64_t o0 = a.off[r], L = a.off[r + 1] - o0;
+    const uint64_t orig = a.off_orig ? a.off_orig[r + 1] - a.off_orig[r] : L;
+    int32_t st;
+    const uint32_t np = read_positions(g, r, L, orig, &st);
+    it.gb0 = o0;
+    if (np == 0) return;
+    const uint32_t p0 = c * a.C;
+    it.nstep = min(np, p0 + a.C) - p0;
+    it.obase = a.out_off[r] - a.out_base + p0;
+    it.nb = it.nstep + (uint32_t)a.k - 1;
+    it.gb0 = o0 + p0;
+}
+
+template <bool CANON>
+__global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t tile_bytes_cap, uint32_t warp_stride) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const int k = a.k;
+    {
+        ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 256;
+        for (uint32_t b = tid; b < 256; b += blockDim.x) {
+            const uint64_t f = fwd_seed(b), r = rev_seed(b);
+            tIn[b] = make_ulonglong2(f, rol64(r, (unsigned)(k - 1)));
+            tOut[b] = make_ulonglong2(rol64(f, (unsigned)k), ror64(r, 1));
+        }
+        if (tid < 16) {
+            const char letter[4] = {'A', 'C', 'T', 'G'}; // class = (byte >> 1) & 3
+            const uint32_t lo = tid & 3u, hi = tid >> 2;
+            const uint64_t Alo = fwd_seed((uint32_t)letter[lo]), Ahi = fwd_seed((uint32_t)letter[hi]);
+            const uint64_t Blo = rev_seed((uint32_t)letter[lo]), Bhi = rev_seed((uint32_t)letter[hi]);
+            uint64_t *q = reinterpret_cast<uint64_t *>(smem + NH_TAB_FAST);
+            q[tid] = Alo ^ rol64(Ahi, (unsigned)k);                                          // X
+            q[16 + tid] = rol64(Blo, (unsigned)(k - 1)) ^ ror64(Bhi, 1);                     // Y
+            q[32 + tid] = rol64(Alo, 1) ^ Ahi;                                               // F2X: lo first, hi second
+            q[48 + tid] = ror64(rol64(Blo, (unsigned)(k - 1)), 1) ^ rol64(Bhi, (unsigned)(k - 1)); // F2Y
+            if (tid < 4) {
+                q[64 + tid] = Alo;                                  // F1X
+                q[68 + tid] = rol64(Blo, (unsigned)(k - 1));        // F1Y
+            }
+        }
+    }
+    const uint32_t region = NH_TABLES + wid * warp_stride;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
+    const uint32_t s_tile = region + 16;
+    uint8_t *tilebuf = smem + s_tile;
+    const uint32_t s_stage = s_tile + tile_bytes_cap;
+    const uint32_t s_desc = s_stage + NH_STAGE;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads(); // tables + barriers ready; the only block-wide barrier
+    const uint64_t n_items = a.n_items_dev ? *a.n_items_dev : a.n_items;
+    const uint64_t total = a.out_off[a.n_reads] - a.out_base;
+    if (total > a.capacity) {
+        if (blockIdx.x == 0 && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
+        return;
+    }
+    const ReadGeom g = a.geom();
+    const uint32_t FT = NH_TAB_FAST;
+    uint32_t parity = 0;
+    for (;;) {
+        uint64_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.ticket, 1ULL);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        const uint64_t item0 = tile * 32ull;
+        if (item0 >= n_items) break;
+        const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_items - item0);
+        NItem it;
+        nthash_item(a, g, item0 + lane, n_items, it);
+        const uint64_t lo = __shfl_sync(0xffffffffu, it.gb0, 0);
+        const uint64_t hi = __shfl_sync(0xffffffffu, it.gb0 + it.nb, (int)nvalid - 1);
+        const uint64_t lo_al = lo & ~15ULL;
+        const uint64_t span = hi > lo_al ? hi - lo_al : 0;
+        const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
+        const bool span_ok = bytes + 16u <= tile_bytes_cap; // + the word-granular look-ahead of the last block
+        if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
+        bool fast = false;
+        if (bytes && span_ok) {
+            if (lane == 0) {
+                fence_proxy_async(); // the previous tile's generic-proxy accesses precede the async write
+                mbar_expect_tx(mbar, bytes);
+                tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            uint32_t bad = 0;
+            for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
+                uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
+                v.x = fast_word(v.x, bad); v.y = fast_word(v.y, bad);
+                v.z = fast_word(v.z, bad); v.w = fast_word(v.w, bad);
+                *reinterpret_cast<uint4 *>(tilebuf + o) = v;
+            }
+            fast = !__any_sync(0xffffffffu, bad != 0);
+            if (!fast) { // some other byte (alignment slop included): the original bytes again, general tables
+                __syncwarp();
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(mbar, bytes);
+                    tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
+                }
+                mbar_wait(mbar, parity);
+                parity ^= 1u;
+            }
+        }
+        __syncwarp();
+        const uint32_t nstep = span_ok ? it.nstep : 0u;
+        // Virtual steps: v = u + shift with shift = (element index of the item's first hash in out_val) mod 4, so
+        // that every staging row starts on a 32-byte sector of global memory: rows that straddle sectors cost
+        // a third of the write bandwidth (scripts/ubench/bulkstore.cu: 2.96 vs 4.0 TB/s for this pattern).
+        uint64_t *g0 = a.out_val + it.obase;
+        const uint32_t shift = nstep ? (uint32_t)((reinterpret_cast<uintptr_t>(g0) >> 3) & 3u) : 0u;
+        const uint32_t vend = shift + nstep; // one past the last virtual step
+        // where the lane's rows go: address of virtual step 0
+        *reinterpret_cast<uint64_t *>(smem + s_desc + lane * 8u) = reinterpret_cast<uint64_t>(g0 - shift);
+        uint32_t maxv = vend;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, o));
+        const uint32_t sb = nstep ? s_tile + (uint32_t)(it.gb0 - lo_al) : s_tile + 8u; // idle lanes: a safe base
+        const uint32_t sbv = sb - shift;                                               // byte of virtual base 0
+        uint64_t fh = 0, rh = 0;
+        if (nstep) {
+            if (fast) {
+                int j = 0;
+                for (; j + 1 < k - 1; j += 2) {
+                    const uint32_t o = (lds8(smem, sb + j) & 0x18u) | (lds8(smem, sb + j + 1) & 0x60u);
+                    fh = rol64(fh, 2) ^ lds64(smem, FT + 256u + o);
+                    rh = ror64(rh, 2) ^ lds64(smem, FT + 384u + o);
+                }
+                if (j < k - 1) {
+                    const uint32_t o = lds8(smem, sb + j) & 0x18u;
+                    fh = rol1(fh) ^ lds64(smem, FT + 512u + o);
+                    rh = ror1(rh) ^ lds64(smem, FT + 544u + o);
+                }
+            } else {
+                const ulonglong2 *tIn = reinterpret_cast<const ulonglong2 *>(smem);
+                for (int j = 0; j < k - 1; j++) {
+                    const ulonglong2 e = tIn[lds8(smem, sb + j)];
+                    fh = rol1(fh) ^ e.x;
+                    rh = ror1(rh) ^ e.y;
+                }
+            }
+        }
+        const uint32_t last_block = vend ? ((vend - 1) / 16u) * 16u : 0u; // first virtual step of the lane's last block
+        const uint32_t s_row = s_stage + lane * NH_ROW;
+        __syncwarp();
+        for (uint32_t v0 = 0; v0 < maxv; v0 += 16u) {
+            // lanes whose item is finished (or absent) re-read their own last block: the loads stay
+            // unconditional and inside the tile
+            const uint32_t vl = min(v0, last_block);
+            Bytes16 win, wout;
+            win.load(smem, sbv + vl + (uint32_t)k - 1);
+            wout.load(smem, sbv + vl - 1);
+            // real slots of this block: [lo, hi); the item's first k-mer is virtual step `shift`
+            const uint32_t lo = v0 == 0 ? shift : 0u;
+            const uint32_t hi = vend > v0 ? min(16u, vend - v0) : 0u;
+            const uint32_t first = v0 == 0 ? shift : 16u;
+            const bool full = __all_sync(0xffffffffu, lo == 0u && hi == 16u && shift == 0u) ||
+                              (v0 != 0 && __all_sync(0xffffffffu, hi == 16u));
+            // straight-line code for whole blocks; the predicated variant only for a block some lane does not fill
+            if (fast) {
+                if (full) { if (v0 == 0) block16<CANON, true, true, true>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh);
+                            else block16<CANON, true, true, false>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh); }
+                else block16<CANON, true, false, false>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh);
+            } else {
+                if (full) { if (v0 == 0) block16<CANON, false, true, true>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh);
+                            else block16<CANON, false, true, false>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh); }
+                else block16<CANON, false, false, false>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh);
+            }
+            __syncwarp();
+            // flush: rows 2i and 2i+1 per store instruction
+            const uint32_t half = lane >> 4, e = lane & 15u;
+            if (full) {
+#pragma unroll 8
+                for (uint32_t i = 0; i < 16u; i++) {
+                    const uint32_t src = 2u * i + half;
+                    uint64_t *dst = reinterpret_cast<uint64_t *>(lds64(smem, s_desc + src * 8u));
+                    dst[v0 + e] = lds64(smem, s_stage + src * NH_ROW + e * 8u);
+                }
+            } else {
+                const uint32_t lohi = lo | (hi << 8);
+                for (uint32_t i = 0; i < 16u; i++) {
+                    const uint32_t src = 2u * i + half;
+                    const uint32_t lh = __shfl_sync(0xffffffffu, lohi, (int)src);
+                    if (e >= (lh & 0xffu) && e < (lh >> 8)) {
+                        uint64_t *dst = reinterpret_cast<uint64_t *>(lds64(smem, s_desc + src * 8u));
+                        dst[v0 + e] = lds64(smem, s_stage + src * NH_ROW + e * 8u);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+} // namespace
+
+// values-only ntHash batches (out_pos == nullptr).  occ != nullptr: the grid is sized here, report 1.
+cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ) {
+    if (occ) { *occ = 1; return cudaSuccess; }
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    const uint32_t tile_cap = ((32u * a.span_max + 32u + 15u) & ~15u) + 16u;
+    const uint32_t stride = (16u + tile_cap + NH_STAGE + NH_DESC + 15u) & ~15u;
+    int nw = (int)((227u * 1024u - NH_TABLES) / stride);
+    if (nw > 24) nw = 24;
+    if (nw < 1) return cudaErrorInvalidValue;
+    const uint32_t sm_total = NH_TABLES + (uint32_t)nw * stride;
+    const void *fn = a.canonical ? (const void *)k_nthash_warp<true> : (const void *)k_nthash_warp<false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total);
+    if (e != cudaSuccess) return e;
+    if (a.canonical) k_nthash_warp<true><<<sm_count, nw * 32, sm_total, st>>>(a, tile_cap, stride);
+    else k_nthash_warp<false><<<sm_count, nw * 32, sm_total, st>>>(a, tile_cap, stride);
+    return cudaGetLastError();
+}
+
+bool nthash_warp_fits(uint32_t span_max) {
+    const uint32_t tile_cap = ((32u * span_max + 32u + 15u) & ~15u) + 16u;
+    const uint32_t stride = (16u + tile_cap + NH_STAGE + NH_DESC + 15u) & ~15u;
+    return (227u * 1024u - NH_TABLES) / stride >= 4u;
+}
+
+} // namespace b200sk

@@ -382,3 +382,26 @@ def test_narrow_positions(gpu_ctx, pw):
     if pw == 1:
         with pytest.raises(cabi.SketchError):
             gpu_ctx.run(cabi.make_params(cabi.MODE_NTHASH, 21, pos_width=1, max_read_len=300), b, o)
+
+
+@pytest.mark.parametrize("k,canonical", [(21, True), (21, False), (5, True), (31, True), (64, True), (2, False)])
+def test_nthash_values_only_kernel(gpu_ctx, k, canonical):
+    """want_pos=False takes the warp-tile ntHash kernel (b200sk_nthash.cu): all-ACGT fast path with pair tables,
+    general path for any other byte, whole and partial 16-step blocks, long reads in chunks, circular."""
+    cases = []
+    cases.append(synth.uniform_reads(20000, 150, 5) + (150,))                       # fast path, 8 blocks + tail of 2
+    cases.append(synth.uniform_reads(3000, 16 + k - 1, 6) + (16 + k - 1,))          # exactly one whole block
+    cases.append(synth.ragged_reads(np.random.default_rng(7).integers(0, 400, size=3000), 7) + (0,))
+    cases.append(synth.ragged_reads(np.random.default_rng(8).integers(0, 300, size=2000), 8,
+                                    alphabet=b"ACGTNacgtRYKMSWBDHVU-*") + (0,))      # general tables
+    cases.append(synth.ragged_reads([150] * 999 + [0, 3, 20], 9, alphabet=b"ACGTacgt") + (150,))  # lower case, fast
+    L = synth.ont_like_lengths(200, 45)
+    cases.append(synth.ragged_reads(L, 45) + (0,))                                   # chunked items
+    for b, o, hint in cases:
+        for circular in (False, True):
+            p = cabi.make_params(cabi.MODE_NTHASH, k, canonical=canonical, circular=circular, max_read_len=hint,
+                                 want_pos=False)
+            res = gpu_ctx.run(p, b, o)
+            ref = oracle.run_batch(b, o, oracle.MODE_NTHASH, threads=8, k=k, canonical=canonical, circular=circular)
+            assert res["pos"] is None
+            assert_same(res, ref, f"k={k} canonical={canonical} circular={circular} hint={hint}")
