@@ -23,7 +23,7 @@ cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStrea
 bool sparse_reg_supported(int mode, int k, int w, int s);
 cudaError_t launch_scan_counts(const KArgs &a, uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st);
 cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *ill,
-                                 cudaStream_t st);
+                                 cudaStream_t st, uint64_t n_bases);
 cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
 bool build_codon_aux(int id, uint8_t *aux);
 cudaError_t launch_scan_geom(const uint64_t *off, uint64_t n_reads, const ReadGeom &g, uint64_t *out,
@@ -313,7 +313,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     if (q.mode == B200SK_MODE_KMER) {
         // NextKmer stops at the first illegal base (iterator.go:730-748): find it once per read
         CK(ctx->ill.reserve(n_reads * 4));
-        CK(launch_first_illegal(d_bases, d_off, n_reads, (uint32_t *)ctx->ill.p, st));
+        CK(launch_first_illegal(d_bases, d_off, n_reads, (uint32_t *)ctx->ill.p, st, n_bases));
         ctx->launches++;
         a.ill = (const uint32_t *)ctx->ill.p;
     }

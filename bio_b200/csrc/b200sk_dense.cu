@@ -645,8 +645,55 @@ bool build_codon_aux(int id, uint8_t *aux) {
 }
 
 // ------------------------------------------------------------------ launch
+// The same per 16-byte vector of the whole base array (read boundaries ignored until a hit): every word is
+// first tested for "all of ACGTacgt" with the PRMT class trick; only a word that fails is looked at byte by
+// byte (IUPAC codes and U are legal, sketches/kmers.go:23-40), and only a truly illegal byte searches its read
+// and lowers ill[read] -- illegal bases are rare, so the pass is a plain streaming read.
+__global__ void __launch_bounds__(256) k_first_illegal_vec(const uint8_t *__restrict__ bases, uint64_t n_bases,
+                                                           const uint64_t *__restrict__ off, uint64_t n_reads,
+                                                           uint32_t *ill) {
+    const uint64_t b_lo = off[0], b_hi = off[n_reads]; // the bytes that belong to reads
+    (void)n_bases;
+    const uint64_t nvec = (b_hi + 15) / 16;
+    for (uint64_t v = b_lo / 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+         v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = reinterpret_cast<const uint4 *>(bases)[v];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t lc = w[i] | 0x20202020u;
+            const uint32_t t = (lc >> 1) & 0x03030303u;
+            const uint32_t u2 = t | (t >> 4);
+            const uint32_t sel = __byte_perm(u2, 0u, 0x4420u);
+            if (lc == __byte_perm(0x67746361u, 0u, sel)) continue; // four of a, c, g, t
+            for (int j = 0; j < 4; j++) {
+                const uint64_t pos = v * 16 + (uint64_t)i * 4 + j;
+                if (pos >= b_hi) break;
+                if (pos < b_lo) continue;
+                if (base2bit_of((w[i] >> (8 * j)) & 0xffu) != 4) continue;
+                uint64_t lo = 0, hi = n_reads; // read that holds byte pos: largest r with off[r] <= pos
+                while (hi - lo > 1) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (off[mid] <= pos) lo = mid; else hi = mid;
+                }
+                if (pos < off[lo + 1]) atomicMin(ill + lo, (uint32_t)(pos - off[lo]));
+            }
+        }
+    }
+}
+
 cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *ill,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, uint64_t n_bases) {
+    if (n_bases && (reinterpret_cast<uintptr_t>(bases) & 15u) == 0) {
+        // off[0] may be > 0 and the array is readable up to the next 16-byte boundary (the TMA contract)
+        cudaError_t e = cudaMemsetAsync(ill, 0xff, n_reads * 4, st);
+        if (e != cudaSuccess) return e;
+        const uint64_t nvec = (n_bases + 15) / 16;
+        uint64_t cb = (nvec + 255) / 256;
+        if (cb > 148 * 16) cb = 148 * 16;
+        k_first_illegal_vec<<<(unsigned)cb, 256, 0, st>>>(bases, n_bases, off, n_reads, ill);
+        return cudaGetLastError();
+    }
     uint64_t cb = (n_reads + 7) / 8;
     if (cb > 148 * 16) cb = 148 * 16;
     if (cb == 0) cb = 1;
@@ -678,7 +725,10 @@ cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t s
         // values only (no Index() array): the warp-tile kernel; with positions: the generic dense kernel
         if (!a.out_pos && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
         return launch_dense_mode<B200SK_MODE_NTHASH>(a, threads, blocks, st, occ);
-    case B200SK_MODE_KMER: return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
+    case B200SK_MODE_KMER:
+        // canonical codes, values only: the warp-tile kernel; both strands / positions: the generic dense kernel
+        if (!a.out_pos && a.canonical && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
+        return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
     case B200SK_MODE_PROTEIN: return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
     case B200SK_MODE_SIMHASH: { // counter planes: enough bits for n = k-m+1 (a.w carries m)
         const int n = a.k - a.w + 1;

@@ -20,6 +20,11 @@
 // 128-byte stores at the full HBM write bandwidth -- scripts/ubench/bulkstore.cu: 6.4 TB/s -- but UBLKCP is a
 // uniform-datapath instruction: with per-lane addresses the compiler emits a loop over the 32 lanes, 12
 // instructions per row against 6 per warp-step here.)
+// The same kernel also serves NextKmer (sketches/iterator.go:668-759) for canonical, values-only batches
+// (KIND_KMER): no tables beyond the 256-byte base2bit LUT (sketches/kmers.go:23-40), the rolling update of
+// iterator.go:736,740 and the canonical minimum of :754-756; reads with an illegal base stop before the first
+// k-mer that holds it (k_first_illegal + read_positions).  Both-strand k-mers and batches that want Index()
+// stay with the generic dense kernel.
 #include "b200sk_tile.cuh"
 
 namespace b200sk {
@@ -98,6 +103,24 @@ __device__ __forceinline__ void block16(uint8_t *smem, uint32_t FT, const Bytes1
     }
 }
 
+// KIND_KMER: 16 virtual steps of 2-bit codes (iterator.go:736,740,754).  lut: 256-byte base2bit table.
+template <bool CANON, bool FULL>
+__device__ __forceinline__ void block16_kmer(uint8_t *smem, const Bytes16 &win, uint32_t lo, uint32_t hi, uint32_t s_row,
+                                             uint64_t mask1, uint32_t sh, uint64_t &code, uint64_t &rc) {
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        if (FULL || ((uint32_t)e >= lo && (uint32_t)e < hi)) {
+            const uint64_t bit = smem[win.byte(e)] & 3u;
+            code = ((code & mask1) << 2) | bit;
+            rc = (rc >> 2) | ((bit ^ 3ull) << sh);
+            *reinterpret_cast<uint64_t *>(smem + s_row + e * 8) = (CANON && rc < code) ? rc : code;
+        }
+    }
+}
+
+#define KIND_NTHASH 0
+#define KIND_KMER 1
+
 struct NItem {
     uint64_t gb0, obase;
     uint32_t nb, nstep;
@@ -130,12 +153,25 @@ __device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, u
     it.gb0 = o0 + p0;
 }
 
-template <bool CANON>
+template <int KIND, bool CANON>
 __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t tile_bytes_cap, uint32_t warp_stride) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const int k = a.k;
-    {
+    if (KIND == KIND_KMER) {
+        for (uint32_t b = tid; b < 256; b += blockDim.x) {
+            uint32_t bit; // sketches/kmers.go:23-40 (IUPAC codes map to their first base)
+            switch (b) {
+            case 'A': case 'a': case 'D': case 'd': case 'H': case 'h': case 'M': case 'm':
+            case 'N': case 'n': case 'R': case 'r': case 'V': case 'v': case 'W': case 'w': bit = 0; break;
+            case 'B': case 'b': case 'C': case 'c': case 'S': case 's': case 'Y': case 'y': bit = 1; break;
+            case 'G': case 'g': case 'K': case 'k': bit = 2; break;
+            case 'T': case 't': case 'U': case 'u': bit = 3; break;
+            default: bit = 0; break; // illegal bases never reach a step (read_positions stops before them)
+            }
+            smem[b] = (uint8_t)bit;
+        }
+    } else {
         ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 256;
         for (uint32_t b = tid; b < 256; b += blockDim.x) {
             const uint64_t f = fwd_seed(b), r = rev_seed(b);
@@ -204,14 +240,15 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
             mbar_wait(mbar, parity);
             parity ^= 1u;
             uint32_t bad = 0;
+            if (KIND == KIND_NTHASH)
             for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
                 uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
                 v.x = fast_word(v.x, bad); v.y = fast_word(v.y, bad);
                 v.z = fast_word(v.z, bad); v.w = fast_word(v.w, bad);
                 *reinterpret_cast<uint4 *>(tilebuf + o) = v;
             }
-            fast = !__any_sync(0xffffffffu, bad != 0);
-            if (!fast) { // some other byte (alignment slop included): the original bytes again, general tables
+            fast = KIND == KIND_NTHASH && !__any_sync(0xffffffffu, bad != 0);
+            if (KIND == KIND_NTHASH && !fast) { // some other byte (alignment slop included): the original bytes again, general tables
                 __syncwarp();
                 if (lane == 0) {
                     fence_proxy_async();
@@ -237,8 +274,17 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
         for (int o = 16; o > 0; o >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, o));
         const uint32_t sb = nstep ? s_tile + (uint32_t)(it.gb0 - lo_al) : s_tile + 8u; // idle lanes: a safe base
         const uint32_t sbv = sb - shift;                                               // byte of virtual base 0
-        uint64_t fh = 0, rh = 0;
-        if (nstep) {
+        uint64_t fh = 0, rh = 0; // KIND_KMER: code and reverse-complement code
+        const uint32_t ksh = 2u * (uint32_t)(k - 1);
+        const uint64_t kmask1 = (1ull << ksh) - 1ull; // iterator.go:699
+        if (KIND == KIND_KMER) {
+            if (nstep)
+                for (int j = 0; j < k - 1; j++) {
+                    const uint64_t bit = smem[lds8(smem, sb + j)] & 3u;
+                    fh = (fh << 2) | bit;
+                    rh = (rh >> 2) | ((bit ^ 3ull) << ksh);
+                }
+        } else if (nstep) {
             if (fast) {
                 int j = 0;
                 for (; j + 1 < k - 1; j += 2) {
@@ -277,7 +323,10 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
             const bool full = __all_sync(0xffffffffu, lo == 0u && hi == 16u && shift == 0u) ||
                               (v0 != 0 && __all_sync(0xffffffffu, hi == 16u));
             // straight-line code for whole blocks; the predicated variant only for a block some lane does not fill
-            if (fast) {
+            if (KIND == KIND_KMER) {
+                if (full) block16_kmer<CANON, true>(smem, win, lo, hi, s_row, kmask1, ksh, fh, rh);
+                else block16_kmer<CANON, false>(smem, win, lo, hi, s_row, kmask1, ksh, fh, rh);
+            } else if (fast) {
                 if (full) { if (v0 == 0) block16<CANON, true, true, true>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh);
                             else block16<CANON, true, true, false>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh); }
                 else block16<CANON, true, false, false>(smem, FT, win, wout, lo, hi, first, s_row, fh, rh);
@@ -330,11 +379,12 @@ cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ) {
     if (nw > 24) nw = 24;
     if (nw < 1) return cudaErrorInvalidValue;
     const uint32_t sm_total = NH_TABLES + (uint32_t)nw * stride;
-    const void *fn = a.canonical ? (const void *)k_nthash_warp<true> : (const void *)k_nthash_warp<false>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total);
+    void (*fn)(const KArgs, uint32_t, uint32_t);
+    if (a.mode == B200SK_MODE_KMER) fn = k_nthash_warp<KIND_KMER, true>;
+    else fn = a.canonical ? k_nthash_warp<KIND_NTHASH, true> : k_nthash_warp<KIND_NTHASH, false>;
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total);
     if (e != cudaSuccess) return e;
-    if (a.canonical) k_nthash_warp<true><<<sm_count, nw * 32, sm_total, st>>>(a, tile_cap, stride);
-    else k_nthash_warp<false><<<sm_count, nw * 32, sm_total, st>>>(a, tile_cap, stride);
+    fn<<<sm_count, nw * 32, sm_total, st>>>(a, tile_cap, stride);
     return cudaGetLastError();
 }
 

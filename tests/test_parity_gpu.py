@@ -405,3 +405,21 @@ def test_nthash_values_only_kernel(gpu_ctx, k, canonical):
             ref = oracle.run_batch(b, o, oracle.MODE_NTHASH, threads=8, k=k, canonical=canonical, circular=circular)
             assert res["pos"] is None
             assert_same(res, ref, f"k={k} canonical={canonical} circular={circular} hint={hint}")
+
+
+@pytest.mark.parametrize("k", [1, 5, 21, 31, 32])
+def test_kmer_values_only_kernel(gpu_ctx, k):
+    """Canonical k-mer codes with want_pos=False take the warp-tile kernel: IUPAC codes (first base), illegal bases
+    (the read stops before the first k-mer holding one, status ErrIllegalBase), ragged and long reads."""
+    cases = [synth.uniform_reads(20000, 150, 15) + (150,),
+             synth.ragged_reads(np.random.default_rng(16).integers(0, 400, size=3000), 16) + (0,),
+             synth.ragged_reads(np.random.default_rng(17).integers(0, 300, size=2000), 17,
+                                alphabet=b"ACGTNacgtRYKMSWBDHVU") + (0,),
+             synth.ragged_reads(np.random.default_rng(18).integers(30, 300, size=2000), 18,
+                                alphabet=b"ACGTACGTACGTACGTACGTACGT-*X") + (0,),
+             synth.ragged_reads(synth.ont_like_lengths(150, 46), 46) + (0,)]
+    for b, o, hint in cases:
+        p = cabi.make_params(cabi.MODE_KMER, k, canonical=True, max_read_len=hint, want_pos=False)
+        res = gpu_ctx.run(p, b, o)
+        ref = oracle.run_batch(b, o, oracle.MODE_KMER, threads=8, k=k, canonical=True)
+        assert_same(res, ref, f"k={k} hint={hint}")
