@@ -287,3 +287,74 @@ func (it *Iterator) NextKmer() (uint64, bool, error) {
 
 // Index returns the 0-based position of the last returned element (iterator.go:776, sketch.go:488).
 func (it *Iterator) Index() int { return int(it.pos[it.i-1]) }
+
+// ---- record feeder: seqio/fastx.Reader.Read over a chunk of text (seqio/fastx/reader.go:233-471) -----------
+
+// ErrNotFASTXFormat / ErrBadFASTQFormat are the reference's errors (seqio/fastx/reader.go:16,19).
+var (
+	ErrNotFASTXFormat = errors.New("fastx: invalid FASTA/Q format")
+	ErrBadFASTQFormat = errors.New("fastx: bad fastq format")
+)
+
+// TextChunk is one chunk of FASTA/FASTQ text in C-owned pinned memory (fill Bytes()[:n] from the file or from
+// xopen's decompressor, prefixed with the Carry of the previous chunk).
+type TextChunk struct {
+	ctx  *Context
+	buf  unsafe.Pointer
+	cap_ int
+}
+
+// NewTextChunk allocates a pinned chunk buffer.
+func NewTextChunk(ctx *Context, capBytes int) *TextChunk {
+	return &TextChunk{ctx: ctx, buf: C.b200sk_alloc_pinned(C.size_t(capBytes)), cap_: capBytes}
+}
+
+// Bytes is the chunk buffer.
+func (t *TextChunk) Bytes() []byte { return unsafe.Slice((*byte)(t.buf), t.cap_) }
+
+// Free releases the buffer.
+func (t *TextChunk) Free() { C.b200sk_free_pinned(t.buf); t.buf = nil }
+
+// FastxResult is a sketched chunk: the Result of its records plus what locates every record in the text.
+type FastxResult struct {
+	Result
+	Format   int    // 1 FASTA, 2 FASTQ (pass it to the next chunk of the same file)
+	Records  int    // complete records in this chunk
+	Consumed int    // text[Consumed:n] is the cut record that opens the next chunk
+	IsFastq  bool
+}
+
+// MinimizerSketchText replaces
+//     for { rec, err := reader.Read(); sk, _ := sketches.NewMinimizerSketch(rec.Seq, k, w, false); for sk.Next() ... }
+// over text[:n]: ONE cgo call copies the chunk to the GPU, splits it into records there, sketches them and
+// brings the sketches back; the bases never exist as Go slices.
+func (t *TextChunk) MinimizerSketchText(n, format int, final bool, k, w int) (*FastxResult, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_MINIMIZER, k: C.int32_t(k), w: C.int32_t(w), want_pos: 1, pos_width: 4}
+	var info C.b200sk_fastx_info
+	var v *C.uint64_t
+	var ps *C.uint32_t
+	var o *C.uint64_t
+	var st *C.int32_t
+	var total C.uint64_t
+	rc := C.b200sk_run_fastx(t.ctx.h, &p, (*C.uint8_t)(t.buf), C.uint64_t(n), C.int(format), C.int(cbool(final)),
+		&info, &v, &ps, &o, &st, &total)
+	switch rc {
+	case 0:
+	case C.B200SK_ERR_NOT_FASTX:
+		return nil, ErrNotFASTXFormat
+	case C.B200SK_ERR_BAD_FASTQ:
+		return nil, ErrBadFASTQFormat
+	default:
+		return nil, codeToError(rc)
+	}
+	nrec := int(info.n_records)
+	return &FastxResult{
+		Result: Result{
+			val:    unsafe.Slice((*uint64)(unsafe.Pointer(v)), int(total)),
+			pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
+			off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), nrec+1),
+			status: unsafe.Slice((*int32)(unsafe.Pointer(st)), nrec),
+		},
+		Format: int(info.format), Records: nrec, Consumed: int(info.consumed), IsFastq: info.format == C.B200SK_FASTX_FASTQ,
+	}, nil
+}
