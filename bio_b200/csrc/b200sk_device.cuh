@@ -133,6 +133,40 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint64_t
     return excl;
 }
 
+// The same in two halves, so that work which does not need the prefix can sit between them: publish the
+// tile's own total first (later tiles can already add it up), resolve the exclusive prefix afterwards.
+__device__ __forceinline__ void lookback_publish(uint64_t *state, uint64_t tile, uint64_t total) {
+    if ((threadIdx.x & 31u) == 0)
+        st_state(state + tile, ((tile == 0 ? B200SK_FLAG_INC : B200SK_FLAG_AGG) << 62) | total);
+}
+__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t tile, uint64_t total) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0) return 0;
+    uint64_t excl = 0;
+    int64_t idx = (int64_t)tile - 1 - (int64_t)lane;
+    while (true) {
+        uint64_t v = (B200SK_FLAG_INC << 62); // lanes before tile 0 read as "inclusive 0"
+        if (idx >= 0) {
+            do {
+                v = ld_state(state + idx);
+            } while ((v >> 62) == B200SK_FLAG_EMPTY);
+        }
+        const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
+        uint64_t contrib = v & B200SK_VAL_MASK;
+        if (inc) {
+            const unsigned first = __ffs(inc) - 1;
+            if (lane > first) contrib = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (inc) break;
+        idx -= 32;
+    }
+    if (lane == 0) st_state(state + tile, (B200SK_FLAG_INC << 62) | (excl + total));
+    return excl;
+}
+
 // Block-wide exclusive scan of one uint32 per thread (blockDim.x <= 1024, multiple of 32).
 // warp_sums: shared scratch of >= 33 uint32.  Returns exclusive prefix; *block_total = sum.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t *block_total) {

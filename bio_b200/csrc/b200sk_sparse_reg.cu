@@ -198,14 +198,111 @@ template <int W> struct CodeWords {
 };
 #define B200SK_TAB(tab, c) lds_v2u64(sm, (tab) + (c) * 16u)
 
+// ------------------------------------------------------------------ all-ACGT fast path
+// When every byte of a tile is one of ACGTacgt the tile is rewritten as cls * 40 = (cls << 3) | (cls << 5)
+// with cls = (byte >> 1) & 3 (a=0 c=1 t=2 g=3).  (in & 0x18) | (out & 0x60) is then directly the byte
+// offset into 16-entry PAIR tables of 8-byte entries,
+//     X[in, out] = A[in] ^ rol(A[out], h),   Y[in, out] = rol(B[in], h-1) ^ ror(B[out], 1),
+// so a rolling step is ONE table offset (one PRMT), two conflict-free LDS.64 and one three-input XOR per
+// 32-bit half -- against two code extractions, two address multiplies, two LDS.128 and two more XORs per
+// half with the general 64-entry tables.  The k-1 (s-1) initial folds go two bases at a time through
+//     F2X[c0, c1] = rol(A[c0], 1) ^ A[c1],   F2Y[c0, c1] = ror(RB[c0], 1) ^ RB[c1],   RB[c] = rol(B[c], h-1).
+// Fast-table block (byte offsets from its base FT): X 0, Y 128, F2X 256, F2Y 384, F1X 512 (A[c], 4 entries),
+// F1Y 544 (RB[c]); syncmer k-mer hasher: XK 576, YK 704, F2YK 832, F1YK 960.  992 bytes.
+#define FT_X 0u
+#define FT_Y 128u
+#define FT_F2X 256u
+#define FT_F2Y 384u
+#define FT_F1X 512u
+#define FT_F1Y 544u
+#define FT_XK 576u
+#define FT_YK 704u
+#define FT_F2YK 832u
+#define FT_F1YK 960u
+#define FT_BYTES 1024u
+__device__ __forceinline__ uint64_t lds_u64(const uint8_t *sm, uint32_t o) {
+    return *reinterpret_cast<const uint64_t *>(sm + o);
+}
+__device__ __forceinline__ void build_fast_tables(uint8_t *ft, uint32_t t, int h, int kk, bool sync) {
+    if (t >= 16) return;
+    const char letter[4] = {'A', 'C', 'T', 'G'}; // class = (byte >> 1) & 3
+    const uint32_t lo = t & 3u, hi = t >> 2;
+    const uint64_t Alo = fwd_seed((uint32_t)letter[lo]), Ahi = fwd_seed((uint32_t)letter[hi]);
+    const uint64_t Blo = rev_seed((uint32_t)letter[lo]), Bhi = rev_seed((uint32_t)letter[hi]);
+    uint64_t *q = reinterpret_cast<uint64_t *>(ft);
+    q[FT_X / 8 + t] = Alo ^ rol64(Ahi, (unsigned)h);
+    q[FT_Y / 8 + t] = rol64(Blo, (unsigned)(h - 1)) ^ ror64(Bhi, 1);
+    q[FT_F2X / 8 + t] = rol64(Alo, 1) ^ Ahi;
+    q[FT_F2Y / 8 + t] = ror64(rol64(Blo, (unsigned)(h - 1)), 1) ^ rol64(Bhi, (unsigned)(h - 1));
+    if (t < 4) {
+        q[FT_F1X / 8 + t] = Alo;
+        q[FT_F1Y / 8 + t] = rol64(Blo, (unsigned)(h - 1));
+    }
+    if (sync) {
+        q[FT_XK / 8 + t] = Alo ^ rol64(Ahi, (unsigned)kk);
+        q[FT_YK / 8 + t] = rol64(Blo, (unsigned)(kk - 1)) ^ ror64(Bhi, 1);
+        q[FT_F2YK / 8 + t] = ror64(rol64(Blo, (unsigned)(kk - 1)), 1) ^ rol64(Bhi, (unsigned)(kk - 1));
+        if (t < 4) q[FT_F1YK / 8 + t] = rol64(Blo, (unsigned)(kk - 1));
+    }
+}
+// ASCII word -> four fast-path bytes; bad accumulates a non-zero value when a byte is not one of ACGTacgt
+__device__ __forceinline__ uint32_t fast_word(uint32_t w, uint32_t &bad) {
+    const uint32_t x = w | 0x20202020u;                       // lower case
+    const uint32_t t = (x >> 1) & 0x03030303u;                // class of every byte
+    const uint32_t u2 = t | (t >> 4);                         // nibble pairs in bytes 0 and 2
+    const uint32_t sel = __byte_perm(u2, 0u, 0x4420u);        // four nibbles = PRMT selector
+    bad |= x ^ __byte_perm(0x67746361u, 0u, sel);             // 'a','c','t','g' by class
+    return t * 40u;
+}
+// pair-table offsets of one block of W steps: in bytes from pin, out bytes from pout
+template <int W> struct PairWords {
+    static constexpr int NWORD = (W + 3 + 3) / 4, NG = (W + 3) / 4;
+    uint32_t x[NG];
+    __device__ __forceinline__ void load(const uint8_t *sm, uint32_t pin, uint32_t pout) {
+        const uint32_t ai = pin & ~3u, ao = pout & ~3u;
+        const uint32_t si = 0x3210u + 0x1111u * (pin & 3u), so = 0x3210u + 0x1111u * (pout & 3u);
+        uint32_t wi[NWORD + 1], wo[NWORD + 1];
+#pragma unroll
+        for (int i = 0; i < NWORD; i++) {
+            wi[i] = *reinterpret_cast<const uint32_t *>(sm + ai + 4u * i);
+            wo[i] = *reinterpret_cast<const uint32_t *>(sm + ao + 4u * i);
+        }
+        wi[NWORD] = 0; wo[NWORD] = 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const int g1 = g + 1 < NWORD ? g + 1 : NWORD;
+            x[g] = (__byte_perm(wi[g], wi[g1], si) & 0x18181818u) | (__byte_perm(wo[g], wo[g1], so) & 0x60606060u);
+        }
+    }
+    __device__ __forceinline__ uint32_t off(const int j) const { return __byte_perm(x[j >> 2], 0u, 0x4440u | (j & 3)); }
+};
+// the h-1 initial folds of a hasher over fast-path bytes starting at shared offset sb
+__device__ __forceinline__ void fast_fold(const uint8_t *sm, uint32_t ft, uint32_t sb, int n, uint64_t &f, uint64_t &r) {
+    int j = 0;
+    for (; j + 1 < n; j += 2) {
+        const uint32_t o = (lds_u8(sm, sb + j) & 0x18u) | (lds_u8(sm, sb + j + 1) & 0x60u);
+        f = rol64(f, 2) ^ lds_u64(sm, ft + FT_F2X + o);
+        r = ror64(r, 2) ^ lds_u64(sm, ft + FT_F2Y + o);
+    }
+    if (j < n) {
+        const uint32_t o = lds_u8(sm, sb + j) & 0x18u;
+        f = rol1(f) ^ lds_u64(sm, ft + FT_F1X + o);
+        r = ror1(r) ^ lds_u64(sm, ft + FT_F1Y + o);
+    }
+}
+
 // NextMinimizer (sketch.go:205-309) over one item; its codes start at shared offset sb.
-template <int W, class SinkT>
+
+// FAST: the tile holds fast-path bytes and ft is the fast-table block; else 6-bit codes and tabIn/tabOut.
+template <int W, bool FAST, class SinkT>
 __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t sb, uint32_t nstep, int k,
                                                    uint32_t w_runtime, uint32_t tabIn, uint32_t tabOut,
-                                                   SinkT &sink) {
+                                                   uint32_t ft, SinkT &sink) {
     Roll h;
     h.f = 0; h.r = 0;
-    for (int j = 0; j < k - 1; j++) h.fold(B200SK_LD128(tabIn, sb + j));
+    if (FAST) fast_fold(sm, ft, sb, k - 1, h.f, h.r);
+    else
+        for (int j = 0; j < k - 1; j++) h.fold(B200SK_LD128(tabIn, sb + j));
     WinReg<W> wm;
     wm.init(w_runtime);
     uint32_t prev = W - 1; // frame-relative position of the previous window's minimum (none yet)
@@ -213,19 +310,32 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
     uint32_t pout = sb - 1;              // outgoing code of step j is pout + j (step 0 has none)
     uint64_t mv;
     uint32_t mu;
-    CodeWords<W> cin, cout;
+    CodeWords<FAST ? 1 : W> cin, cout;
+    PairWords<FAST ? W : 1> pw;
+#define B200SK_LOAD_BLOCK()                                                \
+    if (FAST) pw.load(sm, pin, pout);                                      \
+    else { cin.load(sm, pin); cout.load(sm, pout); }
+#define B200SK_ROLL(J)                                                     \
+    if (FAST) {                                                            \
+        const uint32_t o = pw.off(J);                                      \
+        h.f = rol1(h.f) ^ lds_u64(sm, ft + FT_X + o);                      \
+        h.r = ror1(h.r) ^ lds_u64(sm, ft + FT_Y + o);                      \
+    } else h.roll(B200SK_TAB(tabIn, cin.code(J)), B200SK_TAB(tabOut, cout.code(J)));
 #define B200SK_MIN_STEP(J, FIRST)                                          \
     if (wm.push(J, FIRST, h.canonical(), mv, mu)) {                        \
-        sink.emit_if(mu != prev, mv, mu - prev); /* sketch.go:297-307 */   \
+        sink.emit_if(mu != prev, mv, mu - prev); /* sketch.go:297-307 */     \
         prev = mu;                                                         \
     }
-    cin.load(sm, pin);
-    cout.load(sm, pout);
-    h.fold(B200SK_TAB(tabIn, cin.code(0))); // the first k-mer has no outgoing base
+    B200SK_LOAD_BLOCK()
+    if (FAST) { // the first k-mer has no outgoing base
+        const uint32_t o = pw.off(0) & 0x18u;
+        h.f = rol1(h.f) ^ lds_u64(sm, ft + FT_F1X + o);
+        h.r = ror1(h.r) ^ lds_u64(sm, ft + FT_F1Y + o);
+    } else h.fold(B200SK_TAB(tabIn, cin.code(0)));
     B200SK_MIN_STEP(0, true)
 #pragma unroll
     for (int j = 1; j < W; j++) {
-        h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
+        B200SK_ROLL(j)
         B200SK_MIN_STEP(j, true)
     }
     wm.close_block();
@@ -233,11 +343,10 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
     pin += W; pout += W;
     uint32_t u0 = W;
     while (u0 + W <= nstep) { // full blocks
-        cin.load(sm, pin);
-        cout.load(sm, pout);
+        B200SK_LOAD_BLOCK()
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
+            B200SK_ROLL(j)
             B200SK_MIN_STEP(j, false)
         }
         wm.close_block();
@@ -246,16 +355,25 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
         u0 += W;
     }
     const uint32_t rem = nstep - u0; // tail: fewer than W elements left
-    cin.load(sm, pin);
-    cout.load(sm, pout);
+    B200SK_LOAD_BLOCK()
 #pragma unroll
     for (int j = 0; j < W - 1; j++) {
         if ((uint32_t)j >= rem) break;
-        h.roll(B200SK_TAB(tabIn, cin.code(j)), B200SK_TAB(tabOut, cout.code(j)));
+        B200SK_ROLL(j)
         B200SK_MIN_STEP(j, false)
     }
 #undef B200SK_MIN_STEP
+#undef B200SK_ROLL
+#undef B200SK_LOAD_BLOCK
 }
+
+// NextSyncmer (sketch.go:312-477, bounded closed syncmers, s < k) over one item.  W = 2(k-s): the window of
+// s-mer hashes.  For the window starting at idx the leftmost minimum s-mer m anchors k-mer b = m if
+// m - idx < k-s, else m - (k-s) (sketch.go:414-420); a k-mer is emitted when b changes and b <= end.
+// The last k-s k-mer hashes wait in a shared-memory ring (slot = position mod (k-s)).
+// tabs: offsets of tInS {A, rolB_{s-1}}, tOutS {rolA_s, rorB_1}, tOutK {rolA_k, rorB_1} (16 B entries) and
+// tInK {rolB_{k-1}} (8 B entries); FAST: the fast-table block ft instead.  lim0 = end - q0 (stream index
+// of the last emittable k-mer).
 
 // NextSyncmer (sketch.go:312-477, bounded closed syncmers, s < k) over one item.  W = 2(k-s): the window of
 // s-mer hashes.  For the window starting at idx the leftmost minimum s-mer m anchors k-mer b = m if
@@ -341,6 +459,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     // tables (64 codes): [0,1K) in {A, rolB_{h-1}}, [1K,2K) out {rolA_h, rorB_1} for the streamed hash
     // (h = k for minimizers, s for syncmers); syncmer adds [2K,3K) k-mer out table, [3K,3.5K) rolB_{k-1}
     const int hk = SYNC ? a.s : a.k;
+    constexpr uint32_t FT = 2048u; // fast-table block (minimizer kernels; the syncmer tables live there otherwise)
     {
         ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 64, *tOutK = tIn + 128;
         uint64_t *tInK = reinterpret_cast<uint64_t *>(smem + 3072);
@@ -354,6 +473,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                 tInK[c] = rol64(r, (unsigned)(a.k - 1));
             }
         }
+        if (!SYNC) build_fast_tables(smem + FT, tid, hk, a.k, false); // minimizers: pair tables at [2K, 3K)
     }
     const uint32_t region = a.sm_tile + wid * a.sm_ring_bytes;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
@@ -392,20 +512,45 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         }
         if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
         if (it.valid && it.first_chunk && a.status) a.status[it.r] = it.status;
+        bool fast = false;
         if (bytes && span_ok) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
-            // ASCII -> codes, 16 bytes per lane per trip
-            for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
-                uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
-                const uint32_t orr = v.x | v.y | v.z | v.w, andd = v.x & v.y & v.z & v.w;
-                if ((orr & 0x80808080u) == 0 && (andd & 0x40404040u) == 0x40404040u) {
-                    v.x &= 0x1f1f1f1fu; v.y &= 0x1f1f1f1fu; v.z &= 0x1f1f1f1fu; v.w &= 0x1f1f1f1fu;
-                } else {
-                    v.x = codes_of_word(v.x); v.y = codes_of_word(v.y);
-                    v.z = codes_of_word(v.z); v.w = codes_of_word(v.w);
+            if (!SYNC) {
+                // ASCII -> fast bytes, 16 bytes per lane per trip; any byte outside ACGTacgt (alignment slop
+                // included: a false alarm only costs the general path) -> fetch again and write 6-bit codes
+                uint32_t bad = 0;
+                for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
+                    uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
+                    v.x = fast_word(v.x, bad); v.y = fast_word(v.y, bad);
+                    v.z = fast_word(v.z, bad); v.w = fast_word(v.w, bad);
+                    *reinterpret_cast<uint4 *>(tilebuf + o) = v;
                 }
-                *reinterpret_cast<uint4 *>(tilebuf + o) = v;
+                fast = !__any_sync(0xffffffffu, bad != 0);
+                if (!fast) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(mbar, bytes);
+                        tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
+                    }
+                    mbar_wait(mbar, parity);
+                    parity ^= 1u;
+                }
+            }
+            if (!fast) {
+                // ASCII -> codes, 16 bytes per lane per trip
+                for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
+                    uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
+                    const uint32_t orr = v.x | v.y | v.z | v.w, andd = v.x & v.y & v.z & v.w;
+                    if ((orr & 0x80808080u) == 0 && (andd & 0x40404040u) == 0x40404040u) {
+                        v.x &= 0x1f1f1f1fu; v.y &= 0x1f1f1f1fu; v.z &= 0x1f1f1f1fu; v.w &= 0x1f1f1f1fu;
+                    } else {
+                        v.x = codes_of_word(v.x); v.y = codes_of_word(v.y);
+                        v.z = codes_of_word(v.z); v.w = codes_of_word(v.w);
+                    }
+                    *reinterpret_cast<uint4 *>(tilebuf + o) = v;
+                }
             }
         }
         __syncwarp();
@@ -422,7 +567,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                 syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
                                     s_kring, lim0, halo, sink);
             else
-                minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, sink);
+                if (fast) minimizer_item_reg<W, true>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, sink);
+                else minimizer_item_reg<W, false>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, sink);
         }
         __syncwarp();
         // a non-first chunk walks one window more (the one before its first own window) to seed the
@@ -439,7 +585,27 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         }
         const uint32_t excl = inc - cnt;
         const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint64_t tb = lookback_exclusive(a.tile_state, tile, total);
+        // Ordered allocation in two halves: publish the tile's count, then -- while the tiles before this one
+        // finish -- scatter the staged lists into one contiguous buffer (the codes are dead now; nothing here
+        // needs the prefix), and only then wait for the prefix.
+        lookback_publish(a.tile_state, tile, total);
+        const uint32_t OB = a.sm_tile_bytes / 12u;
+        uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
+        uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
+        auto scatter = [&](uint32_t r0) {
+            uint32_t pos = it.q0 - 1u;
+            for (uint32_t j = 0; j < sink.cnt; j++) {
+                pos += listp[j * 32u + lane];
+                const uint32_t o = excl + j - skip - r0;
+                if (j >= skip && o < OB) { // unsigned compare also rejects entries before r0
+                    obv[o] = listv[j * 32u + lane];
+                    obp[o] = pos;
+                }
+            }
+            __syncwarp();
+        };
+        if (!any_overflow && total) scatter(0);
+        const uint64_t tb = lookback_resolve(a.tile_state, tile, total);
         const uint64_t mine = tb + excl;
         if (it.valid && it.first_chunk) a.out_off[it.r] = a.out_base + mine;
         if (it.valid && it.last_item) a.out_off[a.n_reads] = a.out_base + mine + cnt;
@@ -447,22 +613,10 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         if (!fits && lane == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
         if (fits && total) {
             if (!any_overflow) {
-                // ordered copy: scatter the staged lists into one contiguous buffer (the codes are dead
-                // now), then stream it out coalesced
-                const uint32_t OB = a.sm_tile_bytes / 12u;
-                uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
-                uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
+                // stream the buffer out coalesced; a tile with more elements than the buffer holds takes
+                // further scatter + copy rounds
                 for (uint32_t r0 = 0; r0 < total; r0 += OB) {
-                    uint32_t pos = it.q0 - 1u;
-                    for (uint32_t j = 0; j < sink.cnt; j++) {
-                        pos += listp[j * 32u + lane];
-                        const uint32_t o = excl + j - skip - r0;
-                        if (j >= skip && o < OB) { // unsigned compare also rejects entries before r0
-                            obv[o] = listv[j * 32u + lane];
-                            obp[o] = pos;
-                        }
-                    }
-                    __syncwarp();
+                    if (r0) scatter(r0);
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
                     for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
@@ -491,7 +645,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                         syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
                                             2048u, s_kring, lim0, halo, gs);
                     else
-                        minimizer_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, gs);
+                        if (fast) minimizer_item_reg<W, true>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, gs);
+                        else minimizer_item_reg<W, false>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, gs);
                 }
                 __syncwarp();
             }
