@@ -233,7 +233,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         for (uint32_t shave = 0; shave <= 2 && shave + 8 < pl.lcap; shave++) {
             Plan c = pl;
             c.lcap = pl.lcap - shave;
-            c.sm_tile = 4096;
+            c.sm_tile = mode == B200SK_MODE_SYNCMER ? 3584u + 1024u : 4096u; // tables (+ the syncmer's fast tables)
             c.sm_tile_bytes = up16(32u * c.span_max + 32);
             c.sm_ring = 16 + c.sm_tile_bytes;
             c.sm_listv = c.sm_ring + (uint32_t)d * 256u;

@@ -374,27 +374,37 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
 // tabs: offsets of tInS {A, rolB_{s-1}}, tOutS {rolA_s, rorB_1}, tOutK {rolA_k, rorB_1} (16 B entries) and
 // tInK {rolB_{k-1}} (8 B entries); FAST: the fast-table block ft instead.  lim0 = end - q0 (stream index
 // of the last emittable k-mer).
-
-// NextSyncmer (sketch.go:312-477, bounded closed syncmers, s < k) over one item.  W = 2(k-s): the window of
-// s-mer hashes.  For the window starting at idx the leftmost minimum s-mer m anchors k-mer b = m if
-// m - idx < k-s, else m - (k-s) (sketch.go:414-420); a k-mer is emitted when b changes and b <= end.
-// The last k-s k-mer hashes wait in a shared-memory ring (slot = position mod (k-s)).
-// tabs: offsets of tInS {A, rolB_{s-1}}, tOutS {rolA_s, rorB_1}, tOutK {rolA_k, rorB_1} (16 B entries) and
-// tInK {rolB_{k-1}} (8 B entries).  lim0 = end - q0 (stream index of the last emittable k-mer).
-template <int W, class SinkT>
+template <int W, bool FAST, class SinkT>
 __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint32_t nstep, int s,
                                                  uint32_t w_runtime, uint32_t tInS, uint32_t tOutS, uint32_t tInK,
-                                                 uint32_t tOutK, uint32_t kring, int32_t lim0, uint32_t halo,
-                                                 SinkT &sink) {
+                                                 uint32_t tOutK, uint32_t ft, uint32_t kring, int32_t lim0,
+                                                 uint32_t halo, SinkT &sink) {
     constexpr int D = W / 2;
     Roll hs_, hk_; // s-mer and k-mer hashers
     hs_.f = hs_.r = hk_.f = hk_.r = 0;
-    for (int j = 0; j < s - 1; j++) {
-        const uint32_t c = lds_u8(sm, sb + j);
-        const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);
-        hs_.fold(e);
-        hk_.fold(make_ulonglong2(e.x, *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u)));
-    }
+    if (FAST) {
+        int j = 0;
+        for (; j + 1 < s - 1; j += 2) {
+            const uint32_t o = (lds_u8(sm, sb + j) & 0x18u) | (lds_u8(sm, sb + j + 1) & 0x60u);
+            const uint64_t x = lds_u64(sm, ft + FT_F2X + o);
+            hs_.f = rol64(hs_.f, 2) ^ x;
+            hs_.r = ror64(hs_.r, 2) ^ lds_u64(sm, ft + FT_F2Y + o);
+            hk_.r = ror64(hk_.r, 2) ^ lds_u64(sm, ft + FT_F2YK + o);
+        }
+        if (j < s - 1) {
+            const uint32_t o = lds_u8(sm, sb + j) & 0x18u;
+            hs_.f = rol1(hs_.f) ^ lds_u64(sm, ft + FT_F1X + o);
+            hs_.r = ror1(hs_.r) ^ lds_u64(sm, ft + FT_F1Y + o);
+            hk_.r = ror1(hk_.r) ^ lds_u64(sm, ft + FT_F1YK + o);
+        }
+        hk_.f = hs_.f; // both hashers fold the same bases with the same forward seeds
+    } else
+        for (int j = 0; j < s - 1; j++) {
+            const uint32_t c = lds_u8(sm, sb + j);
+            const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);
+            hs_.fold(e);
+            hk_.fold(make_ulonglong2(e.x, *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u)));
+        }
     WinReg<W> wm;
     wm.init(w_runtime);
     uint32_t prevb = W - 1; // frame-relative position of the previous window's k-mer (none yet: stream -1)
@@ -404,14 +414,36 @@ __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint3
     uint32_t pok = sb - 1 - D;           // k-mer outgoing code of step j is pok + j (steps <= D have none)
     uint64_t mv;
     uint32_t mu;
-#define B200SK_SYNC_STEP(J, FIRST)                                                                         \
-    {                                                                                                      \
+#define B200SK_SYNC_HASH(J, FIRST)                                                                         \
+    if (FAST) {                                                                                            \
+        const uint32_t ci = lds_u8(sm, pin + (J)) & 0x18u;                                                 \
+        if ((FIRST) && (J) == 0) {                                                                         \
+            hs_.f = rol1(hs_.f) ^ lds_u64(sm, ft + FT_F1X + ci);                                           \
+            hs_.r = ror1(hs_.r) ^ lds_u64(sm, ft + FT_F1Y + ci);                                           \
+        } else {                                                                                           \
+            const uint32_t o = ci | (lds_u8(sm, pos + (J)) & 0x60u);                                       \
+            hs_.f = rol1(hs_.f) ^ lds_u64(sm, ft + FT_X + o);                                              \
+            hs_.r = ror1(hs_.r) ^ lds_u64(sm, ft + FT_Y + o);                                              \
+        }                                                                                                  \
+        if ((FIRST) && (J) <= D) {                                                                         \
+            hk_.f = rol1(hk_.f) ^ lds_u64(sm, ft + FT_F1X + ci);                                           \
+            hk_.r = ror1(hk_.r) ^ lds_u64(sm, ft + FT_F1YK + ci);                                          \
+        } else {                                                                                           \
+            const uint32_t o = ci | (lds_u8(sm, pok + (J)) & 0x60u);                                       \
+            hk_.f = rol1(hk_.f) ^ lds_u64(sm, ft + FT_XK + o);                                             \
+            hk_.r = ror1(hk_.r) ^ lds_u64(sm, ft + FT_YK + o);                                             \
+        }                                                                                                  \
+    } else {                                                                                               \
         const uint32_t c = lds_u8(sm, pin + (J));                                                          \
         const ulonglong2 e = lds_v2u64(sm, tInS + c * 16u);                                                \
         const uint64_t ek = *reinterpret_cast<const uint64_t *>(sm + tInK + c * 8u);                       \
         if ((FIRST) && (J) == 0) hs_.fold(e); else hs_.roll(e, B200SK_LD128(tOutS, pos + (J)));           \
         if ((FIRST) && (J) <= D) hk_.fold(make_ulonglong2(e.x, ek));                                       \
         else hk_.roll(make_ulonglong2(e.x, ek), B200SK_LD128(tOutK, pok + (J)));                           \
+    }
+#define B200SK_SYNC_STEP(J, FIRST)                                                                         \
+    {                                                                                                      \
+        B200SK_SYNC_HASH(J, FIRST)                                                                         \
         *reinterpret_cast<uint64_t *>(sm + kring + ((J) % D) * 256u) = hk_.canonical(); /* k-mer (J-D) */  \
         if (wm.push(J, FIRST, hs_.canonical(), mv, mu)) {                                                  \
             const uint32_t off = mu - (uint32_t)((J) + 1);        /* m - idx */                            \
@@ -419,7 +451,7 @@ __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint3
             const uint64_t kv = *reinterpret_cast<const uint64_t *>(sm + kring + (mu % (uint32_t)D) * 256u); \
             uint32_t ok = (b != prevb) & ((int32_t)b <= lim);                                              \
             if ((FIRST) && (J) == W - 1) ok |= halo; /* a non-first chunk's seeding window: always staged, dropped later */ \
-            sink.emit_if(ok, kv, b - prevb);                                                               \
+            sink.emit_if(ok, kv, b - prevb);                                                                  \
             prevb = b;                                                                                     \
         }                                                                                                  \
     }
@@ -444,6 +476,7 @@ __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint3
         B200SK_SYNC_STEP(j, false)
     }
 #undef B200SK_SYNC_STEP
+#undef B200SK_SYNC_HASH
 }
 
 // ------------------------------------------------------------------ kernel: one tile per WARP
@@ -459,7 +492,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     // tables (64 codes): [0,1K) in {A, rolB_{h-1}}, [1K,2K) out {rolA_h, rorB_1} for the streamed hash
     // (h = k for minimizers, s for syncmers); syncmer adds [2K,3K) k-mer out table, [3K,3.5K) rolB_{k-1}
     const int hk = SYNC ? a.s : a.k;
-    constexpr uint32_t FT = 2048u; // fast-table block (minimizer kernels; the syncmer tables live there otherwise)
+    constexpr uint32_t FT = SYNC ? 3584u : 2048u; // fast-table block (1 KB)
     {
         ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 64, *tOutK = tIn + 128;
         uint64_t *tInK = reinterpret_cast<uint64_t *>(smem + 3072);
@@ -473,7 +506,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                 tInK[c] = rol64(r, (unsigned)(a.k - 1));
             }
         }
-        if (!SYNC) build_fast_tables(smem + FT, tid, hk, a.k, false); // minimizers: pair tables at [2K, 3K)
+        build_fast_tables(smem + FT, tid, hk, a.k, SYNC);
     }
     const uint32_t region = a.sm_tile + wid * a.sm_ring_bytes;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
@@ -516,7 +549,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         if (bytes && span_ok) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
-            if (!SYNC) {
+            {
                 // ASCII -> fast bytes, 16 bytes per lane per trip; any byte outside ACGTacgt (alignment slop
                 // included: a false alarm only costs the general path) -> fetch again and write 6-bit codes
                 uint32_t bad = 0;
@@ -564,8 +597,10 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         const uint32_t halo = it.q0 != it.p0 ? 1u : 0u;
         if (run) {
             if (SYNC)
-                syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
-                                    s_kring, lim0, halo, sink);
+                if (fast) syncmer_item_reg<W, true>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
+                                                     FT, s_kring, lim0, halo, sink);
+                else syncmer_item_reg<W, false>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
+                                                FT, s_kring, lim0, halo, sink);
             else
                 if (fast) minimizer_item_reg<W, true>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, sink);
                 else minimizer_item_reg<W, false>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, sink);
@@ -642,8 +677,10 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     gs.gv = a.out_val + mine; gs.gp = a.out_pos; gs.gi = mine; gs.pw = a.pos_width;
                     gs.pos = it.q0 - 1u; gs.cnt = 0; gs.skip = skip;
                     if (SYNC)
-                        syncmer_item_reg<W>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
-                                            2048u, s_kring, lim0, halo, gs);
+                        if (fast) syncmer_item_reg<W, true>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
+                                                             2048u, FT, s_kring, lim0, halo, gs);
+                        else syncmer_item_reg<W, false>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
+                                                        2048u, FT, s_kring, lim0, halo, gs);
                     else
                         if (fast) minimizer_item_reg<W, true>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, gs);
                         else minimizer_item_reg<W, false>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, gs);
