@@ -34,6 +34,51 @@ def fastq_text(n, L, seed):
     return a.reshape(-1)
 
 
+def fasta_text(n_rec, rec_len, width, seed):
+    """n_rec records '>s%09d\n' + rec_len bases in lines of `width` (vectorised; rec_len a multiple of width)."""
+    rng = np.random.default_rng(seed)
+    rows = rec_len // width
+    rec = 12 + rows * (width + 1)
+    a = np.empty((n_rec, rec), dtype=np.uint8)
+    a[:, 0] = ord(">")
+    a[:, 1] = ord("s")
+    idx = np.arange(n_rec, dtype=np.int64)
+    for d in range(9):
+        a[:, 2 + d] = ord("0") + (idx // 10 ** (8 - d)) % 10
+    a[:, 11] = 10
+    body = a[:, 12:].reshape(n_rec, rows, width + 1)
+    body[:, :, :width] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n_rec, rows, width), dtype=np.uint8)]
+    body[:, :, width] = 10
+    return a.reshape(-1)
+
+
+def bench_fasta(ctx, peaks):
+    n_rec, rec_len, width = 200_000, 9_960, 60  # ~2 GB of 60-column FASTA, 10 kb records
+    text = fasta_text(n_rec, rec_len, width, 47)
+    nb = text.size
+    pad = np.zeros((nb + 15) // 16 * 16 + 16, dtype=np.uint8)
+    pad[:nb] = text
+    d_text = torch.from_numpy(pad).cuda()
+    for _ in range(2):
+        info = ctx.fastx_parse_device(d_text, nb, 0, True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(5):
+        e0.record()
+        info = ctx.fastx_parse_device(d_text, nb, 0, True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    assert info.n_records == n_rec and info.n_bases == n_rec * rec_len
+    t = float(np.median(ms)) / 1e3
+    nlines = n_rec * (1 + rec_len // width)
+    alg = nb + n_rec * rec_len + 2 * 8 * n_rec + 8 * nlines + 8 * nlines  # text in; bases, record tables, line table, out_pos out
+    print(json.dumps({"config": f"feeder: FASTA {n_rec} x {rec_len} bp in {width}-column lines ({nb / 1e9:.2f} GB text) -> records in HBM",
+                      "ms": t * 1e3, "text_GBps": nb / t / 1e9, "bases_per_s": n_rec * rec_len / t,
+                      "algorithmic_GBps": alg / t / 1e9, "hbm_frac_of_measured": alg / t / 1e9 / peaks["hbm_gbs"]}), flush=True)
+    del d_text
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
     L = 150
@@ -66,6 +111,7 @@ def main():
                       "ms": t * 1e3, "text_GBps": nb / t / 1e9, "bases_per_s": n * L / t, "records_per_s": n / t,
                       "algorithmic_GBps": alg / t / 1e9, "hbm_frac_of_measured": alg / t / 1e9 / peaks["hbm_gbs"],
                       "bytes_per_base": alg / (n * L)}), flush=True)
+    bench_fasta(ctx, peaks)
     # ---- text in pinned host memory -> minimizers on the host (one C-ABI call)
     L_ = cabi.lib()
     hp = L_.b200sk_alloc_pinned(nb)
