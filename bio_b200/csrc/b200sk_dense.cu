@@ -729,7 +729,10 @@ cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t s
         // canonical codes, values only: the warp-tile kernel; both strands / positions: the generic dense kernel
         if (!a.out_pos && a.canonical && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
         return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
-    case B200SK_MODE_PROTEIN: return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
+    case B200SK_MODE_PROTEIN:
+        // k <= 16, one item per read, values only: the warp-tile kernel (amino acids in a register window)
+        if (!a.out_pos && a.k <= 16 && !a.item_first && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
+        return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
     case B200SK_MODE_SIMHASH: { // counter planes: enough bits for n = k-m+1 (a.w carries m)
         const int n = a.k - a.w + 1;
         if (n < 16) return launch_dense_mode<B200SK_MODE_SIMHASH, 4>(a, threads, blocks, st, occ);

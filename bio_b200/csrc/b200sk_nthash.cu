@@ -25,6 +25,11 @@
 // iterator.go:736,740 and the canonical minimum of :754-756; reads with an illegal base stop before the first
 // k-mer that holds it (k_first_illegal + read_positions).  Both-strand k-mers and batches that want Index()
 // stay with the generic dense kernel.
+// And ProteinIterator.Next (sketches/iterator-protein.go:46-90) for k <= 16 on reads of one item each
+// (KIND_PROTEIN): the frame is translated codon by codon as the lane walks (all-ACGT tiles: 2-bit classes and a
+// 64-entry amino-acid table per strand; any other byte: CodonTable.Get over the 4-bit IUPAC matrix), the last 16
+// amino acids live in a 128-bit register window, and wyhash(seed 1) of the k newest is computed from registers.
+#include "b200sk_protein.cuh"
 #include "b200sk_tile.cuh"
 
 namespace b200sk {
@@ -120,12 +125,76 @@ __device__ __forceinline__ void block16_kmer(uint8_t *smem, const Bytes16 &win, 
 
 #define KIND_NTHASH 0
 #define KIND_KMER 1
+#define KIND_PROTEIN 2
+
+// wyhash (zeebo/wyhash v0.0.1 layout, b200sk_protein.cuh) of the k <= 16 newest bytes of a 128-bit window whose
+// top byte is the newest: the k-mer's bytes are the top k bytes of (whi:wlo).
+__device__ __forceinline__ uint64_t wy_tail_of(uint64_t v, uint32_t n) { // v: n bytes, first byte lowest; n in 1..8
+    switch (n) {
+    case 1: case 2: case 4: return v;
+    case 3: return ((v & 0xffffull) << 8) | ((v >> 16) & 0xffull);
+    case 5: return ((v & 0xffffffffull) << 8) | ((v >> 32) & 0xffull);
+    case 6: return ((v & 0xffffffffull) << 16) | ((v >> 32) & 0xffffull);
+    case 7: return ((v & 0xffffffffull) << 24) | (((v >> 32) & 0xffffull) << 8) | ((v >> 48) & 0xffull);
+    default: return (v << 32) | (v >> 32);
+    }
+}
+__device__ __forceinline__ uint64_t wyhash_window(uint64_t wlo, uint64_t whi, uint32_t k) {
+    const uint64_t seed = 1ull ^ WYP0;
+    uint64_t h;
+    if (k <= 8) {
+        const uint64_t v = whi >> (8u * (8u - k));
+        h = wymum(seed, wy_tail_of(v, k) ^ WYP1);
+    } else {
+        const uint32_t sft = 8u * (16u - k); // < 64
+        const uint64_t first8 = sft ? ((wlo >> sft) | (whi << (64u - sft))) : wlo;
+        const uint64_t rest = whi >> sft;
+        h = wymum(((first8 << 32) | (first8 >> 32)) ^ seed, wy_tail_of(rest, k - 8u) ^ WYP2);
+    }
+    return wymum(h, (uint64_t)k ^ WYP5);
+}
+
+// KIND_PROTEIN: 16 virtual steps of amino-acid k-mer hashes.  Slot e is amino-acid k-mer u = v0 + e - shift, whose
+// newest amino acid has index u + k - 1.  DIR 0: the records are amino acids already; 1: forward frame; 2:
+// reverse frame (codons run down the read, complemented).  FAST (DIR 1, 2): the tile holds 2-bit classes and the
+// 64-entry tables at smem + 4608 (forward) / + 4672 (reverse) give the amino acid; else CodonTable.Get over the
+// copy of the aux block at smem + 0.  cb: shared offset of the first base of amino acid 0 (forward) or of the base
+// the first codon starts from (reverse).
+template <int DIR, bool FAST>
+__device__ __forceinline__ uint32_t protein_aa(const uint8_t *smem, uint32_t cb, uint32_t t) {
+    if (DIR == 0) return lds8(smem, cb + t);
+    if (DIR == 1) {
+        const uint32_t p = cb + 3u * t;
+        const uint32_t b0 = lds8(smem, p), b1 = lds8(smem, p + 1), b2 = lds8(smem, p + 2);
+        if (FAST) return smem[4608u + b0 * 16u + b1 * 4u + b2];
+        return codon_aa(smem, b0, b1, b2);
+    }
+    const uint32_t p = cb - 3u * t;
+    const uint32_t b0 = lds8(smem, p), b1 = lds8(smem, p - 1), b2 = lds8(smem, p - 2);
+    if (FAST) return smem[4672u + b0 * 16u + b1 * 4u + b2];
+    const uint8_t *pl = smem + 4352; // DNA pair letters; other bytes pass through (codon_tables.go:222-226)
+    return codon_aa(smem, pl[b0], pl[b1], pl[b2]);
+}
+template <int DIR, bool FAST, bool FULL>
+__device__ __forceinline__ void block16_protein(uint8_t *smem, uint32_t cb, uint32_t t0, uint32_t lo, uint32_t hi,
+                                                uint32_t s_row, uint32_t k, uint64_t &wlo, uint64_t &whi) {
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        if (FULL || ((uint32_t)e >= lo && (uint32_t)e < hi)) {
+            const uint64_t aa = protein_aa<DIR, FAST>(smem, cb, t0 + (uint32_t)e);
+            wlo = (wlo >> 8) | (whi << 56);
+            whi = (whi >> 8) | (aa << 56);
+            *reinterpret_cast<uint64_t *>(smem + s_row + e * 8) = wyhash_window(wlo, whi, k); // iterator-protein.go:87
+        }
+    }
+}
 
 struct NItem {
     uint64_t gb0, obase;
     uint32_t nb, nstep;
 };
 
+template <int KIND>
 __device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, uint64_t item, uint64_t n_items, NItem &it) {
     it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0;
     if (item >= n_items) return;
@@ -149,6 +218,13 @@ __device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, u
     const uint32_t p0 = c * a.C;
     it.nstep = min(np, p0 + a.C) - p0;
     it.obase = a.out_off[r] - a.out_base + p0;
+    if (KIND == KIND_PROTEIN) { // one item per read: the bases (or amino acids) of the frame's naa codons
+        const uint32_t naa = it.nstep + (uint32_t)a.k - 1;
+        if (g.protein_input) { it.nb = naa; it.gb0 = o0; }
+        else if (a.frame > 0) { it.nb = 3u * naa; it.gb0 = o0 + (uint32_t)(a.frame - 1); }
+        else { it.nb = 3u * naa; it.gb0 = o0 + (L - (uint64_t)(-a.frame)) + 1 - it.nb; } // codons run down from base L-|f|
+        return;
+    }
     it.nb = it.nstep + (uint32_t)a.k - 1;
     it.gb0 = o0 + p0;
 }
@@ -158,7 +234,18 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const int k = a.k;
-    if (KIND == KIND_KMER) {
+    if (KIND == KIND_PROTEIN) {
+        // the aux block (codon matrix over IUPAC codes, base2code, pair letters), then the 64-entry tables of the
+        // all-ACGT fast path: class = (byte >> 1) & 3 -> a, c, t, g; complement = class ^ 2
+        for (uint32_t i = tid; i < 4608; i += blockDim.x) smem[i] = a.aux[i];
+        __syncthreads();
+        if (tid < 64) {
+            const char letter[4] = {'A', 'C', 'T', 'G'};
+            const uint32_t c0 = tid >> 4, c1 = (tid >> 2) & 3u, c2 = tid & 3u;
+            smem[4608 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c0], (uint32_t)letter[c1], (uint32_t)letter[c2]);
+            smem[4672 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c0 ^ 2u], (uint32_t)letter[c1 ^ 2u], (uint32_t)letter[c2 ^ 2u]);
+        }
+    } else if (KIND == KIND_KMER) {
         for (uint32_t b = tid; b < 256; b += blockDim.x) {
             uint32_t bit; // sketches/kmers.go:23-40 (IUPAC codes map to their first base)
             switch (b) {
@@ -222,7 +309,7 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
         if (item0 >= n_items) break;
         const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_items - item0);
         NItem it;
-        nthash_item(a, g, item0 + lane, n_items, it);
+        nthash_item<KIND>(a, g, item0 + lane, n_items, it);
         const uint64_t lo = __shfl_sync(0xffffffffu, it.gb0, 0);
         const uint64_t hi = __shfl_sync(0xffffffffu, it.gb0 + it.nb, (int)nvalid - 1);
         const uint64_t lo_al = lo & ~15ULL;
@@ -240,15 +327,20 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
             mbar_wait(mbar, parity);
             parity ^= 1u;
             uint32_t bad = 0;
-            if (KIND == KIND_NTHASH)
+            const bool try_fast = KIND == KIND_NTHASH || (KIND == KIND_PROTEIN && !g.protein_input);
+            if (try_fast)
             for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
                 uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
                 v.x = fast_word(v.x, bad); v.y = fast_word(v.y, bad);
                 v.z = fast_word(v.z, bad); v.w = fast_word(v.w, bad);
+                if (KIND == KIND_PROTEIN) { // plain classes 0..3 (cls * 40 = cls << 3 | cls << 5)
+                    v.x = (v.x >> 3) & 0x03030303u; v.y = (v.y >> 3) & 0x03030303u;
+                    v.z = (v.z >> 3) & 0x03030303u; v.w = (v.w >> 3) & 0x03030303u;
+                }
                 *reinterpret_cast<uint4 *>(tilebuf + o) = v;
             }
-            fast = KIND == KIND_NTHASH && !__any_sync(0xffffffffu, bad != 0);
-            if (KIND == KIND_NTHASH && !fast) { // some other byte (alignment slop included): the original bytes again, general tables
+            fast = try_fast && !__any_sync(0xffffffffu, bad != 0);
+            if (try_fast && !fast) { // some other byte (alignment slop included): the original bytes again, general tables
                 __syncwarp();
                 if (lane == 0) {
                     fence_proxy_async();
@@ -277,7 +369,20 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
         uint64_t fh = 0, rh = 0; // KIND_KMER: code and reverse-complement code
         const uint32_t ksh = 2u * (uint32_t)(k - 1);
         const uint64_t kmask1 = (1ull << ksh) - 1ull; // iterator.go:699
-        if (KIND == KIND_KMER) {
+        // KIND_PROTEIN: (fh, rh) = the 128-bit window (low, high) of the last 16 amino acids; cb as in protein_aa
+        const int pdir = KIND != KIND_PROTEIN ? 0 : g.protein_input ? 0 : a.frame > 0 ? 1 : 2;
+        const uint32_t cb = pdir == 2 ? sb + it.nb - 1u : sb;
+        if (KIND == KIND_PROTEIN) {
+            if (nstep)
+                for (uint32_t t = 0; t + 1 < (uint32_t)k; t++) {
+                    uint64_t aa;
+                    if (pdir == 0) aa = protein_aa<0, false>(smem, cb, t);
+                    else if (pdir == 1) aa = fast ? protein_aa<1, true>(smem, cb, t) : protein_aa<1, false>(smem, cb, t);
+                    else aa = fast ? protein_aa<2, true>(smem, cb, t) : protein_aa<2, false>(smem, cb, t);
+                    fh = (fh >> 8) | (rh << 56);
+                    rh = (rh >> 8) | (aa << 56);
+                }
+        } else if (KIND == KIND_KMER) {
             if (nstep)
                 for (int j = 0; j < k - 1; j++) {
                     const uint64_t bit = smem[lds8(smem, sb + j)] & 3u;
@@ -323,7 +428,17 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
             const bool full = __all_sync(0xffffffffu, lo == 0u && hi == 16u && shift == 0u) ||
                               (v0 != 0 && __all_sync(0xffffffffu, hi == 16u));
             // straight-line code for whole blocks; the predicated variant only for a block some lane does not fill
-            if (KIND == KIND_KMER) {
+            if (KIND == KIND_PROTEIN) {
+                const uint32_t t0 = v0 - shift + (uint32_t)k - 1u; // amino-acid index of slot 0's newest amino acid
+                const uint32_t kk = (uint32_t)k;
+#define B200SK_PBLOCK(DIR, FAST_)                                                                          \
+    if (full) block16_protein<DIR, FAST_, true>(smem, cb, t0, lo, hi, s_row, kk, fh, rh);                  \
+    else block16_protein<DIR, FAST_, false>(smem, cb, t0, lo, hi, s_row, kk, fh, rh);
+                if (pdir == 0) { B200SK_PBLOCK(0, false) }
+                else if (pdir == 1) { if (fast) { B200SK_PBLOCK(1, true) } else { B200SK_PBLOCK(1, false) } }
+                else { if (fast) { B200SK_PBLOCK(2, true) } else { B200SK_PBLOCK(2, false) } }
+#undef B200SK_PBLOCK
+            } else if (KIND == KIND_KMER) {
                 if (full) block16_kmer<CANON, true>(smem, win, lo, hi, s_row, kmask1, ksh, fh, rh);
                 else block16_kmer<CANON, false>(smem, win, lo, hi, s_row, kmask1, ksh, fh, rh);
             } else if (fast) {
@@ -380,7 +495,8 @@ cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ) {
     if (nw < 1) return cudaErrorInvalidValue;
     const uint32_t sm_total = NH_TABLES + (uint32_t)nw * stride;
     void (*fn)(const KArgs, uint32_t, uint32_t);
-    if (a.mode == B200SK_MODE_KMER) fn = k_nthash_warp<KIND_KMER, true>;
+    if (a.mode == B200SK_MODE_PROTEIN) fn = k_nthash_warp<KIND_PROTEIN, true>;
+    else if (a.mode == B200SK_MODE_KMER) fn = k_nthash_warp<KIND_KMER, true>;
     else fn = a.canonical ? k_nthash_warp<KIND_NTHASH, true> : k_nthash_warp<KIND_NTHASH, false>;
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total);
     if (e != cudaSuccess) return e;

@@ -423,3 +423,36 @@ def test_kmer_values_only_kernel(gpu_ctx, k):
         res = gpu_ctx.run(p, b, o)
         ref = oracle.run_batch(b, o, oracle.MODE_KMER, threads=8, k=k, canonical=True)
         assert_same(res, ref, f"k={k} hint={hint}")
+
+
+@pytest.mark.parametrize("frame", [1, 2, 3, -1, -2, -3])
+@pytest.mark.parametrize("k", [1, 3, 8, 9, 11, 16])
+def test_protein_values_only_kernel(gpu_ctx, frame, k):
+    """ProteinIterator with want_pos=False and k <= 16 on short reads takes the warp-tile kernel: amino acids in a
+    register window, 64-entry tables for all-ACGT tiles, CodonTable.Get for any other byte."""
+    cases = [synth.uniform_reads(6000, 150, 25) + (150,),
+             synth.ragged_reads(np.random.default_rng(26).integers(0, 380, size=3000), 26) + (380,),
+             synth.ragged_reads(np.random.default_rng(27).integers(0, 300, size=2000), 27,
+                                alphabet=b"ACGTNacgtRYKMSWBDHVU-*") + (300,),
+             synth.ragged_reads([150] * 500 + [0, 2, 33, 34, 35], 28, alphabet=b"ACGTacgt") + (150,)]
+    for table in (1, 11):
+        for b, o, hint in cases:
+            p = cabi.make_params(cabi.MODE_PROTEIN, k, frame=frame, codon_table=table, max_read_len=hint, want_pos=False)
+            res = gpu_ctx.run(p, b, o)
+            ref = oracle.run_batch(b, o, oracle.MODE_PROTEIN, threads=8, k=k, frame=frame, codon_table=table)
+            assert_same(res, ref, f"k={k} frame={frame} table={table} hint={hint}")
+
+
+def test_protein_values_only_amino_acid_input(gpu_ctx):
+    aa = b"ACDEFGHIKLMNPQRSTVWY*X"
+    lens = [0, 10, 29, 30, 34, 35, 60, 200, 380] * 20
+    b, o = synth.ragged_reads(lens, 78, alphabet=aa)
+    for k in (5, 10, 16):
+        p = cabi.make_params(cabi.MODE_PROTEIN, k, alphabet=cabi.ALPHABET_PROTEIN, max_read_len=380, want_pos=False)
+        res = gpu_ctx.run(p, b, o)
+        vals = []
+        for i, L in enumerate(lens):
+            if L >= 3 * k:  # iterator-protein.go:50: the length check is on 3k even for amino-acid input
+                s = b[int(o[i]):int(o[i + 1])]
+                vals += [oracle.wyhash(s[j:j + k], 1) for j in range(L - k + 1)]
+        assert [int(v) for v in res["val"]] == vals
