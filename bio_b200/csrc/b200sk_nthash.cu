@@ -178,7 +178,7 @@ __device__ __forceinline__ uint32_t protein_aa(const uint8_t *smem, uint32_t cb,
 template <int DIR, bool FAST, bool FULL>
 __device__ __forceinline__ void block16_protein(uint8_t *smem, uint32_t cb, uint32_t t0, uint32_t lo, uint32_t hi,
                                                 uint32_t s_row, uint32_t k, uint64_t &wlo, uint64_t &whi) {
-#pragma unroll
+#pragma unroll 4 // ~60 instructions per step: fully unrolled, the variants of this block do not fit the instruction cache
     for (int e = 0; e < 16; e++) {
         if (FULL || ((uint32_t)e >= lo && (uint32_t)e < hi)) {
             const uint64_t aa = protein_aa<DIR, FAST>(smem, cb, t0 + (uint32_t)e);
