@@ -722,16 +722,16 @@ bool nthash_warp_fits(uint32_t span_max);
 cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
     switch (a.mode) {
     case B200SK_MODE_NTHASH:
-        // values only (no Index() array): the warp-tile kernel; with positions: the generic dense kernel
-        if (!a.out_pos && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
+        if (nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ); // the warp-tile kernel
         return launch_dense_mode<B200SK_MODE_NTHASH>(a, threads, blocks, st, occ);
     case B200SK_MODE_KMER:
-        // canonical codes, values only: the warp-tile kernel; both strands / positions: the generic dense kernel
-        if (!a.out_pos && a.canonical && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
+        // canonical codes of reads that are one item each: the warp-tile kernel (a long read cut short by an illegal
+        // base would leave a hole of untouched bytes in a tile's byte range); both strands: the generic dense kernel
+        if (a.canonical && !a.item_first && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
         return launch_dense_mode<B200SK_MODE_KMER>(a, threads, blocks, st, occ);
     case B200SK_MODE_PROTEIN:
-        // k <= 16, one item per read, values only: the warp-tile kernel (amino acids in a register window)
-        if (!a.out_pos && a.k <= 16 && !a.item_first && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
+        // k <= 16, one item per read: the warp-tile kernel (amino acids in a register window)
+        if (a.k <= 16 && !a.item_first && nthash_warp_fits(a.span_max)) return launch_nthash_warp(a, st, occ);
         return launch_dense_mode<B200SK_MODE_PROTEIN>(a, threads, blocks, st, occ);
     case B200SK_MODE_SIMHASH: { // counter planes: enough bits for n = k-m+1 (a.w carries m)
         const int n = a.k - a.w + 1;

@@ -1,5 +1,4 @@
-// NextHash (sketches/iterator.go:615-665; ntHash-1 of will-rowe/nthash v0.4.0) for batches that want the
-// values only: one tile of 32 items per WARP, no block-wide barrier, no ordering between tiles (the output
+// NextHash (sketches/iterator.go:615-665; ntHash-1 of will-rowe/nthash v0.4.0): one tile of 32 items per WARP, no block-wide barrier, no ordering between tiles (the output
 // offsets of a dense mode follow from the read lengths: k_scan_reads wrote out_off before this kernel runs).
 //
 // Per tile:
@@ -20,11 +19,11 @@
 // 128-byte stores at the full HBM write bandwidth -- scripts/ubench/bulkstore.cu: 6.4 TB/s -- but UBLKCP is a
 // uniform-datapath instruction: with per-lane addresses the compiler emits a loop over the 32 lanes, 12
 // instructions per row against 6 per warp-step here.)
-// The same kernel also serves NextKmer (sketches/iterator.go:668-759) for canonical, values-only batches
+// The same kernel also serves canonical NextKmer (sketches/iterator.go:668-759) on reads of one item each
 // (KIND_KMER): no tables beyond the 256-byte base2bit LUT (sketches/kmers.go:23-40), the rolling update of
 // iterator.go:736,740 and the canonical minimum of :754-756; reads with an illegal base stop before the first
-// k-mer that holds it (k_first_illegal + read_positions).  Both-strand k-mers and batches that want Index()
-// stay with the generic dense kernel.
+// k-mer that holds it (k_first_illegal + read_positions).  Both-strand k-mers stay with the generic dense kernel.
+// Index() of a dense mode is the running position: a second store loop writes it when the caller wants it.
 // And ProteinIterator.Next (sketches/iterator-protein.go:46-90) for k <= 16 on reads of one item each
 // (KIND_PROTEIN): the frame is translated codon by codon as the lane walks (all-ACGT tiles: 2-bit classes and a
 // 64-entry amino-acid table per strand; any other byte: CodonTable.Get over the 4-bit IUPAC matrix), the last 16
@@ -38,7 +37,7 @@ namespace {
 
 #define NH_ROW 136u              // staging row stride (16 values + 8 B of padding)
 #define NH_STAGE (32u * NH_ROW)  // per warp
-#define NH_DESC 256u             // 32 row destinations (8 B each)
+#define NH_DESC 384u             // 32 row destinations (8 B each) + 32 first positions (4 B each)
 #define NH_TAB_GENERAL 8192u     // tIn[256], tOut[256] (16 B entries)
 #define NH_TAB_FAST 8192u        // fast tables start here (640 B used)
 #define NH_TABLES (8192u + 1024u)
@@ -191,12 +190,12 @@ __device__ __forceinline__ void block16_protein(uint8_t *smem, uint32_t cb, uint
 
 struct NItem {
     uint64_t gb0, obase;
-    uint32_t nb, nstep;
+    uint32_t nb, nstep, p0; // p0: Index() of the item's first element
 };
 
 template <int KIND>
 __device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, uint64_t item, uint64_t n_items, NItem &it) {
-    it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0;
+    it.gb0 = 0; it.obase = 0; it.nb = 0; it.nstep = 0; it.p0 = 0;
     if (item >= n_items) return;
     uint64_t r = item;
     uint32_t c = 0;
@@ -217,6 +216,7 @@ __device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, u
     if (np == 0) return;
     const uint32_t p0 = c * a.C;
     it.nstep = min(np, p0 + a.C) - p0;
+    it.p0 = p0;
     it.obase = a.out_off[r] - a.out_base + p0;
     if (KIND == KIND_PROTEIN) { // one item per read: the bases (or amino acids) of the frame's naa codons
         const uint32_t naa = it.nstep + (uint32_t)a.k - 1;
@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
         const uint32_t vend = shift + nstep; // one past the last virtual step
         // where the lane's rows go: address of virtual step 0
         *reinterpret_cast<uint64_t *>(smem + s_desc + lane * 8u) = reinterpret_cast<uint64_t>(g0 - shift);
+        *reinterpret_cast<uint32_t *>(smem + s_desc + 256u + lane * 4u) = it.p0 - shift; // Index() of virtual step 0
         uint32_t maxv = vend;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, o));
@@ -471,6 +472,18 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
                     }
                 }
             }
+            if (a.out_pos) { // Index() of a dense mode is the running position (iterator.go:776)
+                const uint32_t lohi = lo | (hi << 8);
+                for (uint32_t i = 0; i < 16u; i++) {
+                    const uint32_t src = 2u * i + half;
+                    const uint32_t lh = __shfl_sync(0xffffffffu, lohi, (int)src);
+                    if (e >= (lh & 0xffu) && e < (lh >> 8)) {
+                        const uint64_t *dst = reinterpret_cast<const uint64_t *>(lds64(smem, s_desc + src * 8u));
+                        const uint32_t p0v = *reinterpret_cast<const uint32_t *>(smem + s_desc + 256u + src * 4u);
+                        store_pos(a.out_pos, a.pos_width, (uint64_t)(dst - a.out_val) + v0 + e, p0v + v0 + e);
+                    }
+                }
+            }
             __syncwarp();
         }
     }
@@ -478,7 +491,7 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
 
 } // namespace
 
-// values-only ntHash batches (out_pos == nullptr).  occ != nullptr: the grid is sized here, report 1.
+// occ != nullptr: the grid is sized here, report 1.
 cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ) {
     if (occ) { *occ = 1; return cudaSuccess; }
     static int sm_count = 0;
