@@ -1,4 +1,5 @@
-// NextHash (sketches/iterator.go:615-665; ntHash-1 of will-rowe/nthash v0.4.0): one tile of 32 items per WARP, no block-wide barrier, no ordering between tiles (the output
+// NextHash (sketches/iterator.go:615-665; ntHash-1 of will-rowe/nthash v0.4.0): one tile of 32 items per WARP,
+// no block-wide barrier, no ordering between tiles (the output
 // offsets of a dense mode follow from the read lengths: k_scan_reads wrote out_off before this kernel runs).
 //
 // Per tile:
