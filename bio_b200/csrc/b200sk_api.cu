@@ -180,7 +180,8 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         pl.C = np ? np : 1;
         pl.span_max = (uint32_t)max_len;
     } else {
-        pl.C = (mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER) && sparse_reg_supported(mode, k, w, s)
+        pl.C = (mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER || mode == B200SK_MODE_PROTEIN_MINIMIZER) &&
+                       sparse_reg_supported(mode, k, w, s)
                    ? kChunkReg : kChunk;
         if ((uint64_t)pl.C + halo > 20000) return B200SK_ERR_UNSUPPORTED;
         pl.span_max = (uint32_t)(pl.C + halo);

@@ -127,33 +127,6 @@ __device__ __forceinline__ void block16_kmer(uint8_t *smem, const Bytes16 &win, 
 #define KIND_KMER 1
 #define KIND_PROTEIN 2
 
-// wyhash (zeebo/wyhash v0.0.1 layout, b200sk_protein.cuh) of the k <= 16 newest bytes of a 128-bit window whose
-// top byte is the newest: the k-mer's bytes are the top k bytes of (whi:wlo).
-__device__ __forceinline__ uint64_t wy_tail_of(uint64_t v, uint32_t n) { // v: n bytes, first byte lowest; n in 1..8
-    switch (n) {
-    case 1: case 2: case 4: return v;
-    case 3: return ((v & 0xffffull) << 8) | ((v >> 16) & 0xffull);
-    case 5: return ((v & 0xffffffffull) << 8) | ((v >> 32) & 0xffull);
-    case 6: return ((v & 0xffffffffull) << 16) | ((v >> 32) & 0xffffull);
-    case 7: return ((v & 0xffffffffull) << 24) | (((v >> 32) & 0xffffull) << 8) | ((v >> 48) & 0xffull);
-    default: return (v << 32) | (v >> 32);
-    }
-}
-__device__ __forceinline__ uint64_t wyhash_window(uint64_t wlo, uint64_t whi, uint32_t k) {
-    const uint64_t seed = 1ull ^ WYP0;
-    uint64_t h;
-    if (k <= 8) {
-        const uint64_t v = whi >> (8u * (8u - k));
-        h = wymum(seed, wy_tail_of(v, k) ^ WYP1);
-    } else {
-        const uint32_t sft = 8u * (16u - k); // < 64
-        const uint64_t first8 = sft ? ((wlo >> sft) | (whi << (64u - sft))) : wlo;
-        const uint64_t rest = whi >> sft;
-        h = wymum(((first8 << 32) | (first8 >> 32)) ^ seed, wy_tail_of(rest, k - 8u) ^ WYP2);
-    }
-    return wymum(h, (uint64_t)k ^ WYP5);
-}
-
 // KIND_PROTEIN: 16 virtual steps of amino-acid k-mer hashes.  Slot e is amino-acid k-mer u = v0 + e - shift, whose
 // newest amino acid has index u + k - 1.  DIR 0: the records are amino acids already; 1: forward frame; 2:
 // reverse frame (codons run down the read, complemented).  FAST (DIR 1, 2): the tile holds 2-bit classes and the

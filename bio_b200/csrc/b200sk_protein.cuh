@@ -60,6 +60,34 @@ __device__ __forceinline__ uint64_t wyhash_dev(const ByteSrc &s, uint32_t len, u
     return wymum(seed, (uint64_t)len ^ WYP5);
 }
 
+// wyhash (zeebo/wyhash v0.0.1 layout, b200sk_protein.cuh) of the k <= 16 newest bytes of a 128-bit window whose
+// top byte is the newest: the k-mer's bytes are the top k bytes of (whi:wlo).
+__device__ __forceinline__ uint64_t wy_tail_of(uint64_t v, uint32_t n) { // v: n bytes, first byte lowest; n in 1..8
+    switch (n) {
+    case 1: case 2: case 4: return v;
+    case 3: return ((v & 0xffffull) << 8) | ((v >> 16) & 0xffull);
+    case 5: return ((v & 0xffffffffull) << 8) | ((v >> 32) & 0xffull);
+    case 6: return ((v & 0xffffffffull) << 16) | ((v >> 32) & 0xffffull);
+    case 7: return ((v & 0xffffffffull) << 24) | (((v >> 32) & 0xffffull) << 8) | ((v >> 48) & 0xffull);
+    default: return (v << 32) | (v >> 32);
+    }
+}
+__device__ __forceinline__ uint64_t wyhash_window(uint64_t wlo, uint64_t whi, uint32_t k) {
+    const uint64_t seed = 1ull ^ WYP0;
+    uint64_t h;
+    if (k <= 8) {
+        const uint64_t v = whi >> (8u * (8u - k));
+        h = wymum(seed, wy_tail_of(v, k) ^ WYP1);
+    } else {
+        const uint32_t sft = 8u * (16u - k); // < 64
+        const uint64_t first8 = sft ? ((wlo >> sft) | (whi << (64u - sft))) : wlo;
+        const uint64_t rest = whi >> sft;
+        h = wymum(((first8 << 32) | (first8 >> 32)) ^ seed, wy_tail_of(rest, k - 8u) ^ WYP2);
+    }
+    return wymum(h, (uint64_t)k ^ WYP5);
+}
+
+
 // ------------------------------------------------------------------ codon lookup
 // aux layout: [0,4096) matrix[i][j][k] over 4-bit IUPAC codes, [4096,4352) base2code (0xff = invalid),
 // [4352,4608) DNA pair letters.  CodonTable.Get: seq/codon_tables.go:152-170 with allowUnknownCodon=true.

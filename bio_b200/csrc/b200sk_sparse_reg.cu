@@ -16,6 +16,7 @@
 //
 // Reference behaviour: sketches/sketch.go:205-309 (NextMinimizer), :312-477
 // (NextSyncmer), ntHash via will-rowe/nthash v0.4.0 (sketch.go:212,319,367).
+#include "b200sk_protein.cuh"
 #include "b200sk_tile.cuh"
 
 namespace b200sk {
@@ -479,6 +480,57 @@ __device__ __forceinline__ void syncmer_item_reg(uint8_t *sm, uint32_t sb, uint3
 #undef B200SK_SYNC_HASH
 }
 
+// ProteinMinimizerSketch.Next (sketch-protein.go:106-210) over one item of amino acids (the frame was translated
+// by k_translate): wyhash(seed 1) of every amino-acid k-mer (k <= 16) from a 128-bit register window of the last
+// 16 residues, then the same window minimum as NextMinimizer.
+template <int W, class SinkT>
+__device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb, uint32_t nstep, int k,
+                                                 uint32_t w_runtime, SinkT &sink) {
+    uint64_t wlo = 0, whi = 0;
+    for (int j = 0; j < k - 1; j++) {
+        const uint64_t aa = lds_u8(sm, sb + j);
+        wlo = (wlo >> 8) | (whi << 56);
+        whi = (whi >> 8) | (aa << 56);
+    }
+    WinReg<W> wm;
+    wm.init(w_runtime);
+    uint32_t prev = W - 1; // frame-relative position of the previous window's minimum (none yet)
+    uint32_t pin = sb + (uint32_t)k - 1;
+    uint64_t mv;
+    uint32_t mu;
+#define B200SK_PM_STEP(J, FIRST)                                           \
+    {                                                                      \
+        const uint64_t aa = lds_u8(sm, pin + (J));                         \
+        wlo = (wlo >> 8) | (whi << 56);                                    \
+        whi = (whi >> 8) | (aa << 56);                                     \
+        if (wm.push(J, FIRST, wyhash_window(wlo, whi, (uint32_t)k), mv, mu)) { \
+            sink.emit_if(mu != prev, mv, mu - prev);                       \
+            prev = mu;                                                     \
+        }                                                                  \
+    }
+#pragma unroll
+    for (int j = 0; j < W; j++) B200SK_PM_STEP(j, true)
+    wm.close_block();
+    prev -= W;
+    pin += W;
+    uint32_t u0 = W;
+    while (u0 + W <= nstep) {
+#pragma unroll
+        for (int j = 0; j < W; j++) B200SK_PM_STEP(j, false)
+        wm.close_block();
+        prev -= W;
+        pin += W;
+        u0 += W;
+    }
+    const uint32_t rem = nstep - u0;
+#pragma unroll
+    for (int j = 0; j < W - 1; j++) {
+        if ((uint32_t)j >= rem) break;
+        B200SK_PM_STEP(j, false)
+    }
+#undef B200SK_PM_STEP
+}
+
 // ------------------------------------------------------------------ kernel: one tile per WARP
 // A tile is 32 consecutive items; every warp runs its own ticket -> TMA -> walk -> look-back -> ordered
 // copy loop with no block-wide barrier, so warps drift freely and cover each other's latencies.
@@ -489,11 +541,12 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     constexpr bool SYNC = MODE == B200SK_MODE_SYNCMER;
+    constexpr bool PROT = MODE == B200SK_MODE_PROTEIN_MINIMIZER; // items are amino acids: no tables, no rewriting
     // tables (64 codes): [0,1K) in {A, rolB_{h-1}}, [1K,2K) out {rolA_h, rorB_1} for the streamed hash
     // (h = k for minimizers, s for syncmers); syncmer adds [2K,3K) k-mer out table, [3K,3.5K) rolB_{k-1}
     const int hk = SYNC ? a.s : a.k;
     constexpr uint32_t FT = SYNC ? 3584u : 2048u; // fast-table block (1 KB)
-    {
+    if (!PROT) {
         ulonglong2 *tIn = reinterpret_cast<ulonglong2 *>(smem), *tOut = tIn + 64, *tOutK = tIn + 128;
         uint64_t *tInK = reinterpret_cast<uint64_t *>(smem + 3072);
         for (uint32_t c = tid; c < 64; c += blockDim.x) {
@@ -549,7 +602,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         if (bytes && span_ok) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
-            {
+            if (!PROT) {
                 // ASCII -> fast bytes, 16 bytes per lane per trip; any byte outside ACGTacgt (alignment slop
                 // included: a false alarm only costs the general path) -> fetch again and write 6-bit codes
                 uint32_t bad = 0;
@@ -571,7 +624,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     parity ^= 1u;
                 }
             }
-            if (!fast) {
+            if (!fast && !PROT) {
                 // ASCII -> codes, 16 bytes per lane per trip
                 for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
                     uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
@@ -596,7 +649,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         const int32_t lim0 = (int32_t)(it.end - it.q0);
         const uint32_t halo = it.q0 != it.p0 ? 1u : 0u;
         if (run) {
-            if (SYNC)
+            if (PROT) protmin_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, sink);
+            else if (SYNC)
                 if (fast) syncmer_item_reg<W, true>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
                                                      FT, s_kring, lim0, halo, sink);
                 else syncmer_item_reg<W, false>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
@@ -676,7 +730,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     GlobalSink gs;
                     gs.gv = a.out_val + mine; gs.gp = a.out_pos; gs.gi = mine; gs.pw = a.pos_width;
                     gs.pos = it.q0 - 1u; gs.cnt = 0; gs.skip = skip;
-                    if (SYNC)
+                    if (PROT) protmin_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, gs);
+                    else if (SYNC)
                         if (fast) syncmer_item_reg<W, true>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
                                                              2048u, FT, s_kring, lim0, halo, gs);
                         else syncmer_item_reg<W, false>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u,
@@ -711,13 +766,14 @@ static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_
 // units (this file compiled with -DB200SK_PART=0..3, see the Makefile) so that they build in parallel;
 // part 0 also holds the dispatcher.  B200SK_FAST_BUILD (development) keeps a handful.
 #ifndef B200SK_PART
-#error "compile with -DB200SK_PART=0..3"
+#error "compile with -DB200SK_PART=0..4"
 #endif
 #ifdef B200SK_FAST_BUILD
 #define B200SK_LIST_0 B200SK_W(B200SK_MODE_MINIMIZER, 3) B200SK_W(B200SK_MODE_MINIMIZER, 5) B200SK_W(B200SK_MODE_MINIMIZER, 11)
 #define B200SK_LIST_1 B200SK_W(B200SK_MODE_MINIMIZER, 15) B200SK_W(B200SK_MODE_MINIMIZER, 20)
 #define B200SK_LIST_2 B200SK_W(B200SK_MODE_SYNCMER, 2) B200SK_W(B200SK_MODE_SYNCMER, 10)
 #define B200SK_LIST_3 B200SK_W(B200SK_MODE_SYNCMER, 20)
+#define B200SK_LIST_4 B200SK_W(B200SK_MODE_PROTEIN_MINIMIZER, 5)
 #else
 #define B200SK_M(W) B200SK_W(B200SK_MODE_MINIMIZER, W)
 #define B200SK_S(W) B200SK_W(B200SK_MODE_SYNCMER, W)
@@ -731,6 +787,11 @@ static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_
 #define B200SK_LIST_2                                                                                        \
     B200SK_S(2) B200SK_S(4) B200SK_S(6) B200SK_S(8) B200SK_S(10) B200SK_S(12) B200SK_S(14) B200SK_S(16)
 #define B200SK_LIST_3 B200SK_S(18) B200SK_S(20) B200SK_S(22) B200SK_S(24)
+#define B200SK_P(W) B200SK_W(B200SK_MODE_PROTEIN_MINIMIZER, W)
+#define B200SK_LIST_4                                                                                        \
+    B200SK_P(2) B200SK_P(3) B200SK_P(4) B200SK_P(5) B200SK_P(6) B200SK_P(7) B200SK_P(8) B200SK_P(9)          \
+    B200SK_P(10) B200SK_P(11) B200SK_P(12) B200SK_P(13) B200SK_P(14) B200SK_P(15) B200SK_P(16) B200SK_P(17)  \
+    B200SK_P(18) B200SK_P(19) B200SK_P(20) B200SK_P(21) B200SK_P(22) B200SK_P(23) B200SK_P(24)
 #endif
 #define B200SK_CAT2(a, b) a##b
 #define B200SK_CAT(a, b) B200SK_CAT2(a, b)
@@ -758,11 +819,13 @@ bool B200SK_CAT(sparse_reg_has_part, B200SK_PART)(int mode, int window) {
 cudaError_t launch_sparse_reg_part1(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
 cudaError_t launch_sparse_reg_part2(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
 cudaError_t launch_sparse_reg_part3(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
+cudaError_t launch_sparse_reg_part4(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
 bool sparse_reg_has_part1(int, int);
 bool sparse_reg_has_part2(int, int);
 bool sparse_reg_has_part3(int, int);
+bool sparse_reg_has_part4(int, int);
 
-static int window_of(int mode, int k, int w, int s) { return mode == B200SK_MODE_MINIMIZER ? w : 2 * (k - s); }
+static int window_of(int mode, int k, int w, int s) { return mode == B200SK_MODE_SYNCMER ? 2 * (k - s) : w; }
 
 // occ != nullptr: only report the occupancy
 cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
@@ -776,14 +839,18 @@ cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStrea
     if (has) return e;
     e = launch_sparse_reg_part3(a, window, threads, blocks, st, occ, &has);
     if (has) return e;
+    e = launch_sparse_reg_part4(a, window, threads, blocks, st, occ, &has);
+    if (has) return e;
     return cudaErrorInvalidValue;
 }
 
 bool sparse_reg_supported(int mode, int k, int w, int s) {
-    if (mode != B200SK_MODE_MINIMIZER && mode != B200SK_MODE_SYNCMER) return false;
+    if (mode != B200SK_MODE_MINIMIZER && mode != B200SK_MODE_SYNCMER && mode != B200SK_MODE_PROTEIN_MINIMIZER) return false;
+    if (mode == B200SK_MODE_PROTEIN_MINIMIZER && k > 16) return false; // the register window holds 16 residues
     const int window = window_of(mode, k, w, s);
     return sparse_reg_has_part0(mode, window) || sparse_reg_has_part1(mode, window) ||
-           sparse_reg_has_part2(mode, window) || sparse_reg_has_part3(mode, window);
+           sparse_reg_has_part2(mode, window) || sparse_reg_has_part3(mode, window) ||
+           sparse_reg_has_part4(mode, window);
 }
 #endif
 
