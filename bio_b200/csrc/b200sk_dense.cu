@@ -71,28 +71,29 @@ __global__ void k_first_illegal(const uint8_t *__restrict__ bases, const uint64_
 
 // ------------------------------------------------------------------ translation of one frame of every read
 // seq.Seq.Translate(table, frame, trim=false, clean=false, allowUnknownCodon=true, markInitCodonAsM=false)
-// (sketch-protein.go:84, codon_tables.go:205-285): aa[aa_off[r] + t], one warp per read.
+// (sketch-protein.go:84, codon_tables.go:205-285): aa[aa_off[r] + t], eight lanes per read.
 __global__ void __launch_bounds__(256) k_translate(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
                                                    const uint64_t *__restrict__ aa_off, uint64_t n_reads, int frame,
                                                    const uint8_t *__restrict__ aux, uint8_t *aa) {
     __shared__ uint8_t tab[4608];
     for (uint32_t i = threadIdx.x; i < 4608; i += blockDim.x) tab[i] = aux[i];
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
-    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    // eight lanes per read (four reads per warp): a 150-bp frame is 50 residues, 32 lanes per read would idle
+    const unsigned sub = threadIdx.x & 7u;
+    const uint64_t grp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 3;
+    const uint64_t ngrp = ((uint64_t)gridDim.x * blockDim.x) >> 3;
     const uint8_t *pl = tab + 4352;
-    for (uint64_t r = warp; r < n_reads; r += nwarps) {
+    for (uint64_t r = grp; r < n_reads; r += ngrp) {
         const uint8_t *s = bases + off[r];
         const uint64_t L = off[r + 1] - off[r];
         const uint64_t o = aa_off[r], n = aa_off[r + 1] - o;
         if (frame > 0) {
-            for (uint64_t t = lane; t < n; t += 32) {
+            for (uint64_t t = sub; t < n; t += 8) {
                 const uint64_t i = (uint64_t)(frame - 1) + 3 * t;
                 aa[o + t] = (uint8_t)codon_aa(tab, s[i], s[i + 1], s[i + 2]);
             }
         } else {
-            for (uint64_t t = lane; t < n; t += 32) {
+            for (uint64_t t = sub; t < n; t += 8) {
                 const uint64_t i = L - (uint64_t)(-frame) - 3 * t;
                 aa[o + t] = (uint8_t)codon_aa(tab, pl[s[i]], pl[s[i - 1]], pl[s[i - 2]]);
             }
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) k_translate(const uint8_t *__restrict__ b
 
 cudaError_t launch_translate(const uint8_t *bases, const uint64_t *off, const uint64_t *aa_off, uint64_t n_reads,
                              int frame, const uint8_t *aux, uint8_t *aa, cudaStream_t st) {
-    uint64_t cb = (n_reads + 7) / 8;
+    uint64_t cb = (n_reads + 31) / 32;
     if (cb > 148 * 16) cb = 148 * 16;
     if (cb == 0) cb = 1;
     k_translate<<<(unsigned)cb, 256, 0, st>>>(bases, off, aa_off, n_reads, frame, aux, aa);
