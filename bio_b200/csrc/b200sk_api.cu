@@ -16,7 +16,7 @@
 namespace b200sk {
 cudaError_t launch_prepass(const KArgs &a, unsigned long long *meta, cudaStream_t st);
 cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *tile_state,
-                              unsigned long long *ticket, cudaStream_t st);
+                              unsigned long long *ticket, cudaStream_t st, uint64_t *tile_read);
 cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st);
 int main_kernel_occupancy(const KArgs &a, int threads);
 cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
@@ -112,7 +112,7 @@ struct b200sk_ctx {
     DevBuf meta;       // [0] ticket, [1] flags, [2] n_items, [3] max_len, [4] scan ticket  (u64 each)
     DevBuf tile_state; // main kernel look-back words
     DevBuf scan_state; // item scan look-back words
-    DevBuf item_first;
+    DevBuf item_first, tile_read;
     DevBuf circ_bases, circ_off;
     DevBuf ill, aux, aa_bases, aa_off;
     int aux_table = -1;
@@ -438,7 +438,12 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(ctx->scan_state.reserve(sbytes));
         CK(cudaMemsetAsync(ctx->scan_state.p, 0, sbytes, st));
         CK(cudaMemsetAsync(meta + 4, 0, 8, st));
-        CK(launch_scan_items(a, (uint64_t *)ctx->item_first.p, (uint64_t *)ctx->scan_state.p, meta + 4, st));
+        // the read that holds the first item of every group of 32 items: item -> (read, chunk) is then a search
+        // over 32 reads instead of all of them
+        CK(ctx->tile_read.reserve((items_bound / 32 + 2) * 8));
+        CK(launch_scan_items(a, (uint64_t *)ctx->item_first.p, (uint64_t *)ctx->scan_state.p, meta + 4, st,
+                             (uint64_t *)ctx->tile_read.p));
+        a.tile_read = (const uint64_t *)ctx->tile_read.p;
         ctx->launches++;
         a.item_first = (const uint64_t *)ctx->item_first.p;
         a.n_items_dev = (const uint64_t *)ctx->item_first.p + n_reads;
@@ -599,7 +604,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->circ_bases,
+    for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->tile_read, &ctx->circ_bases,
                       &ctx->circ_off, &ctx->ill, &ctx->aux, &ctx->aa_bases, &ctx->aa_off, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
                       &ctx->d_status, &ctx->d_bases2, &ctx->d_off2, &ctx->d_val2, &ctx->d_pos2, &ctx->d_ooff2,
                       &ctx->d_status2})

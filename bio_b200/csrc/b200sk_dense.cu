@@ -181,6 +181,7 @@ __device__ __forceinline__ void dense_item_geometry(const KArgs &a, const ReadGe
             uint32_t c = 0;
             if (a.item_first) {
                 uint64_t lo = 0, hi = a.n_reads;
+                if (a.tile_read) { lo = a.tile_read[item >> 5]; hi = lo + 32 < a.n_reads ? lo + 32 : a.n_reads; }
                 while (hi - lo > 1) {
                     const uint64_t mid = (lo + hi) >> 1;
                     if (a.item_first[mid] <= item) lo = mid; else hi = mid;

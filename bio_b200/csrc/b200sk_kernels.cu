@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) k_scan_reads(const uint64_t *__restrict__
                                                     const uint64_t *__restrict__ off_orig, uint64_t n_reads,
                                                     const ReadGeom g, uint32_t C, uint64_t base,
                                                     uint64_t *item_first, int32_t *status_out,
-                                                    uint64_t *tile_state, unsigned long long *ticket) {
+                                                    uint64_t *tile_state, unsigned long long *ticket,
+                                                    uint64_t *tile_read = nullptr) {
     __shared__ uint32_t warp_sums[34];
     __shared__ uint64_t sh_tile, sh_base;
     for (;;) {
@@ -98,6 +99,8 @@ __global__ void __launch_bounds__(256) k_scan_reads(const uint64_t *__restrict__
         for (int i = 0; i < 4; i++) {
             const uint64_t r = r0 + i;
             if (r < n_reads) item_first[r] = run;
+            if (!COUNTS && tile_read && r < n_reads) // the read that holds item 32 t, for every t this read covers
+                for (uint64_t t = (run + 31) >> 5; (t << 5) < run + c[i]; t++) tile_read[t] = r;
             run += c[i];
             if (r + 1 == n_reads) item_first[n_reads] = run;
         }
@@ -487,12 +490,12 @@ cudaError_t launch_prepass(const KArgs &a, unsigned long long *meta, cudaStream_
 }
 
 cudaError_t launch_scan_items(const KArgs &a, uint64_t *item_first, uint64_t *tile_state,
-                              unsigned long long *ticket, cudaStream_t st) {
+                              unsigned long long *ticket, cudaStream_t st, uint64_t *tile_read) {
     uint64_t tiles = (a.n_reads + 1023) / 1024;
     uint64_t blocks = tiles < 148 * 8 ? tiles : 148 * 8;
     if (blocks == 0) blocks = 1;
     k_scan_reads<false><<<(unsigned)blocks, 256, 0, st>>>(a.off, a.off_orig, a.n_reads, a.geom(), a.C, 0, item_first,
-                                                         nullptr, tile_state, ticket);
+                                                         nullptr, tile_state, ticket, tile_read);
     return cudaGetLastError();
 }
 

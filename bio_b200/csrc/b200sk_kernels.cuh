@@ -22,6 +22,7 @@ struct KArgs {
     const uint64_t *off_orig; // circular only: original offsets (length checks use the un-extended length)
     uint64_t n_reads;
     const uint64_t *item_first; // chunked: exclusive scan of chunks per read (n_reads+1); else nullptr
+    const uint64_t *tile_read;  // chunked: read that holds item 32 t, per group of 32 items (may be nullptr)
     uint64_t n_items;           // == item_first[n_reads] when chunked (read on device), else n_reads
     const uint64_t *n_items_dev;
     uint64_t *out_val;
