@@ -456,3 +456,15 @@ def test_protein_values_only_amino_acid_input(gpu_ctx):
                 s = b[int(o[i]):int(o[i + 1])]
                 vals += [oracle.wyhash(s[j:j + k], 1) for j in range(L - k + 1)]
         assert [int(v) for v in res["val"]] == vals
+
+
+def test_protein_minimizer_low_complexity_overflow(gpu_ctx):
+    """Homopolymer reads translate to one repeated residue: every window moves its leftmost minimum, the staged
+    lists overflow and the items are walked again straight to global memory (register-window kernel, k <= 16)."""
+    b, o = synth.ragged_reads([150] * 300 + [900] * 40, 31, alphabet=b"A")
+    b2, o2 = synth.ragged_reads([150] * 64, 32)
+    bases = np.concatenate([b, b2])
+    off = np.concatenate([o, o2[1:] + o[-1]])
+    for k, w, frame in ((10, 5, 1), (7, 3, -2), (16, 24, 3)):
+        res, ref = run_both(gpu_ctx, cabi.MODE_PROTEIN_MINIMIZER, bases, off, k=k, w=w, frame=frame)
+        assert_same(res, ref, f"k={k} w={w} frame={frame}")
