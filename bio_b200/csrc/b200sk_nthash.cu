@@ -390,6 +390,9 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
         const uint32_t last_block = vend ? ((vend - 1) / 16u) * 16u : 0u; // first virtual step of the lane's last block
         const uint32_t s_row = s_stage + lane * NH_ROW;
         __syncwarp();
+        uint64_t *rowdst[8]; // destinations (virtual step 0) of rows 4i + lane/8
+#pragma unroll
+        for (int i = 0; i < 8; i++) rowdst[i] = reinterpret_cast<uint64_t *>(lds64(smem, s_desc + (4u * i + (lane >> 3)) * 8u));
         for (uint32_t v0 = 0; v0 < maxv; v0 += 16u) {
             // lanes whose item is finished (or absent) re-read their own last block: the loads stay
             // unconditional and inside the tile
@@ -430,11 +433,17 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
             // flush: rows 2i and 2i+1 per store instruction
             const uint32_t half = lane >> 4, e = lane & 15u;
             if (full) {
-#pragma unroll 8
-                for (uint32_t i = 0; i < 16u; i++) {
-                    const uint32_t src = 2u * i + half;
-                    uint64_t *dst = reinterpret_cast<uint64_t *>(lds64(smem, s_desc + src * 8u));
-                    dst[v0 + e] = lds64(smem, s_stage + src * NH_ROW + e * 8u);
+                // whole, sector-aligned rows: four rows per store instruction, eight lanes per row, 16 bytes per
+                // lane (rows start on 32-byte sectors, so the 16-byte stores are aligned); the eight rows a lane
+                // serves keep their destinations in registers
+                const uint32_t q = lane >> 3, e2 = (lane & 7u) * 2u;
+#pragma unroll
+                for (uint32_t i = 0; i < 8u; i++) {
+                    const uint32_t src = 4u * i + q;
+                    ulonglong2 v;
+                    v.x = lds64(smem, s_stage + src * NH_ROW + e2 * 8u);
+                    v.y = lds64(smem, s_stage + src * NH_ROW + e2 * 8u + 8u);
+                    *reinterpret_cast<ulonglong2 *>(rowdst[i] + v0 + e2) = v;
                 }
             } else {
                 const uint32_t lohi = lo | (hi << 8);
