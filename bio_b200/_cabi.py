@@ -44,7 +44,10 @@ EXPORTS = (
     "b200sk_enqueue_device", "b200sk_strerror", "b200sk_last_error", "b200sk_kernel_launches",
     "b200sk_version", "b200sk_timing_enable", "b200sk_timing_collect",
     "b200sk_fastx_parse_device", "b200sk_run_fastx", "b200sk_copy_to_host",
+    "b200sk_fxstream_open", "b200sk_fxstream_next", "b200sk_fxstream_rewind", "b200sk_fxstream_close",
+    "b200sk_fxstream_kernel_launches", "b200sk_fxstream_last_error",
 )
+FXSTREAM_END = 1
 
 FASTX_FASTA, FASTX_FASTQ = 1, 2
 ERR_NOT_FASTX, ERR_BAD_FASTQ = -20, -21
@@ -149,6 +152,19 @@ def lib():
     L.b200sk_run_fastx.argtypes = [vp, PP, u8p, C.c_uint64, C.c_int, C.c_int, C.POINTER(FastxInfo),
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.b200sk_fxstream_open.restype = C.c_int
+    L.b200sk_fxstream_open.argtypes = [C.POINTER(C.c_void_p), C.c_int, PP, u8p, C.c_uint64, C.c_int, C.c_uint64]
+    L.b200sk_fxstream_next.restype = C.c_int
+    L.b200sk_fxstream_next.argtypes = [vp, C.POINTER(FastxInfo), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.b200sk_fxstream_rewind.restype = C.c_int
+    L.b200sk_fxstream_rewind.argtypes = [vp, u8p, C.c_uint64, C.c_int]
+    L.b200sk_fxstream_close.restype = None
+    L.b200sk_fxstream_close.argtypes = [vp]
+    L.b200sk_fxstream_kernel_launches.restype = C.c_uint64
+    L.b200sk_fxstream_kernel_launches.argtypes = [vp]
+    L.b200sk_fxstream_last_error.restype = C.c_char_p
+    L.b200sk_fxstream_last_error.argtypes = [vp]
     _lib = L
     return L
 
@@ -328,3 +344,91 @@ class Context:
         pdt = {1: np.uint8, 2: np.uint16}.get(int(params.pos_width), np.uint32)
         return dict(val=view(ov, t, np.uint64), pos=view(op, t, pdt) if params.want_pos else None,
                     off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t, info=info)
+
+
+class FastxStream:
+    """b200sk_fxstream: a whole FASTA/FASTQ text in host memory, sketched chunk by chunk with the copy and parse
+    of the next chunk overlapping the sketching and copy back of this one.  Iterating yields one dict per chunk
+    (as Context.run_fastx); with copy=False the arrays are views valid until the next chunk is asked for."""
+
+    def __init__(self, params, text, device=0, fmt=0, chunk_bytes=0, copy=True):
+        self._h = None
+        self.params, self.copy = params, copy
+        self._text = self._as_array(text)
+        h = C.c_void_p()
+        rc = lib().b200sk_fxstream_open(C.byref(h), device, C.byref(params), self._ptr(), len(self._text), fmt,
+                                        chunk_bytes)
+        if rc != 0:
+            raise SketchError(rc)
+        self._h = h
+
+    @staticmethod
+    def _as_array(text):
+        import numpy as np
+        return np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(text, dtype=np.uint8)
+
+    def _ptr(self):
+        return self._text.ctypes.data if len(self._text) else None
+
+    def rewind(self, text=None, fmt=0):
+        if text is not None:
+            self._text = self._as_array(text)
+        rc = lib().b200sk_fxstream_rewind(self._h, self._ptr(), len(self._text), fmt)
+        if rc != 0:
+            raise SketchError(rc)
+
+    def next(self):
+        """The next chunk, or None after the last one."""
+        import numpy as np
+        info = FastxInfo()
+        ov, op, oo, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        total = C.c_uint64(0)
+        rc = lib().b200sk_fxstream_next(self._h, C.byref(info), C.byref(ov), C.byref(op), C.byref(oo), C.byref(st),
+                                        C.byref(total))
+        if rc == FXSTREAM_END:
+            return None
+        if rc != 0:
+            e = SketchError(rc, lib().b200sk_fxstream_last_error(self._h).decode() if rc == -100 else "")
+            e.info = info
+            raise e
+        t, n = int(total.value), int(info.n_records)
+
+        def view(ptr, count, dt):
+            if not ptr.value or count == 0:
+                return np.zeros(0, dtype=dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dt).itemsize,))
+            a = a.view(dt)
+            return a.copy() if self.copy else a
+
+        pdt = {1: np.uint8, 2: np.uint16}.get(int(self.params.pos_width), np.uint32)
+        return dict(val=view(ov, t, np.uint64), pos=view(op, t, pdt) if self.params.want_pos else None,
+                    off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t, info=info)
+
+    def __iter__(self):
+        while True:
+            c = self.next()
+            if c is None:
+                return
+            yield c
+
+    @property
+    def kernel_launches(self):
+        return int(lib().b200sk_fxstream_kernel_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200sk_fxstream_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -34,7 +34,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 
 #include "../../include/b200sketch.h"
 #include "b200sk_device.cuh"
@@ -538,18 +541,29 @@ int b200sk_copy_to_host(b200sk_ctx *ctx, void *dst, const void *d_src, uint64_t 
     return 0;
 }
 
-int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *text, uint64_t n_bytes, int format,
-                     int final, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
-                     int32_t **read_status, uint64_t *n_out) {
-    if (!ctx || !p || !info || (n_bytes && !text)) return B200SK_ERR_BAD_ARG;
-    int rc = b200sk_check_params(p);
-    if (rc) return rc;
+} // extern "C"
+
+namespace b200sk {
+
+// b200sk_run_fastx in two stages, so that the pipelined reader below can start the next chunk's copy as soon as
+// this chunk's parse has told where the next chunk begins.
+// stage 1: text chunk (host) -> HBM -> records
+static int fx_stage_parse(b200sk_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int format, int final,
+                          b200sk_fastx_info *info) {
     FCK(cudaSetDevice(ctx_device(ctx)));
     cudaStream_t st = ctx_stream(ctx);
     FxState *fx = state_of(ctx);
     FCK(fx->text.reserve(((n_bytes + 15) & ~15ull) + 16));
     if (n_bytes) FCK(cudaMemcpyAsync(fx->text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
-    if ((rc = b200sk_fastx_parse_device(ctx, (const uint8_t *)fx->text.p, n_bytes, format, final, st, info))) return rc;
+    return b200sk_fastx_parse_device(ctx, (const uint8_t *)fx->text.p, n_bytes, format, final, st, info);
+}
+// stage 2: records -> sketches -> pinned host arrays
+static int fx_sketch_fetch(b200sk_ctx *ctx, const b200sk_params *p, const b200sk_fastx_info *info, uint64_t **out_val,
+                           uint32_t **out_pos, uint64_t **out_off, int32_t **read_status, uint64_t *n_out) {
+    FCK(cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t st = ctx_stream(ctx);
+    FxState *fx = state_of(ctx);
+    int rc = 0;
     const uint64_t nrec = info->n_records;
     b200sk_params q = *p;
     if (q.max_read_len == 0) q.max_read_len = info->max_read_len; // FASTQ: measured by the parse
@@ -558,7 +572,8 @@ int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *tex
     uint64_t got = 0;
     FCK(fx->o_off.reserve((nrec + 1) * 8));
     FCK(fx->o_status.reserve((nrec + 1) * 4));
-    for (int attempt = 0; attempt < 2; attempt++) {
+    if (nrec == 0) FCK(cudaMemsetAsync(fx->o_off.p, 0, 8, st)); // a chunk without a complete record
+    for (int attempt = 0; nrec && attempt < 2; attempt++) {
         FCK(fx->o_val.reserve(cap * 8 + 64));
         if (q.want_pos) FCK(fx->o_pos.reserve(cap * pw + 64));
         rc = b200sk_run_device(ctx, &q, info->d_bases, info->d_read_off, nrec, info->n_bases, (uint64_t *)fx->o_val.p,
@@ -583,6 +598,185 @@ int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *tex
     if (read_status) *read_status = (int32_t *)fx->h_status.p;
     if (n_out) *n_out = got;
     return 0;
+}
+
+} // namespace b200sk
+
+// ------------------------------------------------------------------ pipelined reader
+// A whole FASTA/FASTQ text in host memory, handed back chunk by chunk like a reader loop.  Two slots, each
+// with its own b200sk_ctx (stream, device and pinned buffers) and its own worker thread; chunk j runs on slot
+// j mod 2.  The only dependency between chunks is where the next one starts (the first byte the records of
+// this one do not cover), known after stage 1; so chunk j+1's copy and parse overlap chunk j's sketching
+// and its copy back, and both overlap the caller consuming chunk j-1.
+struct b200sk_fxstream {
+    struct Slot {
+        b200sk_ctx *ctx = nullptr;
+        std::thread th;
+        int state = 0; // 0 free, 1 busy, 2 ready
+        uint64_t chunk = ~0ull;
+        int rc = 0;
+        b200sk_fastx_info info;
+        uint64_t *val = nullptr, *off = nullptr, n_out = 0;
+        uint32_t *pos = nullptr;
+        int32_t *status = nullptr;
+    } slot[2];
+    std::mutex mu;
+    std::condition_variable cv;
+    b200sk_params params;
+    const uint8_t *text = nullptr;
+    uint64_t n_bytes = 0, chunk_bytes = 0;
+    int format = 0;
+    // assignment state (under mu)
+    uint64_t next_start = 0, next_index = 0; // the next chunk to hand to a worker
+    bool start_ready = false;                // next_start is known (stage 1 of the chunk before has ended)
+    bool exhausted = true;                   // no further chunk will be assigned (end of text or error)
+    bool stop = false;
+    uint64_t deliver = 0;                    // index of the chunk the next call returns
+    bool holding = false;                    // the caller still owns the arrays of chunk deliver-1
+
+    void work(int x) {
+        Slot &s = slot[x];
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return stop || (!exhausted && start_ready && s.state == 0 && (next_index & 1) == (uint64_t)x); });
+            if (stop) return;
+            const uint64_t j = next_index, start = next_start;
+            start_ready = false;
+            s.state = 1;
+            s.chunk = j;
+            const int fmt = format;
+            lk.unlock();
+            uint64_t n = std::min(chunk_bytes, n_bytes - start);
+            int rc, final;
+            for (;;) { // a chunk that holds no complete record grows until it does
+                final = start + n == n_bytes;
+                rc = b200sk::fx_stage_parse(s.ctx, text + start, n, fmt, final, &s.info);
+                if (rc || final || s.info.consumed) break;
+                n = std::min(n * 2, n_bytes - start);
+            }
+            lk.lock();
+            if (rc || final) exhausted = true;
+            else {
+                if (!format) format = s.info.format;
+                next_start = start + s.info.consumed;
+                next_index = j + 1;
+                start_ready = true;
+            }
+            cv.notify_all();
+            lk.unlock();
+            if (!rc) rc = b200sk::fx_sketch_fetch(s.ctx, &params, &s.info, &s.val, &s.pos, &s.off, &s.status, &s.n_out);
+            lk.lock();
+            s.rc = rc;
+            if (rc) exhausted = true;
+            s.state = 2;
+            cv.notify_all();
+        }
+    }
+};
+
+extern "C" {
+
+int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *text, uint64_t n_bytes, int format,
+                     int final, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+                     int32_t **read_status, uint64_t *n_out) {
+    if (!ctx || !p || !info || (n_bytes && !text)) return B200SK_ERR_BAD_ARG;
+    int rc = b200sk_check_params(p);
+    if (rc) return rc;
+    if ((rc = b200sk::fx_stage_parse(ctx, text, n_bytes, format, final, info))) return rc;
+    return b200sk::fx_sketch_fetch(ctx, p, info, out_val, out_pos, out_off, read_status, n_out);
+}
+
+int b200sk_fxstream_rewind(b200sk_fxstream *s, const uint8_t *text, uint64_t n_bytes, int format) {
+    if (!s || (n_bytes && !text)) return B200SK_ERR_BAD_ARG;
+    std::unique_lock<std::mutex> lk(s->mu);
+    s->exhausted = true; // nothing new starts; wait for the chunks in flight
+    s->cv.wait(lk, [&] { return s->slot[0].state != 1 && s->slot[1].state != 1; });
+    for (auto &sl : s->slot) { sl.state = 0; sl.chunk = ~0ull; }
+    s->text = text;
+    s->n_bytes = n_bytes;
+    s->format = format;
+    s->next_start = 0;
+    s->next_index = 0;
+    s->deliver = 0;
+    s->holding = false;
+    s->start_ready = true;
+    s->exhausted = false;
+    s->cv.notify_all();
+    return 0;
+}
+
+int b200sk_fxstream_open(b200sk_fxstream **out, int device, const b200sk_params *p, const uint8_t *text,
+                         uint64_t n_bytes, int format, uint64_t chunk_bytes) {
+    if (!out || !p || (n_bytes && !text)) return B200SK_ERR_BAD_ARG;
+    *out = nullptr;
+    int rc = b200sk_check_params(p);
+    if (rc) return rc;
+    b200sk_fxstream *s = new b200sk_fxstream();
+    s->params = *p;
+    s->chunk_bytes = chunk_bytes ? std::max<uint64_t>(chunk_bytes, 64) : (256ull << 20);
+    for (auto &sl : s->slot)
+        if ((rc = b200sk_create(&sl.ctx, device))) {
+            for (auto &t : s->slot) b200sk_destroy(t.ctx);
+            delete s;
+            return rc;
+        }
+    for (int x = 0; x < 2; x++) s->slot[x].th = std::thread([s, x] { s->work(x); });
+    b200sk_fxstream_rewind(s, text, n_bytes, format);
+    *out = s;
+    return 0;
+}
+
+int b200sk_fxstream_next(b200sk_fxstream *s, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos,
+                         uint64_t **out_off, int32_t **read_status, uint64_t *n_out) {
+    if (!s || !info) return B200SK_ERR_BAD_ARG;
+    std::unique_lock<std::mutex> lk(s->mu);
+    if (s->holding) { // the arrays of the chunk returned last go back to their slot
+        b200sk_fxstream::Slot &prev = s->slot[(s->deliver - 1) & 1];
+        prev.state = 0;
+        s->holding = false;
+        s->cv.notify_all();
+    }
+    b200sk_fxstream::Slot &sl = s->slot[s->deliver & 1];
+    s->cv.wait(lk, [&] {
+        return (sl.state == 2 && sl.chunk == s->deliver) || (s->exhausted && sl.state != 1 && sl.chunk != s->deliver);
+    });
+    if (!(sl.state == 2 && sl.chunk == s->deliver)) return B200SK_FXSTREAM_END;
+    s->deliver++;
+    s->holding = true;
+    *info = sl.info;
+    if (sl.rc) return sl.rc;
+    if (out_val) *out_val = sl.val;
+    if (out_pos) *out_pos = sl.pos;
+    if (out_off) *out_off = sl.off;
+    if (read_status) *read_status = sl.status;
+    if (n_out) *n_out = sl.n_out;
+    return 0;
+}
+
+uint64_t b200sk_fxstream_kernel_launches(const b200sk_fxstream *s) {
+    return s ? b200sk_kernel_launches(s->slot[0].ctx) + b200sk_kernel_launches(s->slot[1].ctx) : 0;
+}
+
+const char *b200sk_fxstream_last_error(const b200sk_fxstream *s) {
+    if (!s) return "";
+    const char *e = b200sk_last_error(s->slot[0].ctx);
+    return e && *e ? e : b200sk_last_error(s->slot[1].ctx);
+}
+
+void b200sk_fxstream_close(b200sk_fxstream *s) {
+    if (!s) return;
+    {
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->exhausted = true;
+        s->cv.wait(lk, [&] { return s->slot[0].state != 1 && s->slot[1].state != 1; });
+        s->stop = true;
+        s->cv.notify_all();
+    }
+    for (auto &sl : s->slot) {
+        if (sl.th.joinable()) sl.th.join();
+        b200sk_destroy(sl.ctx);
+    }
+    delete s;
 }
 
 } // extern "C"

@@ -198,6 +198,28 @@ int b200sk_run_fastx(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *tex
                      int final, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
                      int32_t **read_status, uint64_t *n_out);
 
+/* Pipelined reader: the loop above over a WHOLE FASTA/FASTQ text in host memory (an mmap'd or slurped file;
+ * pinned for full copy speed), handed back chunk by chunk in file order -- what
+ *     for chunk := range reader.ChunkChan(bufferSize, chunkSize) { ... }     (seqio/fastx/reader.go:556-603)
+ * is to Read().  Two slots, each with its own device buffers, pinned arrays, stream and worker thread: the copy
+ * and parse of chunk j+1 overlap the sketching and copy back of chunk j and the caller consuming chunk j-1.
+ * Chunks are cut every chunk_bytes of text (0 = 256 MiB) and end on a record boundary (b200sk_fastx_info
+ * .consumed); a chunk that holds no complete record grows until it does.  format: 0 = detect.
+ * b200sk_fxstream_next returns 0 and one chunk of records (info and arrays as b200sk_run_fastx; valid until the
+ * next call on this stream), B200SK_FXSTREAM_END after the last chunk, or the B200SK_ERR_* of the chunk that
+ * failed (chunks before it are returned first; none after it).  One caller thread per stream.
+ * b200sk_fxstream_rewind points an open stream at another text (the buffers are kept). */
+#define B200SK_FXSTREAM_END 1
+typedef struct b200sk_fxstream b200sk_fxstream;
+int b200sk_fxstream_open(b200sk_fxstream **s, int device, const b200sk_params *p, const uint8_t *text,
+                         uint64_t n_bytes, int format, uint64_t chunk_bytes);
+int b200sk_fxstream_next(b200sk_fxstream *s, b200sk_fastx_info *info, uint64_t **out_val, uint32_t **out_pos,
+                         uint64_t **out_off, int32_t **read_status, uint64_t *n_out);
+int b200sk_fxstream_rewind(b200sk_fxstream *s, const uint8_t *text, uint64_t n_bytes, int format);
+void b200sk_fxstream_close(b200sk_fxstream *s);
+uint64_t b200sk_fxstream_kernel_launches(const b200sk_fxstream *s);
+const char *b200sk_fxstream_last_error(const b200sk_fxstream *s);
+
 /* Synchronous copy of a library-owned device array (the feeder's tables) into host memory. */
 int b200sk_copy_to_host(b200sk_ctx *ctx, void *dst, const void *d_src, uint64_t bytes);
 

@@ -130,6 +130,30 @@ def main():
                       "ms": t * 1e3, "bases_per_s": n * L / t, "text_GBps": nb / t / 1e9,
                       "h2d_bytes": nb, "d2h_bytes": int(res["total"]) * 9 + 12 * n, "elements": int(res["total"])}),
           flush=True)
+    total_one_shot = int(res["total"])
+    chk_one_shot = int(res["val"][:1000].sum())
+    # ---- the same through the pipelined reader (b200sk_fxstream: two slots, chunks of chunk_mb of text)
+    for chunk_mb in (64, 256):
+        stream = cabi.FastxStream(p, htext, chunk_bytes=chunk_mb << 20, copy=False)
+        tot = sum(c["total"] for c in stream)  # warm-up: allocates both slots' buffers
+        assert tot == total_one_shot
+        ts = []
+        for _ in range(3):
+            stream.rewind()
+            t0 = time.perf_counter()
+            tot, nrec, nch, first = 0, 0, 0, None
+            for c in stream:
+                if first is None:
+                    first = int(c["val"][:1000].sum())
+                tot += c["total"]; nrec += int(c["info"].n_records); nch += 1
+            ts.append(time.perf_counter() - t0)
+        assert tot == total_one_shot and nrec == n and first == chk_one_shot
+        t = float(np.median(ts))
+        print(json.dumps({"config": f"e2e pipelined: FASTQ text (pinned host) -> minimizers k=21 w=11 (host), {n} x {L} bp, "
+                                    f"b200sk_fxstream, {nch} chunks of {chunk_mb} MiB",
+                          "ms": t * 1e3, "bases_per_s": n * L / t, "text_GBps": nb / t / 1e9,
+                          "h2d_bytes": nb, "d2h_bytes": tot * 9 + 12 * n, "elements": tot}), flush=True)
+        stream.close()
     # ---- CPU: oracle restatement of Reader.Read on one core, bounded sample
     m = min(n, 1_000_000)
     sample = text[:m * (nb // n)].tobytes()

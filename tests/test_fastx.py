@@ -224,3 +224,60 @@ def test_run_fastx_matches_sketch_of_oracle_records():
     ref = oracle.run_batch(o["bases"], o["read_off"], oracle.MODE_MINIMIZER, threads=4, k=21, w=11)
     assert np.array_equal(res["val"], ref["val"]) and np.array_equal(res["off"], ref["off"])
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_fxstream_equals_one_shot():
+    """The pipelined reader (b200sk_fxstream, two slots / two worker threads) over a text cut every few KB returns,
+    chunk after chunk, exactly the records and sketches of the oracle on the whole text; rewind reuses the stream;
+    a record larger than the chunk grows the chunk; errors arrive in order."""
+    cabi, _ = _ctx()
+    cases = [make_fastq(4000, 150, 31, at_quals=True) + (dict(k=21, w=11), 10007),
+             make_fastq(900, 150, 32, crlf=True, tail_newline=False) + (dict(k=21, w=11), 64),
+             make_fasta(400, 33, blank_lines=True) + (dict(k=15, w=7), 4099),
+             make_fastq(50, 150, 34) + (dict(k=21, w=11), 0)]
+    stream = None
+    for text, seqs, kw, chunk in cases:
+        p = cabi.make_params(cabi.MODE_MINIMIZER, **kw)
+        o = oracle.fastx_parse(text)
+        ref = oracle.run_batch(o["bases"], o["read_off"], oracle.MODE_MINIMIZER, threads=4, **kw)
+        for rep in range(2):
+            if stream is None or rep == 0:
+                if stream is not None:
+                    stream.close()
+                stream = cabi.FastxStream(p, text, chunk_bytes=chunk)
+            else:
+                stream.rewind()  # same text again through the same buffers
+            nrec, nval, nchunk, pos_in_text = 0, 0, 0, 0
+            for c in stream:
+                n, t = int(c["info"].n_records), c["total"]
+                assert np.array_equal(c["off"], ref["off"][nrec:nrec + n + 1] - ref["off"][nrec])
+                assert np.array_equal(c["val"], ref["val"][nval:nval + t])
+                assert np.array_equal(c["pos"], ref["pos"][nval:nval + t])
+                assert np.array_equal(c["status"], ref["status"][nrec:nrec + n])
+                nrec, nval, nchunk = nrec + n, nval + t, nchunk + 1
+                pos_in_text += int(c["info"].consumed)
+            assert nrec == o["n_records"] == len(seqs) and nval == len(ref["val"])
+            assert pos_in_text == len(text)
+            assert nchunk > 1 or chunk == 0
+            assert stream.next() is None  # stays at the end
+        assert stream.kernel_launches > 0
+    # empty text: one empty chunk, then the end
+    stream.rewind(b"")
+    c = stream.next()
+    assert c is not None and c["total"] == 0 and int(c["info"].n_records) == 0 and stream.next() is None
+    # a broken record in the middle: the chunks before it arrive, then the error, then nothing
+    good, _ = make_fastq(300, 150, 35)
+    bad = good + b"@broken\nACGT\n+\nII\n" + good
+    stream.rewind(bad)
+    got = 0
+    with pytest.raises(cabi.SketchError) as ei:
+        for c in stream:
+            got += int(c["info"].n_records)
+    assert ei.value.code == cabi.ERR_BAD_FASTQ and got <= 300
+    assert stream.next() is None
+    stream.rewind(b"not a fastx file\n")
+    with pytest.raises(cabi.SketchError) as ei:
+        stream.next()
+    assert ei.value.code == cabi.ERR_NOT_FASTX
+    stream.close()
