@@ -31,6 +31,7 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"io"
 	"unsafe"
 
 	"github.com/shenwei356/bio/seq"
@@ -358,3 +359,64 @@ func (t *TextChunk) MinimizerSketchText(n, format int, final bool, k, w int) (*F
 		Format: int(info.format), Records: nrec, Consumed: int(info.consumed), IsFastq: info.format == C.B200SK_FASTX_FASTQ,
 	}, nil
 }
+
+// FastxStream is the pipelined reader over a whole FASTA/FASTQ text in C-owned pinned memory (a slurped or
+// decompressed file): what `for chunk := range reader.ChunkChan(bufferSize, chunkSize)` is to Read()
+// (seqio/fastx/reader.go:556-603).  The library runs two slots with a worker thread each, so the copy and parse of
+// chunk j+1 overlap the sketching and copy back of chunk j and the Go code consuming chunk j-1.
+type FastxStream struct{ h *C.b200sk_fxstream }
+
+// NewMinimizerStream opens a stream of minimizer sketches over text.Bytes()[:n]; chunkBytes = 0 means 256 MiB.
+func NewMinimizerStream(device int, text *TextChunk, n, format, k, w int, chunkBytes uint64) (*FastxStream, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_MINIMIZER, k: C.int32_t(k), w: C.int32_t(w), want_pos: 1, pos_width: 4}
+	var h *C.b200sk_fxstream
+	if rc := C.b200sk_fxstream_open(&h, C.int(device), &p, (*C.uint8_t)(text.buf), C.uint64_t(n), C.int(format),
+		C.uint64_t(chunkBytes)); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	return &FastxStream{h: h}, nil
+}
+
+// Next returns the next chunk of records in file order, io.EOF after the last one.  The slices of a chunk are
+// valid until the next call.
+func (s *FastxStream) Next() (*FastxResult, error) {
+	var info C.b200sk_fastx_info
+	var v *C.uint64_t
+	var ps *C.uint32_t
+	var o *C.uint64_t
+	var st *C.int32_t
+	var total C.uint64_t
+	rc := C.b200sk_fxstream_next(s.h, &info, &v, &ps, &o, &st, &total)
+	switch rc {
+	case 0:
+	case C.B200SK_FXSTREAM_END:
+		return nil, io.EOF
+	case C.B200SK_ERR_NOT_FASTX:
+		return nil, ErrNotFASTXFormat
+	case C.B200SK_ERR_BAD_FASTQ:
+		return nil, ErrBadFASTQFormat
+	default:
+		return nil, codeToError(rc)
+	}
+	nrec := int(info.n_records)
+	return &FastxResult{
+		Result: Result{
+			val:    unsafe.Slice((*uint64)(unsafe.Pointer(v)), int(total)),
+			pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
+			off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), nrec+1),
+			status: unsafe.Slice((*int32)(unsafe.Pointer(st)), nrec),
+		},
+		Format: int(info.format), Records: nrec, Consumed: int(info.consumed), IsFastq: info.format == C.B200SK_FASTX_FASTQ,
+	}, nil
+}
+
+// Rewind points the stream at another text (the device and pinned buffers are kept).
+func (s *FastxStream) Rewind(text *TextChunk, n, format int) error {
+	if rc := C.b200sk_fxstream_rewind(s.h, (*C.uint8_t)(text.buf), C.uint64_t(n), C.int(format)); rc != 0 {
+		return codeToError(rc)
+	}
+	return nil
+}
+
+// Close stops the workers and frees both slots.
+func (s *FastxStream) Close() { C.b200sk_fxstream_close(s.h); s.h = nil }
