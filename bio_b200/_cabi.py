@@ -372,9 +372,11 @@ class FastxStream:
         return self._text.ctypes.data if len(self._text) else None
 
     def rewind(self, text=None, fmt=0):
+        old = self._text  # chunks of the old text may still be in flight until the call below returns
         if text is not None:
             self._text = self._as_array(text)
         rc = lib().b200sk_fxstream_rewind(self._h, self._ptr(), len(self._text), fmt)
+        del old
         if rc != 0:
             raise SketchError(rc)
 

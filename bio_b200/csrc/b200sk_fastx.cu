@@ -27,7 +27,7 @@
 //   k_fq_scan     FASTQ: per record validate + sequence length -> read_off / rec_off / qual_off (look-back scan),
 //                 then the sequence lines -> packed bases in the same pass
 //   k_fa_scan     FASTA: per line header flag + sequence bytes -> out_pos per line, read_off / rec_off per record
-//   k_fa_copy     FASTA sequence lines -> packed bases (a warp per line)
+//   k_fa_copy     FASTA sequence lines -> packed bases (a warp per 32 lines)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -138,34 +138,36 @@ __device__ __forceinline__ uint32_t range_mask16(uint64_t pos, uint64_t lo, uint
 }
 
 // L[i] = start of line i: L[0] = start0, L[i] = position after the i-th newline at or after start0.
-// One pass: tiles of 32 KB (128 contiguous bytes per thread, eight 16-byte loads in flight), per-tile newline
-// counts ordered by a decoupled look-back.
+// One pass: tiles of 32 KB = 8 rows of 4 KB; in a row thread t owns bytes [16 t, 16 t + 16), so every load
+// instruction of a warp is one contiguous 512-byte run (eight such loads in flight per thread).  Newline counts are
+// scanned per (row, warp) -- position order -- and the per-tile totals ordered by a decoupled look-back.
 #define FX_TILE 32768ull
+#define FX_ROW 4096ull
 __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta,
                                                   uint64_t *tile_state, uint64_t *__restrict__ L, uint64_t cap) {
-    __shared__ uint32_t warp_sums[34];
+    __shared__ uint32_t ws[64]; // newlines of (row u, warp w) at [8 u + w], then their exclusive prefix
     __shared__ uint64_t s_tile, s_base;
     const uint64_t start0 = meta[M_START];
     const bool fasta = meta[M_FORMAT] == B200SK_FASTX_FASTA;
     const uint64_t ntiles = (n + FX_TILE - 1) / FX_TILE;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (blockIdx.x == 0 && tid == 0 && fasta && start0 < n) atomicAdd(meta + M_HDR, 1ULL); // the first record
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(meta + M_TICKET, 1ULL);
         __syncthreads();
         const uint64_t tile = s_tile;
         if (tile >= ntiles) break;
-        const uint64_t pos0 = tile * FX_TILE + (uint64_t)tid * 128;
+        const uint64_t pos0 = tile * FX_TILE + (uint64_t)tid * 16;
         uint4 xs[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const uint64_t pos = pos0 + u * 16;
+            const uint64_t pos = pos0 + u * FX_ROW;
             xs[u] = (pos < n && pos + 16 > start0) ? reinterpret_cast<const uint4 *>(t)[pos / 16] : make_uint4(0, 0, 0, 0);
         }
-        uint32_t m[8], cnt = 0;
+        uint32_t m[8], inc[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const uint64_t pos = pos0 + u * 16;
+            const uint64_t pos = pos0 + u * FX_ROW;
             m[u] = 0;
             if (pos >= start0 && pos + 16 <= n) { // interior: count first, positions only where there is a newline
                 const uint32_t a = eq_msb(xs[u].x, 0x0a0a0a0au), b = eq_msb(xs[u].y, 0x0a0a0a0au);
@@ -174,25 +176,50 @@ __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t,
             } else if (pos < n && pos + 16 > start0) {
                 m[u] = eq_mask16(xs[u], 0x0a0a0a0au) & range_mask16(pos, start0, n);
             }
-            cnt += __popc(m[u]);
+            inc[u] = __popc(m[u]);
         }
-        uint32_t total;
-        const uint32_t excl = block_excl_scan(cnt, warp_sums, &total);
-        if (tid < 32) {
-            const uint64_t b = lookback_exclusive(tile_state, tile, total);
-            if (tid == 0) s_base = b;
+        // eight independent warp scans (inclusive), one per row
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc[u], o);
+                if (lane >= (uint32_t)o) inc[u] += v;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) ws[8 * u + warp] = inc[u];
         }
         __syncthreads();
-        if (tid == 0 && tile + 1 == ntiles) meta[M_NL] = s_base + total; // all newlines of the text
-        uint64_t idx = s_base + excl + 1; // line index the next newline of this thread opens
+        if (tid < 32) { // 64 (row, warp) counts -> exclusive prefix in position order; tile total -> look-back
+            const uint32_t v0 = ws[2 * lane], v1 = ws[2 * lane + 1];
+            uint32_t sum = v0 + v1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, sum, o);
+                if (lane >= (uint32_t)o) sum += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, sum, 31);
+            ws[2 * lane] = sum - v0 - v1;
+            ws[2 * lane + 1] = sum - v1;
+            const uint64_t b = lookback_exclusive(tile_state, tile, total);
+            if (tid == 0) {
+                s_base = b;
+                if (tile + 1 == ntiles) meta[M_NL] = b + total; // all newlines of the text
+            }
+        }
+        __syncthreads();
+        const uint64_t base = s_base;
         uint32_t hd = 0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             uint32_t mm = m[u];
+            uint64_t idx = base + ws[8 * u + warp] + inc[u] - __popc(mm) + 1; // line index this chunk's first newline opens
             while (mm) {
                 const int j = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const uint64_t ls = pos0 + u * 16 + j + 1;
+                const uint64_t ls = pos0 + u * FX_ROW + j + 1;
                 if (idx < cap) L[idx] = ls; // a table sized from a bound: the host re-runs with the exact size
                 idx++;
                 if (fasta && ls < n && t[ls] == '>') hd++; // a record delimiter: '>' right after a newline
@@ -201,7 +228,7 @@ __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t,
         if (fasta) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) hd += __shfl_xor_sync(0xffffffffu, hd, o);
-            if ((tid & 31u) == 0 && hd) atomicAdd(meta + M_HDR, (unsigned long long)hd);
+            if (lane == 0 && hd) atomicAdd(meta + M_HDR, (unsigned long long)hd);
         }
         __syncthreads();
     }
@@ -300,13 +327,15 @@ __global__ void __launch_bounds__(256) k_fa_scan(const uint8_t *__restrict__ t, 
         const uint64_t tile = s_tile;
         if (tile >= ntiles) break;
         const uint64_t i = tile * 256 + tid;
-        uint32_t len = 0, hdr = 0;
+        uint32_t len = 0, hdr = 0, cr = 0;
         uint64_t s = 0;
         if (i < nlines) {
             s = L[i];
             const uint64_t nx = L[i + 1];
             hdr = (nx - 1 > s && t[s] == '>') ? 1u : 0u; // an empty line is not a header
+            const uint32_t full = (uint32_t)(nx - 1 - s);
             len = hdr ? 0u : line_len(t, s, nx);
+            cr = hdr ? 0u : full - len;
         }
         uint32_t total_len, total_hdr;
         const uint32_t excl_len = block_excl_scan(len, warp_sums, &total_len);
@@ -319,7 +348,7 @@ __global__ void __launch_bounds__(256) k_fa_scan(const uint8_t *__restrict__ t, 
         __syncthreads();
         if (i < nlines) {
             const uint64_t op = s_base_len + excl_len;
-            outpos[i] = op;
+            outpos[i] = op | ((uint64_t)hdr << 63) | ((uint64_t)cr << 62); // what k_fa_copy needs to know of the line
             if (hdr) {
                 const uint64_t r = s_base_hdr + excl_hdr;
                 read_off[r] = op;
@@ -335,18 +364,34 @@ __global__ void __launch_bounds__(256) k_fa_scan(const uint8_t *__restrict__ t, 
         __syncthreads();
     }
 }
+// A warp takes 32 consecutive lines: line starts, output positions and the header / CR flags (top bits of outpos,
+// left there by k_fa_scan) arrive in three coalesced loads, so no text byte is read before the copy itself and the
+// 32 lines' copies are independent of each other.
 __global__ void __launch_bounds__(256) k_fa_copy(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
                                                  const uint64_t *__restrict__ outpos, uint64_t nlines, uint64_t limit,
                                                  uint8_t *__restrict__ bases) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t nwarp = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nlines; i += nwarp) {
-        const uint64_t s = L[i], nx = L[i + 1];
-        if (s >= limit) continue;                   // lines of a record that is not complete in this chunk
-        if (nx - 1 > s && t[s] == '>') continue;    // header
-        const uint32_t len = line_len(t, s, nx);
-        const uint64_t d = outpos[i];
-        for (uint32_t j = lane; j < len; j += 32u) bases[d + j] = t[s + j];
+    for (uint64_t base = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < nlines;
+         base += nwarp * 32) {
+        const uint64_t i = base + lane;
+        uint64_t s = 0, d = 0;
+        uint32_t len = 0;
+        if (i < nlines) {
+            s = L[i];
+            const uint64_t nx = L[i + 1], op = outpos[i];
+            d = op & ((1ull << 62) - 1);
+            // not: headers, lines of a record that is not complete in this chunk
+            if (!(op >> 63) && s < limit) len = (uint32_t)(nx - 1 - s) - (uint32_t)((op >> 62) & 1u);
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, len != 0);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint64_t sk = __shfl_sync(0xffffffffu, s, k), dk = __shfl_sync(0xffffffffu, d, k);
+            const uint32_t lk = __shfl_sync(0xffffffffu, len, k);
+            for (uint32_t j = lane; j < lk; j += 32u) bases[dk + j] = t[sk + j];
+        }
     }
 }
 
@@ -512,7 +557,7 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         }
         FCK(fx->bases.reserve(total + 64));
         if (nlines && total) {
-            const unsigned cb = (unsigned)std::min<uint64_t>((nlines + 7) / 8, 148ull * 16);
+            const unsigned cb = (unsigned)std::min<uint64_t>((nlines + 255) / 256, 148ull * 16);
             k_fa_copy<<<cb, 256, 0, st>>>(d_text, L, (const uint64_t *)fx->outpos.p, nlines, limit, (uint8_t *)fx->bases.p);
             ctx_add_launches(ctx, 1);
         }
@@ -633,6 +678,7 @@ struct b200sk_fxstream {
     bool stop = false;
     uint64_t deliver = 0;                    // index of the chunk the next call returns
     bool holding = false;                    // the caller still owns the arrays of chunk deliver-1
+    bool failed = false;                     // an error has been returned: nothing follows it
 
     void work(int x) {
         Slot &s = slot[x];
@@ -699,6 +745,7 @@ int b200sk_fxstream_rewind(b200sk_fxstream *s, const uint8_t *text, uint64_t n_b
     s->next_index = 0;
     s->deliver = 0;
     s->holding = false;
+    s->failed = false;
     s->start_ready = true;
     s->exhausted = false;
     s->cv.notify_all();
@@ -736,6 +783,7 @@ int b200sk_fxstream_next(b200sk_fxstream *s, b200sk_fastx_info *info, uint64_t *
         s->holding = false;
         s->cv.notify_all();
     }
+    if (s->failed) return B200SK_FXSTREAM_END;
     b200sk_fxstream::Slot &sl = s->slot[s->deliver & 1];
     s->cv.wait(lk, [&] {
         return (sl.state == 2 && sl.chunk == s->deliver) || (s->exhausted && sl.state != 1 && sl.chunk != s->deliver);
@@ -744,7 +792,10 @@ int b200sk_fxstream_next(b200sk_fxstream *s, b200sk_fastx_info *info, uint64_t *
     s->deliver++;
     s->holding = true;
     *info = sl.info;
-    if (sl.rc) return sl.rc;
+    if (sl.rc) {
+        s->failed = true;
+        return sl.rc;
+    }
     if (out_val) *out_val = sl.val;
     if (out_pos) *out_pos = sl.pos;
     if (out_off) *out_off = sl.off;
