@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="e2e: do not bind the rank to its GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -298,6 +299,9 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
     """Same metric through b200sk_run: inputs in pinned HOST memory, every step copies them to the device,
     sketches, and copies values, positions, offsets and statuses back to pinned host memory."""
     import ctypes
+    from bio_b200 import shard
+    # the pinned buffers allocated below land on the NUMA node of this rank's GPU
+    prev_affinity, binding = shard.bind_host_to_device(dev.index) if not args.no_bind else (None, "off")
     n = args.e2e_reads
     if n <= 0:
         try:
@@ -345,9 +349,11 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
            "h2d_bytes_per_step": nb + (n + 1) * 8,
            "d2h_bytes_per_step": n_out * 9 + (n + 1) * 8 + n * 4, "pos_width": 1,
            "reads_per_gpu_per_step": n, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-           "api": "b200sk_run (host pointers, pinned)", "checksum_first_1000": chk}
+           "api": "b200sk_run (host pointers, pinned)", "checksum_first_1000": chk, "host_binding": binding}
     L.b200sk_free_pinned(hb_ptr)
     L.b200sk_free_pinned(ho_ptr)
+    if prev_affinity is not None:
+        shard.restore_host_binding(prev_affinity)
     return out
 
 

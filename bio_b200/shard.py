@@ -3,6 +3,7 @@ reference constructor: sketches/iterator.go:615-655, sketches/sketch.go:85-202),
 contiguous range of reads on its own GPU; the only exchange is an optional gather of the per-GPU uint64
 hash arrays (rank order == read order, so no sort is needed).  torch.distributed is plumbing here: NCCL
 over NVLink on the GPUs, gloo in the CPU tests."""
+import os
 import time
 
 import numpy as np
@@ -80,3 +81,42 @@ def timed_gather(part, dist, dev, reps=3):
         del out
     return {"bytes_over_nvlink": nbytes, "ms": best, "GBps": nbytes / (best * 1e-3) / 1e9 if best else None,
             "what": "gather of each GPU's uint64 minimizer array (1/world of its output) to rank 0 over NCCL"}
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device(device):
+    """Run the calling thread (and the threads it starts) on the CPUs of the NUMA node GPU `device` hangs off, so
+    that the pinned batch buffers it allocates next are local to that GPU's PCIe root (sysfs `local_cpulist` of the
+    GPU's PCI function).  With several ranks on one host, every rank's H2D/D2H traffic then stays on its own socket
+    instead of crossing the inter-socket link.  Returns (previous affinity, description); a host without the sysfs
+    entry is left as it is."""
+    import torch
+    prev = os.sched_getaffinity(0)
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read()) & prev
+        node = open(base + "/numa_node").read().strip()
+        if not cpus:
+            return prev, "unbound (no local cpus in the allowed set for %s)" % bdf
+        os.sched_setaffinity(0, cpus)
+        return prev, "numa node %s of %s, %d cpus" % (node, bdf, len(cpus))
+    except Exception as e:  # no sysfs / no such attribute: nothing to bind to
+        return prev, "unbound (%s)" % type(e).__name__
+
+
+def restore_host_binding(prev):
+    try:
+        os.sched_setaffinity(0, prev)
+    except Exception:
+        pass

@@ -62,3 +62,16 @@ def test_shard_bounds():
     assert b[0] == 0 and b[-1] == 5 and b == sorted(b)
     b = shard.shard_bounds_by_bases(off, 8)
     assert len(b) == 9 and b == sorted(b)
+
+
+def test_host_binding_helpers():
+    """cpulist parsing; binding is a no-op (and says so) where there is no GPU / sysfs entry to bind to."""
+    import os
+    from bio_b200 import shard
+    assert shard._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert shard._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    prev, what = shard.bind_host_to_device(0)
+    assert prev == before and isinstance(what, str)
+    shard.restore_host_binding(prev)
+    assert os.sched_getaffinity(0) == before
