@@ -470,6 +470,13 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         cap = hm[M_NL] + 3;
     }
     const int detected = (int)hm[M_FORMAT];
+    // reader.go:286-294: while the format is still being detected the reader tolerates leading blank lines only up
+    // to byte 10240 (more than 100 of them): a '\n' at an index > 10240 with nothing but newlines before it is
+    // ErrNotFASTXFormat
+    if (format == 0 && std::min<uint64_t>(hm[M_START], n_bytes) >= 10242) {
+        info->status = B200SK_ERR_NOT_FASTX;
+        return B200SK_ERR_NOT_FASTX;
+    }
     if (hm[M_START] >= n_bytes) { // only newlines: nothing to parse
         info->format = format;
         info->consumed = final ? n_bytes : 0;

@@ -164,7 +164,7 @@ def test_fasta_parity(kw):
 @pytest.mark.gpu
 def test_errors_and_edges():
     cabi, ctx = _ctx()
-    for bad in (b"hello\n", b"\r\n>a\nAC\n"):
+    for bad in (b"hello\n", b"\r\n>a\nAC\n", b" \n"):  # b" \n" = blank.fx, reader_test.go:160
         with pytest.raises(cabi.SketchError) as e:
             _parse_gpu(ctx, bad)
         assert e.value.code == cabi.ERR_NOT_FASTX
@@ -174,9 +174,33 @@ def test_errors_and_edges():
         assert e.value.code == cabi.ERR_BAD_FASTQ
     info, g = _parse_gpu(ctx, b"\n\n\n")
     assert g["n_records"] == 0
+    # reader.go:286-294: leading blank lines are tolerated up to byte 10240 only
+    for lead in (10241, 10242, 20000, 2_000_000):
+        for tail in (b">a\nACGT\n", b""):
+            text = b"\n" * lead + tail
+            o = oracle.fastx_parse(text)
+            if o["status"] == 0:
+                info, g = _parse_gpu(ctx, text)
+                assert g["n_records"] == o["n_records"]
+            else:
+                assert o["status"] == cabi.ERR_NOT_FASTX
+                with pytest.raises(cabi.SketchError) as e:
+                    _parse_gpu(ctx, text)
+                assert e.value.code == cabi.ERR_NOT_FASTX
+    for name, want in (("blank.fx", cabi.ERR_NOT_FASTX), ("blank1.fx", 0), ("empty.fx", 0)):  # reader_test.go:160-197
+        if os.path.isdir(REF):
+            text = open(os.path.join(REF, name), "rb").read()
+            o = oracle.fastx_parse(text)
+            assert o["status"] == want and o["n_records"] == 0
     info, g = _parse_gpu(ctx, b">only header")
     o = oracle.fastx_parse(b">only header")
     assert g["n_records"] == o["n_records"] == 1 and g["read_off"].tolist() == [0, 0]
+    # the reference's test4.fa: a record without sequence between two others, a two-line sequence
+    t4 = b">a\nATC\n>b\n>123\nATCGN\n>abcdefg\nATCGN\nGCCTN\n"
+    info, g = _parse_gpu(ctx, t4)
+    o = oracle.fastx_parse(t4)
+    _same(g, o, False)
+    assert g["read_off"].tolist() == [0, 3, 3, 8, 18] and bytes(g["bases"]) == b"ATCATCGNATCGNGCCTN"
     ctx.close()
 
 
