@@ -130,6 +130,11 @@ __device__ __forceinline__ uint32_t eq_mask16(const uint4 v, uint32_t c4) {
     auto nib = [](uint32_t x) { return (x * 0x00204081u) >> 21 & 0xfu; }; // (1 + 2^7 + 2^14 + 2^21) spreads, top nibble collects
     return nib(a) | (nib(b) << 4) | (nib(c) << 8) | (nib(d) << 12);
 }
+// the same mask from the four eq_msb words of the vector (bit 7 of byte i of word w -> bit 4 w + i)
+__device__ __forceinline__ uint32_t nib_of_msb(uint32_t a) { return (((a >> 7) * 0x00204081u) >> 21) & 0xfu; }
+__device__ __forceinline__ uint32_t mask16_of_msb(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return nib_of_msb(a) | (nib_of_msb(b) << 4) | (nib_of_msb(c) << 8) | (nib_of_msb(d) << 12);
+}
 __device__ __forceinline__ uint32_t range_mask16(uint64_t pos, uint64_t lo, uint64_t hi) { // bytes pos+j in [lo, hi)
     uint32_t m = 0xffffu;
     if (pos < lo) m &= lo - pos >= 16 ? 0u : (0xffffu << (uint32_t)(lo - pos));
@@ -158,25 +163,27 @@ __global__ void __launch_bounds__(256) k_fx_lines(const uint8_t *__restrict__ t,
         const uint64_t tile = s_tile;
         if (tile >= ntiles) break;
         const uint64_t pos0 = tile * FX_TILE + (uint64_t)tid * 16;
-        uint4 xs[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint64_t pos = pos0 + u * FX_ROW;
-            xs[u] = (pos < n && pos + 16 > start0) ? reinterpret_cast<const uint4 *>(t)[pos / 16] : make_uint4(0, 0, 0, 0);
-        }
         uint32_t m[8], inc[8];
+        if (tile * FX_TILE >= start0 && (tile + 1) * FX_TILE <= n) { // a tile inside the text: no range checks
+            uint4 xs[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint64_t pos = pos0 + u * FX_ROW;
-            m[u] = 0;
-            if (pos >= start0 && pos + 16 <= n) { // interior: count first, positions only where there is a newline
+            for (int u = 0; u < 8; u++) xs[u] = reinterpret_cast<const uint4 *>(t)[(pos0 + u * FX_ROW) / 16];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
                 const uint32_t a = eq_msb(xs[u].x, 0x0a0a0a0au), b = eq_msb(xs[u].y, 0x0a0a0a0au);
                 const uint32_t c = eq_msb(xs[u].z, 0x0a0a0a0au), d = eq_msb(xs[u].w, 0x0a0a0a0au);
-                if (a | b | c | d) m[u] = eq_mask16(xs[u], 0x0a0a0a0au);
-            } else if (pos < n && pos + 16 > start0) {
-                m[u] = eq_mask16(xs[u], 0x0a0a0a0au) & range_mask16(pos, start0, n);
+                m[u] = (a | b | c | d) ? mask16_of_msb(a, b, c, d) : 0u;
+                inc[u] = __popc(m[u]);
             }
-            inc[u] = __popc(m[u]);
+        } else { // the tile with the first record / the end of the text
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint64_t pos = pos0 + u * FX_ROW;
+                m[u] = 0;
+                if (pos < n && pos + 16 > start0)
+                    m[u] = eq_mask16(reinterpret_cast<const uint4 *>(t)[pos / 16], 0x0a0a0a0au) & range_mask16(pos, start0, n);
+                inc[u] = __popc(m[u]);
+            }
         }
         // eight independent warp scans (inclusive), one per row
 #pragma unroll
