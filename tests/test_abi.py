@@ -82,3 +82,10 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(cabi.SketchError) as e:
         cabi.Context(0)
     assert e.value.code == cabi.ERR_NO_DEVICE
+    # the pipelined reader refuses the same way (and bad parameters come back before any device is touched)
+    with pytest.raises(cabi.SketchError) as e:
+        cabi.FastxStream(cabi.make_params(cabi.MODE_MINIMIZER, k=21, w=11), b"@r\nACGT\n+\nIIII\n")
+    assert e.value.code == cabi.ERR_NO_DEVICE
+    with pytest.raises(cabi.SketchError) as e:
+        cabi.FastxStream(cabi.make_params(cabi.MODE_MINIMIZER, k=21, w=0), b"@r\nACGT\n+\nIIII\n")
+    assert e.value.code == -3  # ErrInvalidW, sketches/sketch.go:89
