@@ -5,7 +5,9 @@ names, the records being found on the GPU a chunk of text at a time (b200sk_fast
 
 Shape that performs: `Reader.batches()` hands out (FastxInfo, text chunk) pairs whose packed bases and
 offsets are already resident in HBM -- feed `info.d_bases / info.d_read_off` straight to
-`Context.run_device`, or call `Context.run_fastx` to go text -> sketches in one C-ABI call.
+`Context.run_device`, or call `Context.run_fastx` to go text -> sketches in one C-ABI call; `SketchStream`
+(b200sk_fxstream) does that for a whole text with the chunks pipelined -- the `ChunkChan` shape
+(seqio/fastx/reader.go:556-603).
 
 There is no CPU fallback: the reader needs a CUDA device.
 """
@@ -14,6 +16,8 @@ import io
 import numpy as np
 
 from . import _cabi as cabi
+
+SketchStream = cabi.FastxStream  # for chunk in SketchStream(params, text): chunk["val"], chunk["pos"], chunk["off"]
 
 
 class ErrNotFASTXFormat(Exception):  # seqio/fastx/reader.go:16
