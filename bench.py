@@ -4,20 +4,23 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the sketching hot path (sketches.NewMinimizerSketch + NextMinimizer/Index over
-every read, reference: sketches/sketch.go:85,205) over one batch of synthetic reads, through the
-C ABI of libb200sketch.so.  Records shard over ranks with no data-path collective ("weak": every
-GPU holds one C3-sized shard).
+A step = one pass of the sketching hot path (sketches.NewMinimizerSketch + NextMinimizer/Index over every read,
+reference: sketches/sketch.go:85,205) over ONE batch of 100 M synthetic reads (BASELINE.json config 3), through the
+C ABI of libb200sketch.so.  With N GPUs the batch is SHARDED over the ranks ("scaling": "strong") and the gather of
+the per-GPU uint64 arrays to rank 0 is INSIDE the step: every rank's sketching kernel stores its minimizers straight
+into rank 0's gather buffer over NVLink (CUDA-IPC peer mapping, b200sk_gather_*), the per-rank counts travel over
+NCCL (8 bytes each), rank 0 closes the gaps between the rank segments (b200sk_compact_segments).
 
 JSON line (rank 0):
-  value      whole-job bases/s with the batch already resident in HBM (device entry point)
-  e2e        same metric through the host entry point b200sk_run: pinned HOST buffers in, H2D and D2H
-             copies inside the timed region
-  roofline   algorithmic bytes of the sketching kernel / its CUDA-event duration vs measured HBM copy peak
-  cpu_baseline  the oracle (C restatement of the Go loops -- Go is absent here) on the host cores,
-             bounded sample of the same workload
+  value         whole-job bases/s, batch resident in HBM, gathered array complete on rank 0 when the clock stops
+  e2e           same metric through the host entry point b200sk_run: pinned HOST buffers in, H2D and D2H inside
+  roofline      algorithmic bytes of the sketching kernel / its CUDA-event duration vs the measured HBM copy peak
+  parity        sampled oracle check of every config's device output, done BEFORE anything is timed (abort on mismatch)
+  secondary     BASELINE.json configs 2, 4, 5 with their own roofline fractions
+  cpu_baseline  the oracle (C restatement of the Go loops -- Go is absent here) on the host cores (N=1 only)
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -28,8 +31,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, W, READ_LEN = 21, 11, 150
+K, W, S, READ_LEN = 21, 11, 11, 150
 SEED = 43
+BLOCK = 500_000  # reads per generator block: shard boundaries of 1/2/4/8 ranks fall on block boundaries
 METRIC = "bases/sec sketched (k=21,w=11 minimizer)"
 
 
@@ -39,13 +43,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU per step (C3: 100M x 150 bp)")
-    ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU per e2e step (0 = auto)")
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads in the C3 batch (whole job)")
+    ap.add_argument("--c2-reads", type=int, default=10_000_000)
+    ap.add_argument("--c4-reads", type=int, default=1_000_000)
+    ap.add_argument("--c5-reads", type=int, default=10_000_000)
+    ap.add_argument("--parity-reads", type=int, default=100_000, help="reads per config in the oracle sample")
+    ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU per e2e step (0 = the rank's shard, memory permitting)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=2_000_000, help="reads in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="e2e: do not bind the rank to its GPU's NUMA node")
     return ap.parse_args()
 
@@ -127,18 +135,112 @@ def ncu_traffic():
     return None
 
 
-def algorithmic_bytes(n_reads, n_bases, n_out):
-    # each base read once (1 B ASCII), 8 B read offset in; 8 B value + 4 B position per
+def algorithmic_bytes(n_reads, n_bases, n_out, pos_bytes=4):
+    # each base read once (1 B ASCII), 8 B read offset in; 8 B value (+ 4 B position) per
     # emitted element and 8 B output offset per read out.
-    return n_bases + 8 * n_reads + 12 * n_out + 8 * n_reads
+    return n_bases + 8 * n_reads + (8 + pos_bytes) * n_out + 8 * n_reads
+
+
+def shard_bounds(n, world):
+    """equal-count contiguous shards, boundaries on generator blocks when n allows it"""
+    nb = (n + BLOCK - 1) // BLOCK
+    return [min(n, (nb * r // world) * BLOCK) if r < world else n for r in range(world + 1)]
+
+
+def gen_uniform_shard(torch, r0, r1, read_len, seed, dev):
+    """reads [r0, r1) of the job-wide batch: block b of BLOCK reads is drawn from its own seed, so the union over the
+    ranks is the same batch for every N.  Padded by 64 bytes (the 16-byte TMA units of the last tile)."""
+    n = (r1 - r0) * read_len
+    buf = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    buf[n:] = 0
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev)
+    pos = 0
+    b = r0 // BLOCK
+    r = r0
+    while r < r1:
+        e = min(r1, (b + 1) * BLOCK)
+        g.manual_seed(seed * 1_000_003 + b)
+        full = torch.randint(0, 4, (BLOCK * read_len,), generator=g, device=dev, dtype=torch.int64)
+        lo = (r - b * BLOCK) * read_len
+        cnt = (e - r) * read_len
+        buf[pos:pos + cnt] = lut[full[lo:lo + cnt]]
+        pos += cnt
+        r = e
+        b += 1
+    off = torch.arange(r1 - r0 + 1, dtype=torch.int64, device=dev) * read_len
+    return buf, off
+
+
+def gather_ranges(torch, src, starts, lens, chunk=50_000_000):
+    """concatenate src[starts[i] : starts[i] + lens[i]] on the device, in chunks of about `chunk` elements"""
+    outs = []
+    n = starts.numel()
+    i = 0
+    csum = torch.cumsum(lens, 0)
+    while i < n:
+        base = int(csum[i - 1].item()) if i else 0
+        j = int(torch.searchsorted(csum, torch.tensor([base + chunk], device=csum.device)).item()) + 1
+        j = min(max(j, i + 1), n)
+        ls = lens[i:j]
+        tot = int(ls.sum().item())
+        if tot:
+            ex = torch.cumsum(ls, 0) - ls
+            idx = torch.repeat_interleave(starts[i:j] - ex, ls) + torch.arange(tot, device=src.device)
+            outs.append(src[idx])
+        i = j
+    return torch.cat(outs) if outs else src[:0]
+
+
+def parity_sample(torch, np, oracle, name, omode, okw, d_bases, d_off, val, pos, ooff, status, n_sample, seed, threads,
+                  out_base=0):
+    """Compare the device output of a random sample of reads with the oracle.  Returns a dict; raises on a mismatch."""
+    n = d_off.numel() - 1
+    g = torch.Generator(device=d_off.device)
+    g.manual_seed(seed)
+    ns = min(n_sample, n)
+    idx = torch.unique(torch.randint(0, n, (ns,), generator=g, device=d_off.device))
+    starts, lens = d_off[idx], d_off[idx + 1] - d_off[idx]
+    hb = gather_ranges(torch, d_bases, starts, lens).cpu().numpy()
+    ho = np.zeros(idx.numel() + 1, dtype=np.uint64)
+    ho[1:] = torch.cumsum(lens, 0).cpu().numpy()
+    ref = oracle.run_batch(hb, ho, omode, threads=threads, want_pos=pos is not None, **okw)
+    ostart = ooff[idx] - out_base
+    ocnt = ooff[idx + 1] - ooff[idx]
+    gv = gather_ranges(torch, val, ostart, ocnt).cpu().numpy().view(np.uint64)
+    mism = 0
+    if not np.array_equal(ocnt.cpu().numpy().astype(np.uint64), np.diff(ref["off"]).astype(np.uint64)):
+        mism += 1
+    elif not np.array_equal(gv, ref["val"]):
+        mism += int(np.count_nonzero(gv != ref["val"]))
+    if pos is not None and mism == 0:
+        gp = gather_ranges(torch, pos, ostart, ocnt).cpu().numpy().view(np.uint32)
+        mism += int(np.count_nonzero(gp != ref["pos"]))
+    if status is not None and not np.array_equal(status[idx].cpu().numpy(), ref["status"]):
+        mism += 1
+    return {"config": name, "reads_checked": int(idx.numel()), "elements_checked": int(len(ref["val"])),
+            "mismatches": mism, "first_window_ties": int(ref["ties"])}
+
+
+def timed(torch, fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
 
 
 # ---------------------------------------------------------------- reference arm (CPU)
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path.  The reference is pure Go and neither a Go
-    toolchain nor its four un-vendored arithmetic modules exist in this image, so this arm times the
-    oracle: the line-by-line C restatement of sketches/sketch.go:205-309 (+ ntHash), one thread per host
-    core over contiguous read shards -- kind "port"."""
+    """The reference's own CPU implementation of the path.  The reference is pure Go and neither a Go toolchain nor
+    its four un-vendored arithmetic modules exist in this image, so this arm times the oracle: the line-by-line C
+    restatement of sketches/sketch.go:205-309 (+ ntHash), one thread per host core over contiguous read shards --
+    kind "port"."""
     if rank != 0:
         return
     import oracle
@@ -158,15 +260,18 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     v = nb * args.steps / dt
-    sample = f"{n} x {READ_LEN} bp uniform ACGT reads per step (seed {SEED}), same k/w; full workload is {args.reads} reads/GPU"
+    sample = (f"{n} x {READ_LEN} bp uniform ACGT reads per step (seed {SEED}), same k/w; the full workload is one batch "
+              f"of {args.reads} reads")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"C3 minimizer k={K} w={W}, {READ_LEN} bp reads, CPU sample", "reads_per_step": n},
         "cpu_baseline": {"value": v, "unit": "bases/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C restatement of the Go algorithm (oracle/), not the Go binary: no Go toolchain "
-                                 "in the image; published Go figure 18.3 Mbases/s/core (k=31,w=15, Ryzen 2700X)"},
+                         "note": "C restatement of the Go algorithm (oracle/), not the Go binary: no Go toolchain in the "
+                                 "image; published Go figure 18.3 Mbases/s/core (k=31,w=15, Ryzen 2700X).  The port "
+                                 "allocates per read (3 malloc + one 150-byte copy) where Go pools its iterators; it "
+                                 "still runs faster per core than the published Go figure"},
         "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -175,9 +280,9 @@ def run_reference(args, rank, world):
 
 # ---------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
-    import ctypes
     import numpy as np
     import torch
+    import oracle  # the checker of the parity gate and the cpu_baseline leg; never on the measured path
     from bio_b200 import _cabi as cabi, synth
 
     dist = None
@@ -189,62 +294,134 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     ctx = cabi.Context(local_rank)
-
-    n = args.reads
-    nb = n * READ_LEN
-    bases, off = synth.device_uniform_reads(n, READ_LEN, SEED + rank, dev)
-    p = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN)
-    cap = int(cabi.lib().b200sk_output_bound(ctypes.byref(p), nb, n, 0))
-    val = torch.empty(cap, dtype=torch.int64, device=dev)
-    pos = torch.empty(cap, dtype=torch.int32, device=dev)
-    ooff = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    status = torch.empty(n, dtype=torch.int32, device=dev)
-    flags = torch.zeros(1, dtype=torch.int32, device=dev)
-
-    rc, n_out = ctx.run_device(p, bases, off, nb, val, pos, ooff, status)  # also sizes the scratch
-    if rc != 0:
-        raise RuntimeError("capacity estimate too small: need %d" % n_out)
-
-    def step():
-        ctx.enqueue_device(p, bases, off, nb, val, pos, ooff, status, flags)
+    L = cabi.lib()
+    cores = max(1, (os.cpu_count() or 1) // world)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum_i64(x):
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    peak, peak_src = measured_peak()
+    parity = []
+
+    # ------------------------------------------------------------ C3: the headline batch, sharded over the ranks
+    bounds = shard_bounds(args.reads, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    n, nb = r1 - r0, (r1 - r0) * READ_LEN
+    bases, off = gen_uniform_shard(torch, r0, r1, READ_LEN, SEED, dev)
+    p = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN)
+    cap = int(L.b200sk_output_bound(ctypes.byref(p), nb, n, 0))
+    val = torch.empty(cap, dtype=torch.int64, device=dev)
+    pos = torch.empty(cap, dtype=torch.int32, device=dev)
+    ooff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc, n_out = ctx.run_device(p, bases, off, nb, val, pos, ooff, status)  # also sizes the scratch
+    if rc != 0:
+        raise RuntimeError("capacity estimate too small: need %d" % n_out)
+
+    # parity gate: a random sample of this rank's reads against the oracle, before anything is timed
+    pr = parity_sample(torch, np, oracle, "C3 minimizer k=21 w=11", oracle.MODE_MINIMIZER, dict(k=K, w=W), bases, off, val,
+                       pos, ooff, status, max(1, args.parity_reads // world), 1000 + rank, cores)
+    for key in ("reads_checked", "elements_checked", "mismatches", "first_window_ties"):
+        pr[key] = allsum_i64(pr[key])
+    parity.append(pr)
+    if pr["mismatches"]:
+        raise RuntimeError("PARITY FAILED on C3: %r" % pr)
+    local_sum = int(val[:n_out].sum().item())  # wraps mod 2^64: a checksum of the value stream
+    total_out = allsum_i64(n_out)
+    checksum = allsum_i64(local_sum) & 0xFFFFFFFFFFFFFFFF
+
+    # device-resident, local outputs: the per-GPU kernel number (what round 1 reported as `value`)
     ctx.timing_enable(True)
-    l0 = ctx.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.kernel_launches() - l0
+    res_ms = timed(torch, lambda: ctx.enqueue_device(p, bases, off, nb, val, pos, ooff, status, flags),
+                   args.steps, max(args.warmup, 3), barrier)
     kern_ms_sum, kern_n = ctx.timing_collect()
     ctx.timing_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
+    kern_ms = kern_ms_sum / max(kern_n, 1)
+    res_ms_max = allmax(res_ms)
     if int(flags.item()) != 0:
         raise RuntimeError("kernel flags %d" % int(flags.item()))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = nb * world / (ms_step * 1e-3)
 
-    # roofline of the dominant (sketching) kernel on this rank
-    peak, peak_src = measured_peak()
-    kern_ms = kern_ms_sum / max(kern_n, 1)
+    # the step: shard -> sketch -> gathered uint64 array on rank 0
+    gather = None
+    sampler = ClockSampler(local_rank)
+    if world == 1:
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.kernel_launches()
+        ms_step = timed(torch, lambda: ctx.enqueue_device(p, bases, off, nb, val, pos, ooff, status, flags),
+                        args.steps, max(args.warmup, 3), barrier)
+        launches = ctx.kernel_launches() - l0
+        clocks = sampler.stop()
+    else:
+        caps = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(caps, torch.tensor([cap], dtype=torch.int64, device=dev))
+        caps = caps.cpu().numpy().astype(np.uint64)
+        seg_base = np.zeros(world, dtype=np.uint64)
+        seg_base[1:] = np.cumsum(caps)[:-1]
+        hbox = [None]
+        if rank == 0:
+            handle, gaddr = ctx.gather_create(int(caps.sum()))
+            hbox = [handle]
+        dist.broadcast_object_list(hbox, src=0)
+        if rank != 0:
+            gaddr = ctx.gather_open(hbox[0])
+        my_seg = gaddr + int(seg_base[rank]) * 8
+        counts_d = torch.zeros(world, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def step():
+            # the sketching kernel's flush stores into rank 0's buffer (peer st.global over NVLink for rank > 0)
+            ctx.enqueue_device_raw(p, bases, off, nb, my_seg, cap, pos, ooff, status, flags)
+            dist.all_gather_into_tensor(counts_d, ooff[n:n + 1])          # 8 bytes per rank over NCCL
+            if rank == 0:
+                ctx.compact_segments(gaddr, seg_base, counts_d.cpu().numpy().astype(np.uint64), stream)
+
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.kernel_launches()
+        ms_step = allmax(timed(torch, step, args.steps, max(args.warmup, 3), barrier))
+        launches = ctx.kernel_launches() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        if int(flags.item()) != 0:
+            raise RuntimeError("kernel flags %d" % int(flags.item()))
+        # the two halves of the step on their own: kernels with peer stores, and the compaction on rank 0
+        peer_ms = allmax(timed(torch, lambda: ctx.enqueue_device_raw(p, bases, off, nb, my_seg, cap, pos, ooff, status, flags),
+                               max(args.steps // 2, 2), 1, barrier))
+        cnts = counts_d.cpu().numpy().astype(np.uint64)
+        nvbytes = int(cnts[1:].sum()) * 8
+        gsum_ok = None
+        if rank == 0:
+            ctx.compact_segments(gaddr, seg_base, cnts, stream)
+            torch.cuda.synchronize()
+            # the gathered array must be the concatenation of the rank arrays: same count, same checksum
+            g = _as_tensor(torch, gaddr, int(cnts.sum()), dev)
+            gsum_ok = bool((int(g.sum().item()) & 0xFFFFFFFFFFFFFFFF) == checksum and int(cnts.sum()) == total_out)
+            del g
+        barrier()
+        gather = {"bytes_over_nvlink": nvbytes, "how": "peer st.global from the sketching kernel's flush into rank 0's "
+                  "CUDA-IPC buffer; counts by NCCL all-gather (8 B/rank); b200sk_compact_segments on rank 0",
+                  "kernels_with_peer_stores_ms": peer_ms, "kernels_local_ms": res_ms_max,
+                  "ingress_GBps": nvbytes / (peer_ms * 1e-3) / 1e9 if peer_ms else None,
+                  "counts_and_compaction_ms": max(ms_step - peer_ms, 0.0), "gathered_checksum_ok": gsum_ok}
+        ctx.gather_close(gaddr, rank == 0)
+    value = args.reads * READ_LEN / (ms_step * 1e-3)
+
+    # roofline of the dominant (sketching) kernel, this rank's shard with local stores
     alg = algorithmic_bytes(n, nb, n_out)
     achieved = alg / (kern_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
@@ -254,37 +431,45 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                 "kernel": "k_sparse_warp<MINIMIZER,W=11>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
                 "bytes_per_base": alg / nb, "peak_source": peak_src,
-                "kernel_share_of_step": kern_ms / ms_step}
+                "kernel_share_of_step": kern_ms / ms_step,
+                "binding_unit": "integer ALU pipe (profiles/, DESIGN.md 5.1), not HBM"}
     if traffic:
         roofline["traffic_source"] = traffic.get("source")
-
-    # optional: NCCL gather of the per-GPU uint64 hash arrays to rank 0 (not part of `value`)
-    gather = None
-    if dist is not None and not args.no_gather:
-        from bio_b200 import shard
-        part = val[: max(n_out // world, 1)]
-        gather = shard.timed_gather(part, dist, dev)
+    resident = {"value": args.reads * READ_LEN / (res_ms_max * 1e-3), "unit": "bases/s", "ms": res_ms_max,
+                "what": "every rank sketches its shard into its own HBM, no gather (max over ranks)"}
 
     # end-to-end through the host entry point
     e2e = None
     if not args.no_e2e:
         del val, pos, ooff, status
         torch.cuda.empty_cache()
-        e2e = run_e2e(args, ctx, cabi, synth, bases, rank, world, dev, dist, torch, np)
-    del bases
+        e2e = run_e2e(args, ctx, cabi, bases, n, rank, world, dev, dist, torch, np, oracle, cores)
+    del bases, off
+    torch.cuda.empty_cache()
+
+    secondary = []
+    if not args.no_secondary:
+        secondary = run_secondary(args, ctx, cabi, synth, oracle, rank, world, dev, dist, torch, np, peak, parity, cores,
+                                  barrier, allmax, allsum_i64)
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"C3: NewMinimizerSketch k={K} w={W} over {n} x {READ_LEN} bp uniform-ACGT reads per GPU",
-                       "reads_per_gpu": n, "read_len": READ_LEN, "k": K, "w": W, "minimizers_per_read": n_out / n,
-                       "parallelism": f"records sharded over {world} GPU(s), no data-path collective",
+            "config": {"workload": f"C3: NewMinimizerSketch k={K} w={W} over ONE batch of {args.reads} x {READ_LEN} bp "
+                                   f"uniform-ACGT reads sharded over {world} GPU(s), uint64 arrays gathered on rank 0",
+                       "reads": args.reads, "reads_per_gpu": n, "read_len": READ_LEN, "k": K, "w": W,
+                       "minimizers_per_read": total_out / args.reads, "value_checksum": checksum,
+                       "parallelism": f"records sharded over {world} GPU(s); gather inside the step",
                        "l2": "inputs (15 GB) and outputs (27 GB) per step far exceed the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "parity": {"all_ok": all(x["mismatches"] == 0 for x in parity), "configs": parity,
+                       "note": "first_window_ties = sampled reads whose first window holds equal hashes (the only place "
+                               "the unpinned sorts.Quicksort tie order could matter); C5/ProteinIterator: WYHASH_UNPINNED"},
+            "per_gpu_resident": resident, "secondary": secondary,
         }
         if gather:
             line["gather"] = gather
@@ -295,10 +480,18 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
+def _as_tensor(torch, addr, n, dev):
+    """int64 view of n elements of raw device memory at addr (the gather buffer is library-owned)."""
+    class _Mem:
+        pass
+    m = _Mem()
+    m.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (addr, False), "version": 2}
+    return torch.as_tensor(m, device=dev)
+
+
+def run_e2e(args, ctx, cabi, d_bases, n_shard, rank, world, dev, dist, torch, np, oracle, cores):
     """Same metric through b200sk_run: inputs in pinned HOST memory, every step copies them to the device,
     sketches, and copies values, positions, offsets and statuses back to pinned host memory."""
-    import ctypes
     from bio_b200 import shard
     # the pinned buffers allocated below land on the NUMA node of this rank's GPU
     prev_affinity, binding = shard.bind_host_to_device(dev.index) if not args.no_bind else (None, "off")
@@ -309,7 +502,7 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
         except Exception:
             avail = 64 << 30
         per_read = READ_LEN + 8 + 23 * 12 * 1.3 + 12
-        n = int(min(args.reads, 0.45 * avail / world / per_read))
+        n = int(min(n_shard, 0.45 * avail / world / per_read))
     nb = n * READ_LEN
     L = cabi.lib()
     hb_ptr = L.b200sk_alloc_pinned(nb + 64)
@@ -324,7 +517,6 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
     torch.cuda.synchronize()
     # Index() values of a 150-bp read fit one byte: ask for uint8 positions (a quarter less D2H traffic)
     p = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN, pos_width=1)
-    res = None
 
     def step():
         return ctx.run(p, hb, ho, copy=False)
@@ -332,6 +524,14 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
     res = step()  # warm-up: allocates the library's device + pinned output buffers
     res = step()
     n_out = res["total"]
+    # the host path's output against the oracle on the first reads of the batch
+    ns = min(n, 20000)
+    ref = oracle.run_batch(hb[:ns * READ_LEN], ho[:ns + 1], oracle.MODE_MINIMIZER, k=K, w=W, threads=cores)
+    m = int(ref["off"][-1])
+    ok = bool(np.array_equal(res["val"][:m], ref["val"]) and np.array_equal(res["pos"][:m], ref["pos"].astype(np.uint8))
+              and np.array_equal(res["off"][:ns + 1], ref["off"]))
+    if not ok:
+        raise RuntimeError("PARITY FAILED on the host path (b200sk_run)")
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -344,16 +544,121 @@ def run_e2e(args, ctx, cabi, synth, d_bases, rank, world, dev, dist, torch, np):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
-    chk = int(res["val"][:1000].sum()) if n_out else 0
-    out = {"value": nb * world * args.e2e_steps / dt, "unit": "bases/s",
+    tot = torch.tensor([nb], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    out = {"value": int(tot.item()) * args.e2e_steps / dt, "unit": "bases/s",
            "h2d_bytes_per_step": nb + (n + 1) * 8,
            "d2h_bytes_per_step": n_out * 9 + (n + 1) * 8 + n * 4, "pos_width": 1,
            "reads_per_gpu_per_step": n, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-           "api": "b200sk_run (host pointers, pinned)", "checksum_first_1000": chk, "host_binding": binding}
+           "api": "b200sk_run (host pointers, pinned)", "oracle_check_first_reads": ns, "host_binding": binding}
     L.b200sk_free_pinned(hb_ptr)
     L.b200sk_free_pinned(ho_ptr)
     if prev_affinity is not None:
         shard.restore_host_binding(prev_affinity)
+    return out
+
+
+def run_secondary(args, ctx, cabi, synth, oracle, rank, world, dev, dist, torch, np, peak, parity, cores, barrier, allmax,
+                  allsum_i64):
+    """BASELINE.json configs 2, 4 and 5, each sharded over the ranks, each with a sampled oracle check first."""
+    L = cabi.lib()
+    out = []
+    steps = max(3, args.steps // 2)
+
+    def one(name, label, p, omode, okw, bases, off, nb, n, frames=None, pos_bytes=4, note=None):
+        exact = 1 if p.mode in (cabi.MODE_KMER, cabi.MODE_NTHASH, cabi.MODE_PROTEIN, cabi.MODE_SIMHASH) else 0
+        cap = int(L.b200sk_output_bound(ctypes.byref(p), nb, n, exact))
+        val = torch.empty(cap, dtype=torch.int64, device=dev)
+        pos = torch.empty(cap, dtype=torch.int32, device=dev) if p.want_pos else None
+        ooff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        st = torch.empty(n, dtype=torch.int32, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        plist = [p]
+        if frames:
+            plist = []
+            for fr in frames:
+                q = cabi.Params.from_buffer_copy(p)
+                q.frame = fr
+                plist.append(q)
+        totals, mis, checked, ties = 0, 0, 0, 0
+        for q in plist:  # parity first
+            rc, tot = ctx.run_device(q, bases, off, nb, val, pos, ooff, st)
+            if rc != 0:
+                raise RuntimeError("%s: capacity" % name)
+            totals += tot
+            kw = dict(okw)
+            if frames:
+                kw["frame"] = int(q.frame)
+            pr = parity_sample(torch, np, oracle, label, omode, kw, bases, off, val, pos, ooff, st,
+                               max(1, args.parity_reads // world // len(plist)), 7 + rank, cores)
+            mis += pr["mismatches"]; checked += pr["reads_checked"]; ties += pr["first_window_ties"]
+        pr = {"config": label, "reads_checked": allsum_i64(checked), "mismatches": allsum_i64(mis),
+              "first_window_ties": allsum_i64(ties)}
+        if note:
+            pr["note"] = note
+        parity.append(pr)
+        if pr["mismatches"]:
+            raise RuntimeError("PARITY FAILED on %s: %r" % (name, pr))
+
+        def step():
+            for q in plist:
+                ctx.enqueue_device(q, bases, off, nb, val, pos, ooff, st, flags)
+
+        ctx.timing_enable(True)
+        ms = allmax(timed(torch, step, steps, 3, barrier))
+        ksum, kn = ctx.timing_collect()
+        ctx.timing_enable(False)
+        kern_ms = allmax(ksum / max(kn, 1) * len(plist))
+        tb, tr, to = allsum_i64(nb), allsum_i64(n), allsum_i64(totals)
+        alg = tb + 8 * tr + (8 + (pos_bytes if p.want_pos else 0)) * to + 8 * tr
+        out.append({"config": name, "value": tb / (ms * 1e-3), "unit": "bases/s", "ms_per_step": ms, "reads": tr,
+                    "bases": tb, "elements": to, "launches_per_step": len(plist),
+                    "roofline": {"bound": "hbm", "achieved": alg / world / (kern_ms * 1e-3) / 1e9, "peak": peak,
+                                 "unit": "GB/s per GPU", "frac": alg / world / (kern_ms * 1e-3) / 1e9 / peak,
+                                 "kernel_ms": kern_ms, "algorithmic_bytes": alg, "bytes_per_base": alg / tb}})
+        del val, pos, ooff, st
+
+    # C2: canonical ntHash k=21, 10 M x 150 bp (values only: Index() of a dense mode is the running position)
+    b = shard_bounds(args.c2_reads, world)
+    n = b[rank + 1] - b[rank]
+    bases, off = gen_uniform_shard(torch, b[rank], b[rank + 1], READ_LEN, 42, dev)
+    one("C2 ntHash k=21 canonical, %d x 150 bp" % args.c2_reads, "C2 ntHash k=21",
+        cabi.make_params(cabi.MODE_NTHASH, K, max_read_len=READ_LEN, want_pos=False), oracle.MODE_NTHASH, dict(k=K),
+        bases, off, n * READ_LEN, n)
+    del bases, off
+    # C5: ProteinIterator k=11 over the six frames of 150-bp reads (one unit = six launches over the same reads)
+    b = shard_bounds(args.c5_reads, world)
+    n = b[rank + 1] - b[rank]
+    bases, off = gen_uniform_shard(torch, b[rank], b[rank + 1], READ_LEN, 45, dev)
+    one("C5 ProteinIterator k=11, six frames, %d x 150 bp" % args.c5_reads, "C5 protein k=11 x 6 frames",
+        cabi.make_params(cabi.MODE_PROTEIN, 11, max_read_len=READ_LEN, want_pos=False, frame=1), oracle.MODE_PROTEIN,
+        dict(k=11), bases, off, n * READ_LEN, n, frames=(1, 2, 3, -1, -2, -3),
+        note="WYHASH_UNPINNED: GPU == oracle bit-exact; the oracle's wyhash is a restatement no reference vector pins")
+    del bases, off
+    torch.cuda.empty_cache()
+    # C4: closed syncmers k=21 s=11 over ONT-like reads (lognormal lengths, mean 10 kb), sharded by cumulative bases
+    lens = synth.ont_like_lengths(args.c4_reads, 44)
+    ro = np.zeros(args.c4_reads + 1, dtype=np.uint64)
+    np.cumsum(lens, out=ro[1:])
+    cut = cabi.shard_by_bases(ro, world)
+    a0, a1 = int(cut[rank]), int(cut[rank + 1])
+    n = a1 - a0
+    nb = int(ro[a1] - ro[a0])
+    g = torch.Generator(device=dev)
+    g.manual_seed(4400 + rank)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    bases = torch.zeros(nb + 64, dtype=torch.uint8, device=dev)
+    stepb = 1 << 28
+    for s0 in range(0, nb, stepb):
+        e0 = min(nb, s0 + stepb)
+        bases[s0:e0] = lut[torch.randint(0, 4, (e0 - s0,), generator=g, device=dev, dtype=torch.int64)]
+    off = torch.from_numpy((ro[a0:a1 + 1] - ro[a0]).astype(np.int64)).to(dev)
+    one("C4 closed syncmer k=21 s=11, %d ONT-like reads (mean 10 kb)" % args.c4_reads, "C4 syncmer k=21 s=11 ONT",
+        cabi.make_params(cabi.MODE_SYNCMER, K, s=S, max_read_len=int(lens.max())), oracle.MODE_SYNCMER, dict(k=K, s=S),
+        bases, off, nb, n)
+    del bases, off
+    torch.cuda.empty_cache()
     return out
 
 
@@ -374,7 +679,8 @@ def cpu_baseline(args):
     dt = time.perf_counter() - t0
     return {"value": n * READ_LEN * reps / dt, "unit": "bases/s", "cores": cores, "kind": "port",
             "sample": f"{reps} x ({n} x {READ_LEN} bp uniform ACGT reads), oracle NextMinimizer restatement, "
-                      f"{cores} threads over contiguous read shards"}
+                      f"{cores} threads over contiguous read shards",
+            "note": "C restatement of the Go loops (no Go toolchain here); allocates per read where Go pools"}
 
 
 def main():

@@ -46,7 +46,11 @@ EXPORTS = (
     "b200sk_fastx_parse_device", "b200sk_run_fastx", "b200sk_copy_to_host",
     "b200sk_fxstream_open", "b200sk_fxstream_next", "b200sk_fxstream_rewind", "b200sk_fxstream_close",
     "b200sk_fxstream_kernel_launches", "b200sk_fxstream_last_error",
+    "b200sk_gather_create", "b200sk_gather_open", "b200sk_gather_close", "b200sk_compact_segments",
+    "b200sk_shard_by_bases", "b200sk_group_create", "b200sk_group_destroy", "b200sk_group_size", "b200sk_group_run",
+    "b200sk_group_last_error", "b200sk_group_kernel_launches",
 )
+IPC_HANDLE_BYTES = 64
 FXSTREAM_END = 1
 
 FASTX_FASTA, FASTX_FASTQ = 1, 2
@@ -165,6 +169,30 @@ def lib():
     L.b200sk_fxstream_kernel_launches.argtypes = [vp]
     L.b200sk_fxstream_last_error.restype = C.c_char_p
     L.b200sk_fxstream_last_error.argtypes = [vp]
+    L.b200sk_gather_create.restype = C.c_int
+    L.b200sk_gather_create.argtypes = [vp, C.c_uint64, vp, C.POINTER(C.c_void_p)]
+    L.b200sk_gather_open.restype = C.c_int
+    L.b200sk_gather_open.argtypes = [vp, vp, C.POINTER(C.c_void_p)]
+    L.b200sk_gather_close.restype = C.c_int
+    L.b200sk_gather_close.argtypes = [vp, vp, C.c_int]
+    L.b200sk_compact_segments.restype = C.c_int
+    L.b200sk_compact_segments.argtypes = [vp, vp, u64p, u64p, C.c_int, vp]
+    L.b200sk_shard_by_bases.restype = None
+    L.b200sk_shard_by_bases.argtypes = [u64p, C.c_uint64, C.c_int, u64p]
+    L.b200sk_group_create.restype = C.c_int
+    L.b200sk_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+    L.b200sk_group_destroy.restype = None
+    L.b200sk_group_destroy.argtypes = [vp]
+    L.b200sk_group_size.restype = C.c_int
+    L.b200sk_group_size.argtypes = [vp]
+    L.b200sk_group_run.restype = C.c_int
+    L.b200sk_group_run.argtypes = [vp, PP, u8p, u64p, C.c_uint64,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.b200sk_group_last_error.restype = C.c_char_p
+    L.b200sk_group_last_error.argtypes = [vp]
+    L.b200sk_group_kernel_launches.restype = C.c_uint64
+    L.b200sk_group_kernel_launches.argtypes = [vp]
     _lib = L
     return L
 
@@ -282,6 +310,53 @@ class Context:
         if rc != 0:
             self._raise(rc)
 
+    # ---- multi-GPU gather buffer (CUDA IPC): raw device addresses, the caller wraps them as it likes
+    def gather_create(self, capacity_elems):
+        """Root: allocate the gather buffer.  Returns (64-byte handle, device address)."""
+        h = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        d = C.c_void_p()
+        rc = lib().b200sk_gather_create(self._h, int(capacity_elems), h, C.byref(d))
+        if rc != 0:
+            self._raise(rc)
+        return bytes(h), int(d.value)
+
+    def gather_open(self, handle):
+        """Other ranks: map the root's buffer into this process.  Returns the device address."""
+        h = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        d = C.c_void_p()
+        rc = lib().b200sk_gather_open(self._h, h, C.byref(d))
+        if rc != 0:
+            self._raise(rc)
+        return int(d.value)
+
+    def gather_close(self, addr, is_owner):
+        rc = lib().b200sk_gather_close(self._h, C.c_void_p(addr), int(bool(is_owner)))
+        if rc != 0:
+            self._raise(rc)
+
+    def compact_segments(self, addr, seg_base, seg_count, stream=None):
+        import numpy as np
+        b = np.ascontiguousarray(seg_base, dtype=np.uint64)
+        c = np.ascontiguousarray(seg_count, dtype=np.uint64)
+        rc = lib().b200sk_compact_segments(self._h, C.c_void_p(addr), b.ctypes.data, c.ctypes.data, len(b),
+                                           C.c_void_p(stream or 0))
+        if rc != 0:
+            self._raise(rc)
+
+    def enqueue_device_raw(self, params, d_bases, d_off, n_bases, out_val_addr, capacity, out_pos, out_off, status,
+                           flags, stream=None):
+        """enqueue_device with out_val given as a raw device address (a peer-mapped segment of the gather buffer)."""
+        import torch
+        n = d_off.numel() - 1
+        st = torch.cuda.current_stream(d_bases.device).cuda_stream if stream is None else stream
+        rc = lib().b200sk_enqueue_device(
+            self._h, C.byref(params), d_bases.data_ptr(), d_off.data_ptr(), n, n_bases, C.c_void_p(out_val_addr),
+            out_pos.data_ptr() if out_pos is not None else None, out_off.data_ptr(),
+            status.data_ptr() if status is not None else None, int(capacity), st,
+            flags.data_ptr() if flags is not None else None)
+        if rc != 0:
+            self._raise(rc)
+
     # ---- record feeder (seqio/fastx.Reader as a batch operation)
     def fastx_parse_device(self, d_text, n_bytes=None, fmt=0, final=True, stream=None):
         """Split a chunk of FASTA/FASTQ text resident in HBM (torch uint8 CUDA tensor, 16-byte aligned, padded
@@ -344,6 +419,68 @@ class Context:
         pdt = {1: np.uint8, 2: np.uint16}.get(int(params.pos_width), np.uint32)
         return dict(val=view(ov, t, np.uint64), pos=view(op, t, pdt) if params.want_pos else None,
                     off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t, info=info)
+
+
+def shard_by_bases(read_off, n_shards):
+    """cut[n_shards + 1]: shard d owns reads [cut[d], cut[d+1]), balanced by cumulative bases (host logic, no device)."""
+    import numpy as np
+    ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+    cut = np.zeros(n_shards + 1, dtype=np.uint64)
+    lib().b200sk_shard_by_bases(ro.ctypes.data, len(ro) - 1, n_shards, cut.ctypes.data)
+    return cut
+
+
+class Group:
+    """b200sk_group: one process driving several devices (a context, stream and worker thread per device)."""
+
+    def __init__(self, devices):
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = lib().b200sk_group_create(C.byref(h), arr, len(devices))
+        if rc != 0:
+            raise SketchError(rc)
+        self._h = h
+
+    def size(self):
+        return int(lib().b200sk_group_size(self._h))
+
+    def kernel_launches(self):
+        return int(lib().b200sk_group_kernel_launches(self._h))
+
+    def run(self, params, bases, read_off, copy=True):
+        import numpy as np
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n = len(read_off) - 1
+        ov, op, oo, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        total = C.c_uint64(0)
+        rc = lib().b200sk_group_run(self._h, C.byref(params), bases.ctypes.data, read_off.ctypes.data, n,
+                                    C.byref(ov), C.byref(op), C.byref(oo), C.byref(st), C.byref(total))
+        if rc != 0:
+            raise SketchError(rc, lib().b200sk_group_last_error(self._h).decode() if rc == ERR_CUDA else "")
+        t = int(total.value)
+
+        def view(ptr, count, dt):
+            if not ptr.value or count == 0:
+                return np.zeros(0, dtype=dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dt).itemsize,))
+            a = a.view(dt)
+            return a.copy() if copy else a
+
+        pdt = {1: np.uint8, 2: np.uint16}.get(int(params.pos_width), np.uint32)
+        return dict(val=view(ov, t, np.uint64), pos=view(op, t, pdt) if params.want_pos else None,
+                    off=view(oo, n + 1, np.uint64), status=view(st, n, np.int32), total=t)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200sk_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class FastxStream:

@@ -86,6 +86,7 @@ struct Plan {
     int T = 128;
     bool chunked = false;
     bool reg = false;   // window state in registers (b200sk_sparse_reg.cu)
+    bool keyed = false; // ... and the window minimum on 32-bit keys (minimizers, w <= 16)
     bool dense = false; // b200sk_dense.cu
     int ctas_per_sm = 1;
     uint32_t C = 0, span_max = 0, lcap = 0;
@@ -102,6 +103,17 @@ const uint32_t kSmemLimit = 227 * 1024;
 
 inline uint32_t up16(uint32_t v) { return (v + 15u) & ~15u; }
 
+// testing knob: B200SK_WALKER=keyed (or rewalk / norewalk, its two diagnostic variants) runs minimizer batches with
+// w in {3, 5, 11, 15} through the keyed window minimum (b200sk_sparse_reg.cu) instead of the 64-bit register window.
+// Both are bit-exact; the keyed walk is not faster and stays off by default.
+bool keyed_walk_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("B200SK_WALKER");
+        return e && (strcmp(e, "keyed") == 0 || strcmp(e, "rewalk") == 0 || strcmp(e, "norewalk") == 0);
+    }();
+    return on;
+}
+
 } // namespace
 
 struct b200sk_ctx {
@@ -109,7 +121,7 @@ struct b200sk_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;  // compute stream of the host path
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    DevBuf meta;       // [0] ticket, [1] flags, [2] n_items, [3] max_len, [4] scan ticket  (u64 each)
+    DevBuf meta;       // [0] ticket, [1] flags, [2] n_items, [3] max_len, [4] scan ticket, [5] exact re-walks  (u64 each)
     DevBuf tile_state; // main kernel look-back words
     DevBuf scan_state; // item scan look-back words
     DevBuf item_first, tile_read;
@@ -229,6 +241,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         if (pl.lcap < 1) pl.lcap = 1;
     }
     pl.reg = sparse && sparse_reg_supported(mode, k, w, s);
+    pl.keyed = pl.reg && mode == B200SK_MODE_MINIMIZER && (w == 3 || w == 5 || w == 11 || w == 15) && keyed_walk_enabled();
     if (pl.reg) {
         // one tile per warp.  tables 4 KB, then per warp: mbarrier 16 B, tile, k-mer ring (syncmer),
         // lists of (lcap+1) slots x 32 lanes x (8 B value + 1 B position delta).
@@ -242,9 +255,14 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
             c.sm_ring = 16 + c.sm_tile_bytes;
             c.sm_listv = c.sm_ring + (uint32_t)d * 256u;
             c.sm_listp = c.sm_listv + (c.lcap + 1) * 256u;
-            c.sm_ring_bytes = up16(c.sm_listp + (c.lcap + 1) * 32u); // per-warp stride
+            const uint32_t pos_bytes = (c.lcap + 1) * 32u; // one position byte per slot and lane
+            c.sm_ring_bytes = up16(c.sm_listp + pos_bytes); // per-warp stride
             int nw = (int)((232448u - 1024u - c.sm_tile) / c.sm_ring_bytes);
             if (nw > 16) nw = 16;
+            {
+                static const int cap_nw = [] { const char *e = getenv("B200SK_MAX_WARPS"); return e ? atoi(e) : 0; }();
+                if (cap_nw > 0 && nw > cap_nw) nw = cap_nw; // testing knob: occupancy sweep
+            }
             if (nw < 1) continue;
             c.T = nw * 32;
             c.ctas_per_sm = 1;
@@ -410,6 +428,21 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         }
     }
     a.C = pl.C; a.span_max = pl.span_max; a.lcap = pl.lcap;
+    a.keyed = pl.keyed ? 1u : 0u;
+    if (pl.keyed) {
+        static const bool force_rewalk = [] { const char *e = getenv("B200SK_WALKER"); return e && strcmp(e, "rewalk") == 0; }();
+        if (force_rewalk) a.keyed |= 2u; // testing knob: every item also takes the exact re-walk
+        static const bool no_rewalk = [] { const char *e = getenv("B200SK_WALKER"); return e && strcmp(e, "norewalk") == 0; }();
+        if (no_rewalk) a.keyed |= 4u; // timing experiment only: WRONG output for the items the keyed walk hands back
+    }
+    {
+        static const uint32_t spin = [] { const char *e = getenv("B200SK_SPIN_NS"); return e ? (uint32_t)atoi(e) : 0u; }();
+        a.spin_ns = spin;
+        static const bool unordered = [] { const char *e = getenv("B200SK_UNORDERED"); return e && atoi(e) != 0; }();
+        a.unordered = unordered ? meta + 6 : nullptr;
+    }
+    a.key_mask = 0xffffffc0u;
+    a.rewalks = meta + 5;
     a.sm_tile = pl.sm_tile; a.sm_tile_bytes = pl.sm_tile_bytes; a.sm_ring = pl.sm_ring;
     a.sm_ring_bytes = pl.sm_ring_bytes; a.sm_listv = pl.sm_listv; a.sm_listp = pl.sm_listp;
     a.sm_total = pl.sm_total;

@@ -139,7 +139,7 @@ __device__ __forceinline__ void lookback_publish(uint64_t *state, uint64_t tile,
     if ((threadIdx.x & 31u) == 0)
         st_state(state + tile, ((tile == 0 ? B200SK_FLAG_INC : B200SK_FLAG_AGG) << 62) | total);
 }
-__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t tile, uint64_t total) {
+__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t tile, uint64_t total, uint32_t spin_ns = 0) {
     const unsigned lane = threadIdx.x & 31u;
     if (tile == 0) return 0;
     uint64_t excl = 0;
@@ -147,9 +147,11 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t t
     while (true) {
         uint64_t v = (B200SK_FLAG_INC << 62); // lanes before tile 0 read as "inclusive 0"
         if (idx >= 0) {
-            do {
+            v = ld_state(state + idx);
+            while ((v >> 62) == B200SK_FLAG_EMPTY) {
+                if (spin_ns) __nanosleep(spin_ns);
                 v = ld_state(state + idx);
-            } while ((v >> 62) == B200SK_FLAG_EMPTY);
+            }
         }
         const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
         uint64_t contrib = v & B200SK_VAL_MASK;

@@ -285,7 +285,11 @@ __global__ void __launch_bounds__(256) k_fq_scan(const uint8_t *__restrict__ t, 
             const uint32_t qlen = line_len(t, q, e);
             // header '@'; a NON-EMPTY line starting with '+' (reader.go:399); equal lengths (:415)
             const bool ok = t[h] == '@' && p + 1 < q && t[p] == '+' && len == qlen;
-            if (!ok) atomicMin(meta + M_BADREC, (unsigned long long)r);
+            if (!ok) {
+                atomicMin(meta + M_BADREC, (unsigned long long)r);
+                len = 0; // a broken record copies nothing: only records with len == qlen count against the
+                         // n_bytes / 2 the base buffer holds (the call fails with BAD_FASTQ anyway)
+            }
             rec_off[r] = h;
             qual_off[r] = q;
         }

@@ -44,6 +44,11 @@ struct KArgs {
         g.protein_input = alphabet == 5; g.ill = ill;
         return g;
     }
+    unsigned long long *rewalks; // keyed walk: items handed to the exact walk are counted here (may be null)
+    uint32_t keyed;    // minimizers, W <= 16: window minimum on 32-bit keys (b200sk_sparse_reg.cu)
+    uint32_t key_mask; // 0xffffffc0, as a run-time value (see make_key)
+    uint32_t spin_ns;  // look-back poll interval (0 = busy poll)
+    unsigned long long *unordered; // timing experiment: allocate output ranges in completion order (null = ordered)
     uint32_t C;        // positions per chunk
     uint32_t span_max; // max bases one item touches
     uint32_t lcap;     // staged outputs per item (sparse modes)

@@ -368,6 +368,179 @@ __device__ __forceinline__ void minimizer_item_reg(const uint8_t *sm, uint32_t s
 #undef B200SK_LOAD_BLOCK
 }
 
+// ------------------------------------------------------------------ keyed window minimum (W <= 16)
+// The same walk with the window minimum kept on 32-bit KEYS instead of (64-bit value, position) pairs:
+//     key = (top 26 bits of the canonical hash) << 6 | frame position,
+// so a leftmost minimum is ONE unsigned min (VIMNMX / VIMNMX3 / VIADDMNMX) instead of a 64-bit compare
+// and three selects.  Truncating the hash is made exact by detection, not by luck: every min the window
+// logic takes also feeds "later key - earlier key" into an accumulator (acc = min(acc, difference), fused
+// into one VIADDMNMX with a negated register operand); two keys whose 26 hash bits agree differ by their
+// positions only, i.e. by 1..63, and no other pair that can decide a window gives a difference that small
+// unless the hashes are that close -- acc <= 63 at the end of the item means "some comparison was decided by
+// position bits": the walk returns false and the caller walks the item again with the exact 64-bit window
+// (minimizer_item_reg).  On random reads that happens for ~2e-5 of the reads.
+//
+// The emitted VALUES never travel through the mins: the canonical hashes of the last W elements stay in W
+// 64-bit registers (pv), the window logic only marks the frame position of every window minimum in a bit
+// mask, and an element is written out when it leaves the window (W-1 steps after it was hashed) if its bit
+// is set -- by then its register index is a compile-time constant.  Positions are not staged at all: the
+// mask word of every block goes to shared memory and the flush turns set bits back into Index() values.
+struct KeySink {
+    uint32_t ov;    // shared-window address of this lane's next value slot (slot stride 256 B)
+    uint32_t ovlim; // address of the scratch slot behind the last real one: ov sticks there on overflow
+    uint32_t cw;    // position byte of the slot at ov lives at (ov >> 3) + cw  ([slot][lane] bytes, slot stride 32 B)
+    uint32_t tcnt;  // elements written out so far (counted per block from the mask, so it survives an overflow)
+    // pos: stream index of the element (its Index() is q0 + pos), < 256
+    __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t pos) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t.reg .u32 t, a;\n\tsetp.ne.u32 q, %1, 0;\n\t@q st.shared.u64 [%0], %3;\n\t"
+            "shr.u32 a, %0, 3;\n\tadd.u32 a, a, %4;\n\t@q st.shared.u8 [a], %5;\n\t"
+            "selp.u32 t, 256, 0, q;\n\tadd.u32 t, %0, t;\n\tmin.u32 %0, t, %2;\n\t}"
+            : "+r"(ov)
+            : "r"(pred), "r"(ovlim), "l"(v), "r"(cw), "r"(pos));
+    }
+    __device__ __forceinline__ void block_done(uint32_t bits) { tcnt += __popc(bits); }
+};
+__device__ __forceinline__ uint32_t key_sub_min(uint32_t acc, uint32_t later, uint32_t earlier) { // min(acc, later - earlier)
+    uint32_t d;
+    asm("{\n\t.reg .u32 t;\n\tsub.u32 t, %1, %2;\n\tmin.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(later), "r"(earlier), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ uint32_t bit_of_key(uint32_t key) { // 1 << (key & 31)
+    uint32_t b;
+    asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(0u), "r"(1u), "r"(key));
+    return b;
+}
+// key = (hi & kmask) | pos in ONE LOP3: kmask (0xffffffc0) comes in as a run-time value -- with an immediate mask
+// ptxas needs two instructions, and it would also re-derive "key - W" as a second OR instead of folding the
+// subtraction into the suffix minimum (VIADDMNMX)
+__device__ __forceinline__ uint32_t make_key(uint32_t hi, uint32_t kmask, uint32_t pos) {
+    uint32_t k;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k) : "r"(hi), "r"(kmask), "r"(pos));
+    return k;
+}
+
+// returns false when a comparison was (or may have been) decided by the position bits: walk again exactly
+template <int W, bool FAST>
+__device__ __forceinline__ bool minimizer_item_key(const uint8_t *sm, uint32_t sb, uint32_t nstep, int k,
+                                                   uint32_t tabIn, uint32_t tabOut, uint32_t ft, uint32_t kmask,
+                                                   KeySink &sink) {
+    static_assert(W >= 2 && W <= 16, "frame positions 0..2W-1 must fit the 32-bit mask");
+    Roll h;
+    h.f = 0; h.r = 0;
+    if (FAST) fast_fold(sm, ft, sb, k - 1, h.f, h.r);
+    else
+        for (int j = 0; j < k - 1; j++) h.fold(B200SK_LD128(tabIn, sb + j));
+    uint64_t pv[W]; // canonical hash of the newest W elements, slot = element index within its block
+    uint32_t kk[W] = {}; // [J]: key of element J of the current block once hashed; before that the suffix minimum
+                    // (already in this frame's coordinates) of the previous block from element J on
+    uint32_t pk = 0, mask = 0, acc = 0xffffffffu;
+    uint32_t fpos = 0u - (uint32_t)W;    // stream index of frame position 0
+    uint32_t pin = sb + (uint32_t)k - 1; // incoming code of step 0
+    uint32_t pout = sb - 1;              // outgoing code of step j is pout + j (step 0 has none)
+    CodeWords<FAST ? 1 : W> cin, cout;
+    PairWords<FAST ? W : 1> pw;
+#define B200SK_LOAD_BLOCK()                                                \
+    if (FAST) pw.load(sm, pin, pout);                                      \
+    else { cin.load(sm, pin); cout.load(sm, pout); }
+#define B200SK_ROLL(J)                                                     \
+    if (FAST) {                                                            \
+        const uint32_t o = pw.off(J);                                      \
+        h.f = rol1(h.f) ^ lds_u64(sm, ft + FT_X + o);                      \
+        h.r = ror1(h.r) ^ lds_u64(sm, ft + FT_Y + o);                      \
+    } else h.roll(B200SK_TAB(tabIn, cin.code(J)), B200SK_TAB(tabOut, cout.code(J)));
+    // element J of the current block (frame position W + J).  Not FIRST: the window [J+1, W+J] closes here.
+#define B200SK_KEY_STEP(J, FIRST)                                                                     \
+    {                                                                                                 \
+        const uint64_t c = h.canonical();                                                             \
+        const uint32_t key = make_key((uint32_t)(c >> 32), kmask, (uint32_t)(W + (J)));               \
+        if ((J) == 0) pk = key;                                                                       \
+        else { acc = key_sub_min(acc, key, pk); pk = min(pk, key); }                                  \
+        if (!(FIRST) || (J) == W - 1) {                                                               \
+            uint32_t wk = pk;                                                                         \
+            if (!(FIRST) && (J) != W - 1) { acc = key_sub_min(acc, pk, kk[(J) + 1]); wk = min(pk, kk[(J) + 1]); } \
+            mask |= bit_of_key(wk);                                                                   \
+        }                                                                                             \
+        kk[J] = key;                                                                                  \
+        pv[J] = c;                                                                                    \
+        /* the leftmost element of this window, frame position J+1, can never be a minimum again */     \
+        if (!(FIRST) || (J) == W - 1) sink.emit_if(mask & (2u << (J)), pv[((J) + 1) % W], fpos + (uint32_t)((J) + 1)); \
+    }
+    // after element W-1: the block's keys become suffix minima in the next frame's coordinates (-W)
+#define B200SK_KEY_CLOSE()                                                                            \
+    {                                                                                                 \
+        kk[W - 1] -= (uint32_t)W;                                                                     \
+        _Pragma("unroll") for (int jj = W - 2; jj >= 1; jj--) {                                       \
+            const uint32_t t = kk[jj + 1] - kk[jj]; /* + W: kk[jj] is still in the old frame */         \
+            acc = min(acc, t + (uint32_t)W);                                                          \
+            kk[jj] = min(kk[jj] - (uint32_t)W, kk[jj + 1]);                                           \
+        }                                                                                             \
+        sink.block_done(mask & (((1u << W) - 1u) << 1)); /* frame positions 1..W: written out in this block */ \
+        mask >>= W;                                                                                   \
+        fpos += (uint32_t)W;                                                                          \
+    }
+    B200SK_LOAD_BLOCK()
+    if (FAST) { // the first k-mer has no outgoing base
+        const uint32_t o = pw.off(0) & 0x18u;
+        h.f = rol1(h.f) ^ lds_u64(sm, ft + FT_F1X + o);
+        h.r = ror1(h.r) ^ lds_u64(sm, ft + FT_F1Y + o);
+    } else h.fold(B200SK_TAB(tabIn, cin.code(0)));
+    B200SK_KEY_STEP(0, true)
+#pragma unroll
+    for (int j = 1; j < W; j++) {
+        B200SK_ROLL(j)
+        B200SK_KEY_STEP(j, true)
+    }
+    B200SK_KEY_CLOSE()
+    pin += W; pout += W;
+    uint32_t u0 = W;
+    while (u0 + W <= nstep) { // full blocks
+        B200SK_LOAD_BLOCK()
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            B200SK_ROLL(j)
+            B200SK_KEY_STEP(j, false)
+        }
+        B200SK_KEY_CLOSE()
+        pin += W; pout += W;
+        u0 += W;
+    }
+    const uint32_t rem = nstep - u0; // tail: fewer than W elements left
+    B200SK_LOAD_BLOCK()
+#pragma unroll
+    for (int j = 0; j < W - 1; j++) {
+        if ((uint32_t)j >= rem) break;
+        B200SK_ROLL(j)
+        B200SK_KEY_STEP(j, false)
+    }
+    // drain: the last window was [rem, W+rem-1]; positions rem+1 .. W+rem-1 are still inside it
+#pragma unroll
+    for (int q = 1; q <= 2 * W - 2; q++)
+        if ((uint32_t)q > rem && (uint32_t)q < (uint32_t)W + rem) sink.emit_if(mask & (1u << q), pv[q % W], fpos + (uint32_t)q);
+    sink.block_done(mask & ~1u);
+#undef B200SK_KEY_CLOSE
+#undef B200SK_KEY_STEP
+#undef B200SK_ROLL
+#undef B200SK_LOAD_BLOCK
+    return acc > 63u;
+}
+
+// The exact walk (minimizer_item_reg) staged in the keyed format (values + absolute position bytes), for the items
+// the keyed walk hands back.
+struct PosListSink {
+    uint8_t *sm;
+    uint32_t ov0, op0, cap, cnt, sidx; // sidx: stream index of the last element + 1
+    __device__ __forceinline__ void emit_if(uint32_t pred, uint64_t v, uint32_t delta) {
+        if (pred) {
+            sidx += delta;
+            const uint32_t slot = min(cnt, cap);
+            *reinterpret_cast<uint64_t *>(sm + ov0 + slot * 256u) = v;
+            sm[op0 + slot * 32u] = (uint8_t)(sidx - 1u);
+            cnt++;
+        }
+    }
+};
+
 // NextSyncmer (sketch.go:312-477, bounded closed syncmers, s < k) over one item.  W = 2(k-s): the window of
 // s-mer hashes.  For the window starting at idx the leftmost minimum s-mer m anchors k-mer b = m if
 // m - idx < k-s, else m - (k-s) (sketch.go:414-420); a k-mer is emitted when b changes and b <= end.
@@ -536,7 +709,9 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
 // copy loop with no block-wide barrier, so warps drift freely and cover each other's latencies.
 // Shared memory: tables at 0; warp w owns [sm_tile + w*stride, +stride):
 //   +0 mbarrier, +16 tile bytes, +sm_ring k-mer ring (syncmer), +sm_listv values, +sm_listp position deltas.
-template <int MODE, int W>
+// KEYED (minimizers, W <= 16): the keyed walk above with the exact walk behind it; the lists then hold values only
+// and the position bytes are absolute stream indices instead of deltas.
+template <int MODE, int W, bool KEYED>
 __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
@@ -648,7 +823,25 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         const bool run = it.valid && it.nstep && span_ok;
         const int32_t lim0 = (int32_t)(it.end - it.q0);
         const uint32_t halo = it.q0 != it.p0 ? 1u : 0u;
-        if (run) {
+        if constexpr (KEYED) {
+            if (run) {
+                KeySink ks;
+                ks.ov = sink.av; ks.ovlim = sink.av + a.lcap * 256u;
+                ks.cw = sink.ap - (sink.av >> 3); ks.tcnt = 0;
+                const bool exact = fast ? minimizer_item_key<W, true>(smem, sb, it.nstep, a.k, 0u, 1024u, FT, a.key_mask, ks)
+                                        : minimizer_item_key<W, false>(smem, sb, it.nstep, a.k, 0u, 1024u, FT, a.key_mask, ks);
+                sink.cnt = ks.tcnt;
+                if ((!exact && !(a.keyed & 4u)) || (a.keyed & 2u)) { // some window was decided by position bits: the exact 64-bit walk, same staging
+                                                  // (keyed & 2: testing knob, every item takes this path)
+                    PosListSink ps;
+                    ps.sm = smem; ps.ov0 = sink.av - smem_base; ps.op0 = sink.ap - smem_base; ps.cap = a.lcap; ps.cnt = 0; ps.sidx = 0;
+                    if (fast) minimizer_item_reg<W, true>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, ps);
+                    else minimizer_item_reg<W, false>(smem, sb, it.nstep, a.k, (uint32_t)a.w, 0u, 1024u, FT, ps);
+                    sink.cnt = ps.cnt;
+                    if (a.rewalks) atomicAdd(a.rewalks, 1ULL);
+                }
+            }
+        } else if (run) {
             if (PROT) protmin_item_reg<W>(smem, sb, it.nstep, a.k, (uint32_t)a.w, sink);
             else if (SYNC)
                 if (fast) syncmer_item_reg<W, true>(smem, sb, it.nstep, a.s, 2u * (uint32_t)(a.k - a.s), 0u, 1024u, 3072u, 2048u,
@@ -677,14 +870,15 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         // Ordered allocation in two halves: publish the tile's count, then -- while the tiles before this one
         // finish -- scatter the staged lists into one contiguous buffer (the codes are dead now; nothing here
         // needs the prefix), and only then wait for the prefix.
-        lookback_publish(a.tile_state, tile, total);
+        if (!a.unordered) lookback_publish(a.tile_state, tile, total);
         const uint32_t OB = a.sm_tile_bytes / 12u;
         uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
         uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
         auto scatter = [&](uint32_t r0) {
             uint32_t pos = it.q0 - 1u;
             for (uint32_t j = 0; j < sink.cnt; j++) {
-                pos += listp[j * 32u + lane];
+                if (KEYED) pos = it.q0 + listp[j * 32u + lane]; // absolute stream index
+                else pos += listp[j * 32u + lane];
                 const uint32_t o = excl + j - skip - r0;
                 if (j >= skip && o < OB) { // unsigned compare also rejects entries before r0
                     obv[o] = listv[j * 32u + lane];
@@ -694,7 +888,12 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
             __syncwarp();
         };
         if (!any_overflow && total) scatter(0);
-        const uint64_t tb = lookback_resolve(a.tile_state, tile, total);
+        uint64_t tb;
+        if (a.unordered) { // timing experiment only (B200SK_UNORDERED=1): ranges in completion order, WRONG output order
+            unsigned long long t0 = 0;
+            if (lane == 0) t0 = atomicAdd(a.unordered, (unsigned long long)total);
+            tb = __shfl_sync(0xffffffffu, t0, 0);
+        } else tb = lookback_resolve(a.tile_state, tile, total, a.spin_ns);
         const uint64_t mine = tb + excl;
         if (it.valid && it.first_chunk) a.out_off[it.r] = a.out_base + mine;
         if (it.valid && it.last_item) a.out_off[a.n_reads] = a.out_base + mine + cnt;
@@ -720,7 +919,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                 if (!overflow) {
                     uint32_t pos = it.q0 - 1u;
                     for (uint32_t j = 0; j < sink.cnt; j++) {
-                        pos += listp[j * 32u + lane];
+                        if (KEYED) pos = it.q0 + listp[j * 32u + lane];
+                        else pos += listp[j * 32u + lane];
                         if (j >= skip) {
                             a.out_val[mine + j - skip] = listv[j * 32u + lane];
                             if (a.out_pos) store_pos(a.out_pos, a.pos_width, mine + j - skip, pos);
@@ -747,9 +947,19 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
 }
 
 // ------------------------------------------------------------------ launch
+// The keyed walk is an EXPERIMENT kept for A/B (B200SK_WALKER=keyed): bit-exact, 6 % fewer main-loop
+// instructions, not faster -- the kernel is bound by its total integer-ALU instruction count, which the drain and the
+// detection give back, and every item handed to the exact walk stalls the ordered output of all later tiles.
+// Instantiated for the window sizes the A/B script uses.
+template <int MODE, int W> constexpr bool has_keyed() {
+    return MODE == B200SK_MODE_MINIMIZER && (W == 3 || W == 5 || W == 11 || W == 15);
+}
 template <int MODE, int W>
 static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
-    const void *fn = (const void *)k_sparse_warp<MODE, W>;
+    const void *fn = (const void *)k_sparse_warp<MODE, W, false>;
+    if constexpr (has_keyed<MODE, W>()) {
+        if (a.keyed) fn = (const void *)k_sparse_warp<MODE, W, true>;
+    }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.sm_total);
     if (e != cudaSuccess) return e;
     if (occ) {
@@ -758,8 +968,8 @@ static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_
         *occ = nb < 1 ? 1 : nb;
         return e;
     }
-    k_sparse_warp<MODE, W><<<blocks, threads, a.sm_total, st>>>(a);
-    return cudaGetLastError();
+    void *args[] = {(void *)&a};
+    return cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3((unsigned)threads), args, a.sm_total, st);
 }
 
 // Window sizes with a register-resident instantiation.  The instantiations are spread over four translation

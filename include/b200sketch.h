@@ -220,6 +220,43 @@ void b200sk_fxstream_close(b200sk_fxstream *s);
 uint64_t b200sk_fxstream_kernel_launches(const b200sk_fxstream *s);
 const char *b200sk_fxstream_last_error(const b200sk_fxstream *s);
 
+/* ---- multi-GPU -------------------------------------------------------------------------------
+ * Records carry no cross-record state (sketches/iterator.go:615-655, sketches/sketch.go:85-202): a batch shards
+ * over GPUs by contiguous read ranges and the only exchange is the gather of the per-GPU uint64 arrays; rank order
+ * == read order, so the gathered array is exactly what one GPU would have produced.
+ *
+ * One process per GPU: the root allocates the gather buffer and exports it over CUDA IPC; every other rank maps
+ * it and passes a pointer INTO it as d_out_val of b200sk_enqueue_device / b200sk_run_device -- the sketching
+ * kernel's own flush then stores its elements straight into the root's HBM over NVLink, tile by tile while the
+ * rest of the shard is still being walked (no staging copy, no collective on the data path).  Rank r's segment
+ * starts at a base the caller picks from b200sk_output_bound of the shards before it; the element counts
+ * (d_out_off[n_reads] of every rank, 8 bytes each) travel through whatever the host side uses.
+ * b200sk_compact_segments then closes the gaps on the root, in place.  The handle is a cudaIpcMemHandle_t. */
+#define B200SK_IPC_HANDLE_BYTES 64
+int b200sk_gather_create(b200sk_ctx *ctx, uint64_t capacity_elems, uint8_t *handle /*[64] out*/, uint64_t **d_buf);
+int b200sk_gather_open(b200sk_ctx *ctx, const uint8_t *handle /*[64]*/, uint64_t **d_buf);
+int b200sk_gather_close(b200sk_ctx *ctx, uint64_t *d_buf, int is_owner);
+/* seg_base / seg_count: host arrays, segment r = d_buf[seg_base[r] .. seg_base[r] + seg_count[r]), ordered,
+ * disjoint, seg_base[0] == 0.  Afterwards d_buf[0 .. sum of counts) is the gathered array. */
+int b200sk_compact_segments(b200sk_ctx *ctx, uint64_t *d_buf, const uint64_t *seg_base, const uint64_t *seg_count,
+                            int n_seg, void *stream);
+/* cut[n_shards + 1]: shard d owns reads [cut[d], cut[d+1]), balanced by cumulative bases (long, skewed reads). */
+void b200sk_shard_by_bases(const uint64_t *read_off, uint64_t n_reads, int n_shards, uint64_t *cut);
+
+/* One process, several devices: what SURVEY.md 8b calls b200sk_create(ctx**, devices, n).  One context, stream and
+ * worker thread per device; b200sk_group_run has the contract of b200sk_run (host pointers in, library-owned pinned
+ * arrays in read order out, valid until the next call on the group) with the reads sharded over every device of
+ * the group by cumulative bases.  One caller thread per group. */
+typedef struct b200sk_group b200sk_group;
+int b200sk_group_create(b200sk_group **g, const int *devices, int n_devices);
+void b200sk_group_destroy(b200sk_group *g);
+int b200sk_group_size(const b200sk_group *g);
+int b200sk_group_run(b200sk_group *g, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
+                     uint64_t n_reads, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+                     int32_t **read_status, uint64_t *n_out);
+const char *b200sk_group_last_error(const b200sk_group *g);
+uint64_t b200sk_group_kernel_launches(const b200sk_group *g);
+
 /* Synchronous copy of a library-owned device array (the feeder's tables) into host memory. */
 int b200sk_copy_to_host(b200sk_ctx *ctx, void *dst, const void *d_src, uint64_t bytes);
 

@@ -7,7 +7,7 @@ import pytest
 
 import oracle
 
-REF = "/root/reference/seqio/fastx"
+REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastx")  # copies of the reference's fixtures
 
 
 def make_fastq(n, read_len, seed, crlf=False, at_quals=False, tail_newline=True, lower=False):
@@ -51,8 +51,6 @@ def make_fasta(n, seed, width=60, crlf=False, blank_lines=False):
 # ------------------------------------------------------------------ oracle (CPU)
 def test_oracle_pinned_by_reference_fixtures():
     """reader_test.go:84,105,125,130-158: record counts of the reference's own fixtures."""
-    if not os.path.isdir(REF):
-        pytest.skip("reference tree not present (GPU box)")
     want = {"test.fa": 6, "test.fq": 8, "test2.fq": 5, "test3.fq": 3}
     for name, n in want.items():
         r = oracle.fastx_parse(open(os.path.join(REF, name), "rb").read())
@@ -172,6 +170,17 @@ def test_errors_and_edges():
         with pytest.raises(cabi.SketchError) as e:
             _parse_gpu(ctx, bad)
         assert e.value.code == cabi.ERR_BAD_FASTQ
+    # a broken record whose sequence line is far longer than its quality line must not be copied past the base
+    # buffer (sized n_bytes / 2): the call fails cleanly and the context stays usable
+    big = b"@a\n" + b"ACGT" * 300_000 + b"\n+\nI\n"
+    with pytest.raises(cabi.SketchError) as e:
+        _parse_gpu(ctx, big)
+    assert e.value.code == cabi.ERR_BAD_FASTQ
+    with pytest.raises(cabi.SketchError) as e:
+        _parse_gpu(ctx, b"@ok\nAC\n+\nII\n" + big)
+    assert e.value.code == cabi.ERR_BAD_FASTQ
+    info, g = _parse_gpu(ctx, b"@ok\nACGT\n+\nIIII\n")
+    assert g["n_records"] == 1 and bytes(g["bases"]) == b"ACGT"
     info, g = _parse_gpu(ctx, b"\n\n\n")
     assert g["n_records"] == 0
     # reader.go:286-294: leading blank lines are tolerated up to byte 10240 only
@@ -188,10 +197,9 @@ def test_errors_and_edges():
                     _parse_gpu(ctx, text)
                 assert e.value.code == cabi.ERR_NOT_FASTX
     for name, want in (("blank.fx", cabi.ERR_NOT_FASTX), ("blank1.fx", 0), ("empty.fx", 0)):  # reader_test.go:160-197
-        if os.path.isdir(REF):
-            text = open(os.path.join(REF, name), "rb").read()
-            o = oracle.fastx_parse(text)
-            assert o["status"] == want and o["n_records"] == 0
+        text = open(os.path.join(REF, name), "rb").read()
+        o = oracle.fastx_parse(text)
+        assert o["status"] == want and o["n_records"] == 0
     info, g = _parse_gpu(ctx, b">only header")
     o = oracle.fastx_parse(b">only header")
     assert g["n_records"] == o["n_records"] == 1 and g["read_off"].tolist() == [0, 0]
