@@ -49,6 +49,7 @@ EXPORTS = (
     "b200sk_gather_create", "b200sk_gather_open", "b200sk_gather_close", "b200sk_compact_segments",
     "b200sk_shard_by_bases", "b200sk_group_create", "b200sk_group_destroy", "b200sk_group_size", "b200sk_group_run",
     "b200sk_group_last_error", "b200sk_group_kernel_launches",
+    "b200sk_scale_max_hash", "b200sk_reduce_device",
 )
 IPC_HANDLE_BYTES = 64
 FXSTREAM_END = 1
@@ -193,6 +194,11 @@ def lib():
     L.b200sk_group_last_error.argtypes = [vp]
     L.b200sk_group_kernel_launches.restype = C.c_uint64
     L.b200sk_group_kernel_launches.argtypes = [vp]
+    L.b200sk_scale_max_hash.restype = C.c_uint64
+    L.b200sk_scale_max_hash.argtypes = [C.c_uint32]
+    L.b200sk_reduce_device.restype = C.c_int
+    L.b200sk_reduce_device.argtypes = [vp, u64p, C.c_uint64, C.c_uint32, C.c_int, u64p, C.c_uint64,
+                                       C.POINTER(C.c_uint64), vp]
     _lib = L
     return L
 
@@ -356,6 +362,19 @@ class Context:
             flags.data_ptr() if flags is not None else None)
         if rc != 0:
             self._raise(rc)
+
+    # ---- downstream reduction: FracMinHash filter + sort + unique on resident arrays
+    def reduce_device(self, d_val, n, d_out, scale=1, unique=True, stream=None):
+        """d_val[:n] (torch int64 CUDA tensor, consumed as scratch) -> d_out: values <= MaxUint64/scale, sorted, distinct.
+        Returns (rc, number of elements produced or needed)."""
+        import torch
+        st = torch.cuda.current_stream(d_val.device).cuda_stream if stream is None else stream
+        total = C.c_uint64(0)
+        rc = lib().b200sk_reduce_device(self._h, d_val.data_ptr(), int(n), int(scale), int(bool(unique)),
+                                        d_out.data_ptr(), d_out.numel(), C.byref(total), st)
+        if rc not in (0, ERR_CAPACITY):
+            self._raise(rc)
+        return rc, int(total.value)
 
     # ---- record feeder (seqio/fastx.Reader as a batch operation)
     def fastx_parse_device(self, d_text, n_bytes=None, fmt=0, final=True, stream=None):

@@ -134,6 +134,7 @@ struct b200sk_ctx {
     DevBuf d_bases2, d_off2, d_val2, d_pos2, d_ooff2, d_status2; // slot 1
     HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
     void *fx = nullptr; // record feeder state (b200sk_fastx.cu)
+    void *reduce = nullptr; // sort / unique workspace (b200sk_reduce.cu)
     uint64_t launches = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -146,6 +147,8 @@ void fx_free(void *p);
 int ctx_device(b200sk_ctx *ctx) { return ctx->device; }
 cudaStream_t ctx_stream(b200sk_ctx *ctx) { return ctx->own_stream; }
 void **ctx_fx_slot(b200sk_ctx *ctx) { return &ctx->fx; }
+void **ctx_reduce_slot(b200sk_ctx *ctx) { return &ctx->reduce; }
+void reduce_free(void *p);
 void ctx_set_error(b200sk_ctx *ctx, const char *msg) { ctx->last_error = msg; }
 void ctx_add_launches(b200sk_ctx *ctx, uint64_t n) { ctx->launches += n; }
 } // namespace b200sk
@@ -644,6 +647,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
         b->release();
     for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();
     b200sk::fx_free(ctx->fx);
+    b200sk::reduce_free(ctx->reduce);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

@@ -257,6 +257,17 @@ int b200sk_group_run(b200sk_group *g, const b200sk_params *p, const uint8_t *bas
 const char *b200sk_group_last_error(const b200sk_group *g);
 uint64_t b200sk_group_kernel_launches(const b200sk_group *g);
 
+/* ---- downstream reduction of the hash arrays -----------------------------------------------
+ * What the tools built on package sketches (kmcp, unikmer: sketches/README.md:14-15,42) do with the uint64 stream:
+ * keep the FracMinHash fraction h <= MaxUint64 / scale -- the rule sketches/iterator.go:180-185,281,443 applies to
+ * its m-mer hashes --, sort ascending, drop duplicates.  Done on the device, so that only the reduced sketch crosses
+ * PCIe / NVLink.  d_val[0..n) is consumed as scratch; d_out (capacity elements, must not alias d_val; capacity >= n
+ * when scale <= 1) receives the result; *n_out = its length (or the length needed, with B200SK_ERR_CAPACITY).
+ * scale <= 1: no filter.  unique = 0: sorted, duplicates kept. */
+uint64_t b200sk_scale_max_hash(uint32_t scale); /* MaxUint64 / scale, iterator.go:184 */
+int b200sk_reduce_device(b200sk_ctx *ctx, uint64_t *d_val, uint64_t n, uint32_t scale, int unique, uint64_t *d_out,
+                         uint64_t capacity, uint64_t *n_out, void *stream);
+
 /* Synchronous copy of a library-owned device array (the feeder's tables) into host memory. */
 int b200sk_copy_to_host(b200sk_ctx *ctx, void *dst, const void *d_src, uint64_t bytes);
 

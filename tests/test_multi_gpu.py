@@ -1,0 +1,160 @@
+"""Multi-GPU side of the C ABI (include/b200sketch.h): shard boundaries (host logic, CPU), the device
+group (one process, a context + worker thread per device), the gather buffer over CUDA IPC with the sketching kernel
+storing straight into the root's memory, and the in-place segment compaction."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from bio_b200 import _cabi as cabi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_by_bases_host_logic():
+    lens = synth.ont_like_lengths(5000, 3)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    for world in (1, 2, 3, 8):
+        cut = cabi.shard_by_bases(off, world)
+        assert cut[0] == 0 and cut[-1] == len(lens) and np.all(np.diff(cut.astype(np.int64)) >= 0)
+        per = np.diff(off[cut.astype(np.int64)].astype(np.int64))
+        assert per.max() - per.min() <= 2 * int(lens.max())  # balanced up to one read either side
+    # more shards than reads: empty shards, still a partition
+    cut = cabi.shard_by_bases(np.array([0, 10, 30], dtype=np.uint64), 8)
+    assert cut[0] == 0 and cut[-1] == 2 and np.all(np.diff(cut.astype(np.int64)) >= 0)
+    # bench.py's equal-count shards: block-aligned for 1/2/4/8 ranks, a partition for any count
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (100_000_000, 10_000_000, 1234567, 3):
+        for world in (1, 2, 4, 8):
+            b = bench.shard_bounds(n, world)
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+    b = bench.shard_bounds(100_000_000, 8)
+    assert all(x % bench.BLOCK == 0 for x in b)
+
+
+def _devices():
+    import torch
+    return [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+
+
+def _same(res, ref):
+    assert np.array_equal(res["off"], ref["off"])
+    assert np.array_equal(res["val"], ref["val"])
+    assert np.array_equal(res["pos"], ref["pos"])
+    assert np.array_equal(res["status"], ref["status"])
+
+
+@pytest.mark.gpu
+def test_group_one_process_several_contexts():
+    """b200sk_group_run: two contexts driven from two threads of one process (two devices when the box has them,
+    else two contexts on device 0), reads sharded by bases, results assembled in read order."""
+    g = cabi.Group(_devices())
+    assert g.size() == 2
+    b, o = synth.uniform_reads(30000, 150, 5)
+    res = g.run(cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150), b, o)
+    _same(res, oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=21, w=11, threads=8))
+    lens = np.array([0, 5, 30, 31, 32, 150, 0, 0, 400, 20, 31, 1000, 3, 151, 20000] * 40)
+    b, o = synth.ragged_reads(lens, 7, alphabet=b"ACGTNacgt")
+    for mode, omode, kw in ((cabi.MODE_MINIMIZER, oracle.MODE_MINIMIZER, dict(k=21, w=11)),
+                            (cabi.MODE_SYNCMER, oracle.MODE_SYNCMER, dict(k=21, s=11)),
+                            (cabi.MODE_NTHASH, oracle.MODE_NTHASH, dict(k=21))):
+        res = g.run(cabi.make_params(mode, **kw), b, o)
+        _same(res, oracle.run_batch(b, o, omode, threads=8, **kw))
+    # fewer reads than devices, and none at all
+    b1, o1 = synth.uniform_reads(1, 150, 9)
+    _same(g.run(cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11), b1, o1),
+          oracle.run_batch(b1, o1, oracle.MODE_MINIMIZER, k=21, w=11))
+    res = g.run(cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert res["total"] == 0 and res["off"].tolist() == [0]
+    with pytest.raises(cabi.SketchError) as e:
+        g.run(cabi.make_params(cabi.MODE_MINIMIZER, 21, w=0), b1, o1)
+    assert e.value.code == cabi.ERR_INVALID_W
+    assert g.kernel_launches() > 0
+    g.close()
+
+
+def _view(addr, n, dev):
+    import torch
+
+    class M:
+        pass
+    m = M()
+    m.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (addr, False), "version": 2}
+    return torch.as_tensor(m, device=dev)
+
+
+@pytest.mark.gpu
+def test_compact_segments_in_place():
+    import torch
+    ctx = cabi.Context(0)
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(1)
+    for counts, gaps in (([1000, 5, 70000, 0, 333], [0, 17, 1, 90000, 4]), ([10], [0]), ([0, 0, 7], [3, 3, 3]),
+                         ([300000, 300001, 299999], [0, 1, 100000])):
+        base, cur = [], 0
+        for c, g in zip(counts, gaps):
+            cur += g
+            base.append(cur)
+            cur += c
+        base[0] = 0
+        handle, addr = ctx.gather_create(cur + 8)
+        buf = _view(addr, cur + 8, dev)
+        buf.fill_(-1)
+        want = []
+        for b, c in zip(base, counts):
+            v = torch.from_numpy(rng.integers(0, 2**62, size=c, dtype=np.int64)).to(dev)
+            buf[b:b + c] = v
+            want.append(v)
+        ctx.compact_segments(addr, base, counts)
+        torch.cuda.synchronize()
+        assert torch.equal(buf[:sum(counts)], torch.cat(want))
+        del buf
+        ctx.gather_close(addr, True)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_ipc_gather_two_processes():
+    """Root (this process) exports the gather buffer; a second PROCESS maps it and its sketching kernel writes the
+    second shard's minimizers straight into its segment; after compaction the buffer is the single-GPU output."""
+    import torch
+    ndev = torch.cuda.device_count()
+    child_dev = 1 if ndev >= 2 else 0
+    dev = torch.device("cuda", 0)
+    n_total, r_split = 24000, 11000
+    b, o = synth.uniform_reads(n_total, 150, 77)
+    ref = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=21, w=11, threads=8)
+    ctx = cabi.Context(0)
+    p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150)
+    L = cabi.lib()
+    cap0 = int(L.b200sk_output_bound(C.byref(p), r_split * 150, r_split, 0))
+    cap1 = int(L.b200sk_output_bound(C.byref(p), (n_total - r_split) * 150, n_total - r_split, 0))
+    handle, gaddr = ctx.gather_create(cap0 + cap1)
+    child = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gather_child.py"), handle.hex(), str(cap0),
+                              str(cap1), str(child_dev), str(n_total), str(r_split), str(n_total)],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    bases = torch.from_numpy(np.concatenate([b[:r_split * 150], np.zeros(64, dtype=np.uint8)])).to(dev)
+    off = torch.from_numpy(o[:r_split + 1].astype(np.int64)).to(dev)
+    pos = torch.empty(cap0, dtype=torch.int32, device=dev)
+    ooff = torch.empty(r_split + 1, dtype=torch.int64, device=dev)
+    st = torch.empty(r_split, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    ctx.enqueue_device_raw(p, bases, off, r_split * 150, gaddr, cap0, pos, ooff, st, flags)
+    torch.cuda.synchronize()
+    out, err = child.communicate(timeout=300)
+    assert child.returncode == 0, err[-2000:]
+    c1 = int([ln for ln in out.splitlines() if ln.startswith("COUNT")][0].split()[1])
+    c0 = int(ooff[r_split].item())
+    assert c0 + c1 == len(ref["val"])
+    ctx.compact_segments(gaddr, [0, cap0], [c0, c1])
+    torch.cuda.synchronize()
+    got = _view(gaddr, c0 + c1, dev).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, ref["val"])
+    ctx.gather_close(gaddr, True)
+    ctx.close()
