@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU per e2e step (0 = the rank's shard, memory permitting)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=2_000_000, help="reads in the bounded CPU sample")
+    ap.add_argument("--scale", type=int, default=100, help="FracMinHash scale of the reduced variants (f4)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reduce", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="e2e: do not bind the rank to its GPU's NUMA node")
@@ -421,6 +423,13 @@ def run_ours(args, rank, world, local_rank):
         ctx.gather_close(gaddr, rank == 0)
     value = args.reads * READ_LEN / (ms_step * 1e-3)
 
+    # f4 on the resident arrays: FracMinHash fraction + sort + unique per rank, the per-rank sketches gathered on
+    # rank 0 (tiny now) and merged there.  Reported beside the full-stream step, not instead of it.
+    reduced = None
+    if not args.no_reduce:
+        reduced = run_reduced_device(args, ctx, cabi, oracle, torch, np, dist, dev, rank, world, p, bases, off, nb, n, val,
+                                     pos, ooff, status, flags, n_out, barrier, allmax, allsum_i64, cores)
+
     # roofline of the dominant (sketching) kernel, this rank's shard with local stores
     alg = algorithmic_bytes(n, nb, n_out)
     achieved = alg / (kern_ms * 1e-3) / 1e9
@@ -469,7 +478,7 @@ def run_ours(args, rank, world, local_rank):
             "parity": {"all_ok": all(x["mismatches"] == 0 for x in parity), "configs": parity,
                        "note": "first_window_ties = sampled reads whose first window holds equal hashes (the only place "
                                "the unpinned sorts.Quicksort tie order could matter); C5/ProteinIterator: WYHASH_UNPINNED"},
-            "per_gpu_resident": resident, "secondary": secondary,
+            "per_gpu_resident": resident, "secondary": secondary, "reduced": reduced,
         }
         if gather:
             line["gather"] = gather
@@ -478,6 +487,76 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_reduced_device(args, ctx, cabi, oracle, torch, np, dist, dev, rank, world, p, bases, off, nb, n, val, pos, ooff,
+                       status, flags, n_out, barrier, allmax, allsum_i64, cores):
+    """sketch -> keep h <= MaxUint64/scale -> sort -> unique on every rank; per-rank sketches to rank 0; merge there."""
+    scale = args.scale
+    state = {"out": torch.empty(min(n_out + 1, n_out // max(scale, 1) * 2 * (W + 1) + (1 << 20)), dtype=torch.int64, device=dev)}
+    res = {}
+    gbuf = None
+    if world > 1:
+        capr = state["out"].numel()
+        hbox = [None]
+        if rank == 0:
+            handle, gaddr = ctx.gather_create(capr * world)
+            hbox = [handle]
+        dist.broadcast_object_list(hbox, src=0)
+        if rank != 0:
+            gaddr = ctx.gather_open(hbox[0])
+        gbuf = _as_tensor(torch, gaddr, capr * world, dev)
+        merged = torch.empty(capr * world, dtype=torch.int64, device=dev) if rank == 0 else None
+        counts_d = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step():
+        ctx.enqueue_device(p, bases, off, nb, val, pos, ooff, status, flags)
+        rc, m = ctx.reduce_device(val, n_out, state["out"], scale=scale, unique=True)
+        if rc != 0:  # the kept fraction of window minima is ~(w+1)/scale, not 1/scale: size from the count reported
+            state["out"] = torch.empty(m + m // 8 + 1024, dtype=torch.int64, device=dev)
+            ctx.enqueue_device(p, bases, off, nb, val, pos, ooff, status, flags)
+            rc, m = ctx.reduce_device(val, n_out, state["out"], scale=scale, unique=True)
+            if rc != 0:
+                raise RuntimeError("reduce: capacity")
+        out = state["out"]
+        state["m"] = m
+        if world > 1:
+            gbuf[rank * capr: rank * capr + m].copy_(out[:m])           # peer store of the reduced sketch (rank > 0)
+            dist.all_gather_into_tensor(counts_d, torch.tensor([m], dtype=torch.int64, device=dev))
+            if rank == 0:
+                c = counts_d.cpu().numpy().astype(np.uint64)
+                ctx.compact_segments(gaddr, np.arange(world, dtype=np.uint64) * np.uint64(capr), c,
+                                     torch.cuda.current_stream(dev).cuda_stream)
+                rc, mm = ctx.reduce_device(gbuf, int(c.sum()), merged, scale=1, unique=True)
+                state["merged"] = mm
+
+    ms = allmax(timed(torch, step, max(2, args.steps // 3), 1, barrier))
+    m = state["m"]
+    # parity of the reduction itself: the oracle's stream for the first reads of this rank, reduced with numpy
+    ns = min(n, 50000)
+    hb = bases[:ns * READ_LEN].cpu().numpy()
+    ho = np.arange(ns + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    ref = oracle.run_batch(hb, ho, oracle.MODE_MINIMIZER, k=K, w=W, threads=cores)
+    want = np.unique(ref["val"][ref["val"] <= np.uint64(((1 << 64) - 1) // max(scale, 1))])
+    ctx.enqueue_device(p, bases, off, nb, val, pos, ooff, status, flags)
+    n_first = int(ooff[ns].item())
+    small = torch.empty(len(want) + 1024, dtype=torch.int64, device=dev)
+    rc, mm = ctx.reduce_device(val[:n_first].clone(), n_first, small, scale=scale, unique=True)
+    ok = bool(rc == 0 and mm == len(want) and np.array_equal(small[:mm].cpu().numpy().view(np.uint64), want))
+    if not ok:
+        raise RuntimeError("PARITY FAILED on the reduced sketch (f4)")
+    kept_sum, nv = allsum_i64(m), allsum_i64(0 if rank == 0 else m) * 8
+    res = {"scale": scale, "what": "sketch + keep h <= MaxUint64/scale + radix sort + unique on every rank"
+           + ("; reduced sketches stored into rank 0's buffer, merged (sort + unique) there" if world > 1 else ""),
+           "value": args.reads * READ_LEN / (ms * 1e-3), "unit": "bases/s", "ms_per_step": ms,
+           "elements_in": allsum_i64(n_out), "distinct_kept_per_rank_sum": kept_sum,
+           "oracle_check": {"reads": ns, "ok": ok}}
+    if world > 1:
+        res["merged_distinct"] = state.get("merged") if rank == 0 else None
+        res["bytes_over_nvlink"] = nv
+        del gbuf
+        ctx.gather_close(gaddr, rank == 0)
+    return res
 
 
 def _as_tensor(torch, addr, n, dev):
@@ -552,6 +631,28 @@ def run_e2e(args, ctx, cabi, d_bases, n_shard, rank, world, dev, dist, torch, np
            "d2h_bytes_per_step": n_out * 9 + (n + 1) * 8 + n * 4, "pos_width": 1,
            "reads_per_gpu_per_step": n, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
            "api": "b200sk_run (host pointers, pinned)", "oracle_check_first_reads": ns, "host_binding": binding}
+    if not args.no_reduce:
+        # the same batch through b200sk_run_reduced: only the FracMinHash sketch (sorted, distinct) comes back
+        red = ctx.run_reduced(p, hb, ho, scale=args.scale, unique=True, copy=False)
+        want = np.unique(ref["val"][ref["val"] <= np.uint64(((1 << 64) - 1) // max(args.scale, 1))])
+        at = np.minimum(np.searchsorted(red, want), max(len(red) - 1, 0))  # red is sorted: every wanted value must be in it
+        if len(red) == 0 or not np.array_equal(red[at], want) or not np.all(red[1:] > red[:-1]):
+            raise RuntimeError("PARITY FAILED on the reduced host path (b200sk_run_reduced)")
+        m = len(red)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            red = ctx.run_reduced(p, hb, ho, scale=args.scale, unique=True, copy=False)
+        dt2 = time.perf_counter() - t0
+        t = torch.tensor([dt2], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt2 = float(t.item())
+        out["reduced"] = {"value": int(tot.item()) * args.e2e_steps / dt2, "unit": "bases/s", "scale": args.scale,
+                          "api": "b200sk_run_reduced (keep h <= MaxUint64/scale, sort, unique on the device)",
+                          "h2d_bytes_per_step": nb + (n + 1) * 8, "d2h_bytes_per_step": m * 8,
+                          "ms_per_step": dt2 / args.e2e_steps * 1e3, "distinct_kept": m}
     L.b200sk_free_pinned(hb_ptr)
     L.b200sk_free_pinned(ho_ptr)
     if prev_affinity is not None:

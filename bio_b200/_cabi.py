@@ -49,7 +49,7 @@ EXPORTS = (
     "b200sk_gather_create", "b200sk_gather_open", "b200sk_gather_close", "b200sk_compact_segments",
     "b200sk_shard_by_bases", "b200sk_group_create", "b200sk_group_destroy", "b200sk_group_size", "b200sk_group_run",
     "b200sk_group_last_error", "b200sk_group_kernel_launches",
-    "b200sk_scale_max_hash", "b200sk_reduce_device",
+    "b200sk_scale_max_hash", "b200sk_reduce_device", "b200sk_run_reduced",
 )
 IPC_HANDLE_BYTES = 64
 FXSTREAM_END = 1
@@ -196,6 +196,9 @@ def lib():
     L.b200sk_group_kernel_launches.argtypes = [vp]
     L.b200sk_scale_max_hash.restype = C.c_uint64
     L.b200sk_scale_max_hash.argtypes = [C.c_uint32]
+    L.b200sk_run_reduced.restype = C.c_int
+    L.b200sk_run_reduced.argtypes = [vp, PP, C.c_uint32, C.c_int, u8p, u64p, C.c_uint64, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_uint64)]
     L.b200sk_reduce_device.restype = C.c_int
     L.b200sk_reduce_device.argtypes = [vp, u64p, C.c_uint64, C.c_uint32, C.c_int, u64p, C.c_uint64,
                                        C.POINTER(C.c_uint64), vp]
@@ -362,6 +365,23 @@ class Context:
             flags.data_ptr() if flags is not None else None)
         if rc != 0:
             self._raise(rc)
+
+    def run_reduced(self, params, bases, read_off, scale=1, unique=True, copy=True):
+        """Host entry point with the reduction inside: returns the sorted (distinct) values <= MaxUint64/scale."""
+        import numpy as np
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        ov = C.c_void_p()
+        total = C.c_uint64(0)
+        rc = lib().b200sk_run_reduced(self._h, C.byref(params), int(scale), int(bool(unique)), bases.ctypes.data,
+                                      read_off.ctypes.data, len(read_off) - 1, C.byref(ov), C.byref(total))
+        if rc != 0:
+            self._raise(rc)
+        t = int(total.value)
+        if not ov.value or t == 0:
+            return np.zeros(0, dtype=np.uint64)
+        a = np.ctypeslib.as_array(C.cast(ov, C.POINTER(C.c_uint64)), shape=(t,))
+        return a.copy() if copy else a
 
     # ---- downstream reduction: FracMinHash filter + sort + unique on resident arrays
     def reduce_device(self, d_val, n, d_out, scale=1, unique=True, stream=None):

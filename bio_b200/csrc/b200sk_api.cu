@@ -26,6 +26,8 @@ cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint
                                  cudaStream_t st, uint64_t n_bases);
 cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
 bool build_codon_aux(int id, uint8_t *aux);
+cudaError_t launch_filter_scale(const uint64_t *in, uint64_t n, uint64_t max_hash, uint64_t *out, uint64_t capacity,
+                                unsigned long long *count, cudaStream_t st);
 cudaError_t launch_scan_geom(const uint64_t *off, uint64_t n_reads, const ReadGeom &g, uint64_t *out,
                              uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st);
 cudaError_t launch_translate(const uint8_t *bases, const uint64_t *off, const uint64_t *aa_off, uint64_t n_reads,
@@ -133,6 +135,8 @@ struct b200sk_ctx {
     DevBuf d_bases, d_off, d_val, d_pos, d_ooff, d_status;       // slot 0
     DevBuf d_bases2, d_off2, d_val2, d_pos2, d_ooff2, d_status2; // slot 1
     HostBuf h_val, h_pos, h_ooff, h_status, h_meta;
+    DevBuf d_acc, d_acc2, d_acc_cnt; // b200sk_run_reduced: accumulation array, sort buffer, kept-element counter
+    uint64_t acc_cap_hint = 0;      // ... and the size a denser-than-planned batch asked for
     void *fx = nullptr; // record feeder state (b200sk_fastx.cu)
     void *reduce = nullptr; // sort / unique workspace (b200sk_reduce.cu)
     uint64_t launches = 0;
@@ -643,7 +647,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
     for (DevBuf *b : {&ctx->meta, &ctx->tile_state, &ctx->scan_state, &ctx->item_first, &ctx->tile_read, &ctx->circ_bases,
                       &ctx->circ_off, &ctx->ill, &ctx->aux, &ctx->aa_bases, &ctx->aa_off, &ctx->d_bases, &ctx->d_off, &ctx->d_val, &ctx->d_pos, &ctx->d_ooff,
                       &ctx->d_status, &ctx->d_bases2, &ctx->d_off2, &ctx->d_val2, &ctx->d_pos2, &ctx->d_ooff2,
-                      &ctx->d_status2})
+                      &ctx->d_status2, &ctx->d_acc, &ctx->d_acc2, &ctx->d_acc_cnt})
         b->release();
     for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();
     b200sk::fx_free(ctx->fx);
@@ -750,10 +754,16 @@ int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_
 // Host entry point.  Sub-batches of reads flow through three streams (H2D copy, kernels, D2H copy) and
 // two device slots, so the PCIe transfers of neighbouring sub-batches overlap each other (full duplex)
 // and the kernels.  Output offsets are made global on the device (out_base = elements emitted so far).
-int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
-               uint64_t n_reads, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
-               int32_t **read_status, uint64_t *n_out) {
-    if (!ctx || !p || !read_off) return B200SK_ERR_BAD_ARG;
+// reduce != nullptr: the sketches of every sub-batch stay on the device, their FracMinHash fraction is appended to
+// one accumulation array there, and only sort | unique of that array comes back (b200sk_run_reduced)
+struct ReduceOpt { uint32_t scale; int unique; };
+static int run_host(b200sk_ctx *ctx, const b200sk_params *p_in, const uint8_t *bases, const uint64_t *read_off,
+                    uint64_t n_reads, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+                    int32_t **read_status, uint64_t *n_out, const ReduceOpt *reduce) {
+    if (!ctx || !p_in || !read_off) return B200SK_ERR_BAD_ARG;
+    b200sk_params pcopy = *p_in;
+    if (reduce) pcopy.want_pos = 0; // an Index() means nothing once the values are sorted
+    const b200sk_params *p = &pcopy;
     int rc = b200sk_check_params(p);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -764,6 +774,21 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
     CK(ctx->h_status.reserve((n_reads + 1) * 4));
     CK(ctx->h_meta.reserve(64));
     uint64_t host_cap = b200sk_output_bound(p, n_bases, n_reads, 0);
+    uint64_t acc_cap = 0;
+    const uint64_t max_hash = reduce ? b200sk_scale_max_hash(reduce->scale) : ~0ULL;
+    if (reduce) { // the accumulation array: the expected fraction with a wide margin (checked, not trusted)
+        // (a window minimum of `win` hashes is <= x with probability ~ win * x: minimizers pass the filter win times
+        // as often as plain k-mer hashes do)
+        const uint64_t win = p->mode == B200SK_MODE_MINIMIZER || p->mode == B200SK_MODE_PROTEIN_MINIMIZER ? (uint64_t)p->w + 1
+                             : p->mode == B200SK_MODE_SYNCMER ? 2ull * (uint64_t)(p->k - p->s) + 1 : 1ull;
+        acc_cap = reduce->scale > 1 ? std::min<uint64_t>(host_cap, host_cap / reduce->scale * 2 * win + (1u << 20)) : host_cap;
+        if (ctx->acc_cap_hint > acc_cap) acc_cap = std::min<uint64_t>(host_cap, ctx->acc_cap_hint);
+        CK(ctx->d_acc.reserve(acc_cap * 8 + 64));
+        CK(ctx->d_acc2.reserve(acc_cap * 8 + 64));
+        CK(ctx->d_acc_cnt.reserve(64));
+        CK(cudaMemsetAsync(ctx->d_acc_cnt.p, 0, 64, s_k));
+        host_cap = 0;
+    }
     CK(ctx->h_val.reserve(host_cap * 8 + 8));
     const uint32_t pw = pos_width_of(*p);
     if (want_pos) CK(ctx->h_pos.reserve(host_cap * pw + 4));
@@ -903,6 +928,18 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
             cap = total; // exact requirement reported by the first pass
             if (attempt == 1) { cudaDeviceSynchronize(); save_slots(); return B200SK_ERR_CAPACITY; }
         }
+        if (reduce) {
+            // nothing of this sub-batch goes to the host: append the kept fraction of its values to the accumulation array
+            if (total) {
+                CKS(launch_filter_scale((const uint64_t *)sl.val.p, total, max_hash, (uint64_t *)ctx->d_acc.p, acc_cap,
+                                        (unsigned long long *)ctx->d_acc_cnt.p, s_k));
+                ctx->launches++;
+            }
+            CKS(cudaEventRecord(sl.out_done, s_k)); // the slot's outputs are free once the filter has read them
+            sl.out_pending = true;
+            running += total;
+            continue;
+        }
         if (running + total > host_cap) { // estimate too small: grow the pinned result arrays, keeping their content
             CKS(cudaStreamSynchronize(s_out));
             host_cap = (running + total) + (running + total) / 4 + 1024;
@@ -922,6 +959,27 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
         running += total;
     }
     CKS(cudaStreamSynchronize(s_out));
+    if (reduce) {
+        unsigned long long kept = 0;
+        CKS(cudaMemcpyAsync(&kept, ctx->d_acc_cnt.p, 8, cudaMemcpyDeviceToHost, s_k));
+        CKS(cudaStreamSynchronize(s_k));
+        save_slots();
+        if (kept > acc_cap) { // the fraction was larger than planned: once more with the size just measured
+            if (ctx->acc_cap_hint >= kept) return B200SK_ERR_CAPACITY;
+            ctx->acc_cap_hint = kept + kept / 8 + 1024;
+            return run_host(ctx, p_in, bases, read_off, n_reads, out_val, out_pos, out_off, read_status, n_out, reduce);
+        }
+        uint64_t m = 0;
+        rc = b200sk_reduce_device(ctx, (uint64_t *)ctx->d_acc.p, kept, reduce->scale, reduce->unique, (uint64_t *)ctx->d_acc2.p,
+                                  acc_cap, &m, s_k);
+        if (rc) return rc;
+        CK(ctx->h_val.reserve(m * 8 + 8));
+        if (m) CK(cudaMemcpyAsync(ctx->h_val.p, ctx->d_acc2.p, m * 8, cudaMemcpyDeviceToHost, s_k));
+        CK(cudaStreamSynchronize(s_k));
+        if (out_val) *out_val = (uint64_t *)ctx->h_val.p;
+        if (n_out) *n_out = m;
+        return 0;
+    }
     save_slots();
 #undef CKS
     if (out_val) *out_val = (uint64_t *)ctx->h_val.p;
@@ -930,6 +988,18 @@ int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, co
     if (read_status) *read_status = (int32_t *)ctx->h_status.p;
     if (n_out) *n_out = running;
     return 0;
+}
+
+int b200sk_run(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
+               uint64_t n_reads, uint64_t **out_val, uint32_t **out_pos, uint64_t **out_off,
+               int32_t **read_status, uint64_t *n_out) {
+    return run_host(ctx, p, bases, read_off, n_reads, out_val, out_pos, out_off, read_status, n_out, nullptr);
+}
+
+int b200sk_run_reduced(b200sk_ctx *ctx, const b200sk_params *p, uint32_t scale, int unique, const uint8_t *bases,
+                       const uint64_t *read_off, uint64_t n_reads, uint64_t **out_val, uint64_t *n_out) {
+    const ReduceOpt ro = {scale, unique};
+    return run_host(ctx, p, bases, read_off, n_reads, out_val, nullptr, nullptr, nullptr, n_out, &ro);
 }
 
 } // extern "C"

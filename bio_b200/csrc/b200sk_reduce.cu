@@ -279,6 +279,15 @@ ReduceState *state_of(b200sk_ctx *ctx) {
 
 } // namespace
 
+// append the values <= max_hash to out[*count ...] (count keeps running across calls)
+cudaError_t launch_filter_scale(const uint64_t *in, uint64_t n, uint64_t max_hash, uint64_t *out, uint64_t capacity,
+                                unsigned long long *count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 2047) / 2048, 148ull * 8);
+    k_filter_scale<<<blocks, 256, 0, st>>>(in, n, max_hash, out, capacity, count);
+    return cudaGetLastError();
+}
+
 void reduce_free(void *p) {
     ReduceState *s = static_cast<ReduceState *>(p);
     if (!s) return;

@@ -89,3 +89,27 @@ def test_minimizer_stream_reduced(gpu_ctx):
         want = _want(ref["val"], scale, True)
         assert rc == 0 and m == len(want)
         assert np.array_equal(out[:m].cpu().numpy().view(np.uint64), want)
+
+
+@pytest.mark.gpu
+def test_run_reduced_host_path(gpu_ctx, monkeypatch):
+    """b200sk_run_reduced: host pointers in, only the reduced sketch back; several sub-batches through the pipeline"""
+    monkeypatch.setenv("B200SK_SUB_BYTES", "300000")  # ~2000 reads per sub-batch
+    b, o = synth.uniform_reads(30000, 150, 33)
+    ref = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=21, w=11, threads=8)
+    p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150)
+    for scale, unique in ((1, True), (1, False), (50, True), (1000, True)):
+        got = gpu_ctx.run_reduced(p, b, o, scale=scale, unique=unique)
+        assert np.array_equal(got, _want(ref["val"], scale, unique)), (scale, unique)
+    lens = np.array([0, 5, 30, 31, 150, 400, 20000, 3] * 30)
+    b, o = synth.ragged_reads(lens, 7, alphabet=b"ACGTN")
+    ref = oracle.run_batch(b, o, oracle.MODE_SYNCMER, k=21, s=11, threads=8)
+    got = gpu_ctx.run_reduced(cabi.make_params(cabi.MODE_SYNCMER, 21, s=11), b, o, scale=4)
+    assert np.array_equal(got, _want(ref["val"], 4, True))
+    got = gpu_ctx.run_reduced(p, np.zeros(0, np.uint8), np.zeros(1, np.uint64), scale=4)
+    assert len(got) == 0
+    # the plain host path still works on the same context afterwards
+    b, o = synth.uniform_reads(3000, 150, 34)
+    res = gpu_ctx.run(p, b, o)
+    ref = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=21, w=11, threads=8)
+    assert np.array_equal(res["val"], ref["val"]) and np.array_equal(res["pos"], ref["pos"])
