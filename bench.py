@@ -7,9 +7,9 @@
 A step = one pass of the sketching hot path (sketches.NewMinimizerSketch + NextMinimizer/Index over every read,
 reference: sketches/sketch.go:85,205) over ONE batch of 100 M synthetic reads (BASELINE.json config 3), through the
 C ABI of libb200sketch.so.  With N GPUs the batch is SHARDED over the ranks ("scaling": "strong") and the gather of
-the per-GPU uint64 arrays to rank 0 is INSIDE the step: every rank's sketching kernel stores its minimizers straight
-into rank 0's gather buffer over NVLink (CUDA-IPC peer mapping, b200sk_gather_*), the per-rank counts travel over
-NCCL (8 bytes each), rank 0 closes the gaps between the rank segments (b200sk_compact_segments).
+the per-GPU arrays to rank 0 is INSIDE the step: the batch is dealt out in chunks of 32 768 reads (chunk c -> rank c % N), the
+ranks' sketching kernels share ONE ordered output chain (b200sk_enqueue_device_sharded: the look-back over per-tile status
+words runs across the GPUs) and every flush stores straight into rank 0's arrays over NVLink at its exact place.
 
 JSON line (rank 0):
   value         whole-job bases/s, batch resident in HBM, gathered array complete on rank 0 when the clock stops
@@ -33,7 +33,8 @@ sys.path.insert(0, ROOT)
 
 K, W, S, READ_LEN = 21, 11, 11, 150
 SEED = 43
-BLOCK = 500_000  # reads per generator block: shard boundaries of 1/2/4/8 ranks fall on block boundaries
+BLOCK = 1 << 19   # reads per generator block (one seed each)
+CHUNK = 1 << 15   # reads per chunk of the sharded C3 batch: chunk c belongs to rank c % N (1024 tiles of 32 reads)
 METRIC = "bases/sec sketched (k=21,w=11 minimizer)"
 
 
@@ -52,6 +53,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=2_000_000, help="reads in the bounded CPU sample")
     ap.add_argument("--scale", type=int, default=100, help="FracMinHash scale of the reduced variants (f4)")
+    ap.add_argument("--gather-pos", type=int, default=1, help="N > 1: also gather the uint8 positions on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reduce", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -149,29 +151,55 @@ def shard_bounds(n, world):
     return [min(n, (nb * r // world) * BLOCK) if r < world else n for r in range(world + 1)]
 
 
-def gen_uniform_shard(torch, r0, r1, read_len, seed, dev):
-    """reads [r0, r1) of the job-wide batch: block b of BLOCK reads is drawn from its own seed, so the union over the
-    ranks is the same batch for every N.  Padded by 64 bytes (the 16-byte TMA units of the last tile)."""
+def gen_uniform_block(torch, b, n_reads, read_len, seed, dev, lut, g):
+    """reads [b * BLOCK, min((b + 1) * BLOCK, n_reads)) of the job-wide batch, drawn from the block's own seed"""
+    g.manual_seed(seed * 1_000_003 + b)
+    full = torch.randint(0, 4, (BLOCK * read_len,), generator=g, device=dev, dtype=torch.int64)
+    cnt = (min(n_reads, (b + 1) * BLOCK) - b * BLOCK) * read_len
+    return lut[full[:cnt]]
+
+
+def gen_uniform_shard(torch, r0, r1, read_len, seed, dev, n_reads=None):
+    """reads [r0, r1) of the job-wide batch (r0 on a block boundary): the union over the ranks is the same batch for
+    every N.  Padded by 64 bytes (the 16-byte TMA units of the last tile)."""
+    assert r0 % BLOCK == 0 or r0 == r1
     n = (r1 - r0) * read_len
     buf = torch.empty(n + 64, dtype=torch.uint8, device=dev)
     buf[n:] = 0
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
     g = torch.Generator(device=dev)
     pos = 0
-    b = r0 // BLOCK
-    r = r0
-    while r < r1:
-        e = min(r1, (b + 1) * BLOCK)
-        g.manual_seed(seed * 1_000_003 + b)
-        full = torch.randint(0, 4, (BLOCK * read_len,), generator=g, device=dev, dtype=torch.int64)
-        lo = (r - b * BLOCK) * read_len
-        cnt = (e - r) * read_len
-        buf[pos:pos + cnt] = lut[full[lo:lo + cnt]]
-        pos += cnt
-        r = e
-        b += 1
+    for b in range(r0 // BLOCK, (r1 + BLOCK - 1) // BLOCK):
+        blk = gen_uniform_block(torch, b, r1, read_len, seed, dev, lut, g)
+        buf[pos:pos + blk.numel()] = blk
+        pos += blk.numel()
     off = torch.arange(r1 - r0 + 1, dtype=torch.int64, device=dev) * read_len
     return buf, off
+
+
+def gen_uniform_chunks(torch, n_reads, rank, world, read_len, seed, dev):
+    """this rank's part of the job-wide batch dealt out in chunks of CHUNK reads (chunk c -> rank c % world), back
+    to back in chunk order.  world == 1: the whole batch, identical to gen_uniform_shard(0, n_reads)."""
+    n_chunks = (n_reads + CHUNK - 1) // CHUNK
+    mine = range(rank, n_chunks, world)
+    n_local = sum(min(n_reads, (c + 1) * CHUNK) - c * CHUNK for c in mine)
+    buf = torch.empty(n_local * read_len + 64, dtype=torch.uint8, device=dev)
+    buf[n_local * read_len:] = 0
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev)
+    pos = 0
+    per = BLOCK // CHUNK
+    for b in range((n_reads + BLOCK - 1) // BLOCK):
+        blk = gen_uniform_block(torch, b, n_reads, read_len, seed, dev, lut, g)
+        for c in range(b * per, min(n_chunks, (b + 1) * per)):
+            if c % world != rank:
+                continue
+            lo = (c * CHUNK - b * BLOCK) * read_len
+            cnt = (min(n_reads, (c + 1) * CHUNK) - c * CHUNK) * read_len
+            buf[pos:pos + cnt] = blk[lo:lo + cnt]
+            pos += cnt
+    off = torch.arange(n_local + 1, dtype=torch.int64, device=dev) * read_len
+    return buf, off, n_local
 
 
 def gather_ranges(torch, src, starts, lens, chunk=50_000_000):
@@ -320,10 +348,8 @@ def run_ours(args, rank, world, local_rank):
     parity = []
 
     # ------------------------------------------------------------ C3: the headline batch, sharded over the ranks
-    bounds = shard_bounds(args.reads, world)
-    r0, r1 = bounds[rank], bounds[rank + 1]
-    n, nb = r1 - r0, (r1 - r0) * READ_LEN
-    bases, off = gen_uniform_shard(torch, r0, r1, READ_LEN, SEED, dev)
+    bases, off, n = gen_uniform_chunks(torch, args.reads, rank, world, READ_LEN, SEED, dev)
+    nb = n * READ_LEN
     p = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN)
     cap = int(L.b200sk_output_bound(ctypes.byref(p), nb, n, 0))
     val = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -370,28 +396,43 @@ def run_ours(args, rank, world, local_rank):
         launches = ctx.kernel_launches() - l0
         clocks = sampler.stop()
     else:
-        caps = torch.zeros(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(caps, torch.tensor([cap], dtype=torch.int64, device=dev))
-        caps = caps.cpu().numpy().astype(np.uint64)
-        seg_base = np.zeros(world, dtype=np.uint64)
-        seg_base[1:] = np.cumsum(caps)[:-1]
-        hbox = [None]
+        # ONE output chain across the GPUs (b200sk_enqueue_device_sharded): the root owns the result arrays, every rank
+        # owns a copy of the per-tile status words; all of them are CUDA-IPC buffers mapped into every process
+        cap_total = int(L.b200sk_output_bound(ctypes.byref(p), args.reads * READ_LEN, args.reads, 0))
+        n_tiles = (args.reads + 31) // 32
+        mine = {"state": ctx.gather_create(n_tiles + 1)}
         if rank == 0:
-            handle, gaddr = ctx.gather_create(int(caps.sum()))
-            hbox = [handle]
-        dist.broadcast_object_list(hbox, src=0)
-        if rank != 0:
-            gaddr = ctx.gather_open(hbox[0])
-        my_seg = gaddr + int(seg_base[rank]) * 8
-        counts_d = torch.zeros(world, dtype=torch.int64, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+            mine.update(val=ctx.gather_create(cap_total), pos=ctx.gather_create(cap_total // 8 + 8),
+                        off=ctx.gather_create(args.reads + 1), status=ctx.gather_create(args.reads // 2 + 8))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, {k: v[0] for k, v in mine.items()})
+        opened = []
 
-        def step():
-            # the sketching kernel's flush stores into rank 0's buffer (peer st.global over NVLink for rank > 0)
-            ctx.enqueue_device_raw(p, bases, off, nb, my_seg, cap, pos, ooff, status, flags)
-            dist.all_gather_into_tensor(counts_d, ooff[n:n + 1])          # 8 bytes per rank over NCCL
-            if rank == 0:
-                ctx.compact_segments(gaddr, seg_base, counts_d.cpu().numpy().astype(np.uint64), stream)
+        def mapped(r, key):
+            if r == rank:
+                return mine[key][1]
+            a = ctx.gather_open(everyone[r][key])
+            opened.append(a)
+            return a
+
+        g_val, g_pos, g_off, g_status = (mapped(0, k) for k in ("val", "pos", "off", "status"))
+        states = [mapped(r, "state") for r in range(world)]
+        ps = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN, pos_width=1)
+        ps_nopos = cabi.make_params(cabi.MODE_MINIMIZER, K, w=W, max_read_len=READ_LEN, want_pos=False)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+        epoch = [0]
+
+        def step(with_pos=bool(args.gather_pos)):
+            epoch[0] += 1
+            spec = cabi.ShardSpec()
+            spec.rank, spec.n_ranks, spec.chunk_reads, spec.n_reads_global = rank, world, CHUNK, args.reads
+            spec.epoch = epoch[0] % 16383 + 1
+            for r in range(world):
+                spec.state[r] = states[r]
+            # every rank's flush stores straight into rank 0's arrays at its exact place (peer st.global over NVLink)
+            ctx.enqueue_device_sharded(ps if with_pos else ps_nopos, spec, bases, off, nb, g_val, g_pos if with_pos else 0,
+                                       g_off, g_status, cap_total, flags)
+            dist.all_reduce(token)  # stream-ordered: no rank starts step e+1 before every rank has finished step e
 
         if rank == 0:
             sampler.start()
@@ -401,26 +442,36 @@ def run_ours(args, rank, world, local_rank):
         clocks = sampler.stop() if rank == 0 else None
         if int(flags.item()) != 0:
             raise RuntimeError("kernel flags %d" % int(flags.item()))
-        # the two halves of the step on their own: kernels with peer stores, and the compaction on rank 0
-        peer_ms = allmax(timed(torch, lambda: ctx.enqueue_device_raw(p, bases, off, nb, my_seg, cap, pos, ooff, status, flags),
-                               max(args.steps // 2, 2), 1, barrier))
-        cnts = counts_d.cpu().numpy().astype(np.uint64)
-        nvbytes = int(cnts[1:].sum()) * 8
         gsum_ok = None
         if rank == 0:
-            ctx.compact_segments(gaddr, seg_base, cnts, stream)
-            torch.cuda.synchronize()
-            # the gathered array must be the concatenation of the rank arrays: same count, same checksum
-            g = _as_tensor(torch, gaddr, int(cnts.sum()), dev)
-            gsum_ok = bool((int(g.sum().item()) & 0xFFFFFFFFFFFFFFFF) == checksum and int(cnts.sum()) == total_out)
-            del g
+            # the root must hold what one GPU would have produced: same count, same checksum, a monotone offset table
+            goff = _as_tensor(torch, g_off, args.reads + 1, dev)
+            tot = int(goff[args.reads].item())
+            g = _as_tensor(torch, g_val, tot, dev)
+            gsum_ok = bool(tot == total_out and (int(g.sum().item()) & 0xFFFFFFFFFFFFFFFF) == checksum
+                           and bool((goff[1:] >= goff[:-1]).all().item()) and int(goff[0].item()) == 0)
+            del g, goff
+            if not gsum_ok:
+                raise RuntimeError("PARITY FAILED: the gathered arrays differ from the per-rank results")
         barrier()
-        gather = {"bytes_over_nvlink": nvbytes, "how": "peer st.global from the sketching kernel's flush into rank 0's "
-                  "CUDA-IPC buffer; counts by NCCL all-gather (8 B/rank); b200sk_compact_segments on rank 0",
-                  "kernels_with_peer_stores_ms": peer_ms, "kernels_local_ms": res_ms_max,
-                  "ingress_GBps": nvbytes / (peer_ms * 1e-3) / 1e9 if peer_ms else None,
-                  "counts_and_compaction_ms": max(ms_step - peer_ms, 0.0), "gathered_checksum_ok": gsum_ok}
-        ctx.gather_close(gaddr, rank == 0)
+        # the same step gathering the uint64 arrays (+ offsets, statuses) only -- what BASELINE.json's north star names
+        vo_ms = allmax(timed(torch, lambda: step(False), max(args.steps // 2, 3), 1, barrier))
+        nvbytes = (total_out - n_out) * (9 if args.gather_pos else 8) + (args.reads - n) * 12 if rank == 0 else 0
+        nvbytes = allsum_i64(nvbytes)
+        gather = {"how": "one output chain across the GPUs: the sketching kernels' look-back runs through every rank's copy "
+                         "of the status words (posted 8-byte peer stores), each flush stores at its exact place in rank 0's "
+                         "arrays (peer st.global over NVLink); no staging copy, no compaction, no counts exchanged; a "
+                         "4-byte NCCL all-reduce separates the steps",
+                  "gathered": "uint64 values" + (" + uint8 positions" if args.gather_pos else "") + " + per-read offsets and statuses, all on rank 0",
+                  "bytes_into_rank0_over_nvlink": nvbytes, "ingress_GBps": nvbytes / (ms_step * 1e-3) / 1e9,
+                  "kernels_local_ms": res_ms_max, "gathered_checksum_ok": gsum_ok, "chunk_reads": CHUNK,
+                  "values_only": {"ms_per_step": vo_ms, "value": args.reads * READ_LEN / (vo_ms * 1e-3), "unit": "bases/s",
+                                  "what": "the same step without the uint8 positions (uint64 arrays + offsets + statuses)"}}
+        for a in opened:
+            ctx.gather_close(a, False)
+        barrier()
+        for v in mine.values():
+            ctx.gather_close(v[1], True)
     value = args.reads * READ_LEN / (ms_step * 1e-3)
 
     # f4 on the resident arrays: FracMinHash fraction + sort + unique per rank, the per-rank sketches gathered on

@@ -49,7 +49,7 @@ EXPORTS = (
     "b200sk_gather_create", "b200sk_gather_open", "b200sk_gather_close", "b200sk_compact_segments",
     "b200sk_shard_by_bases", "b200sk_group_create", "b200sk_group_destroy", "b200sk_group_size", "b200sk_group_run",
     "b200sk_group_last_error", "b200sk_group_kernel_launches",
-    "b200sk_scale_max_hash", "b200sk_reduce_device", "b200sk_run_reduced",
+    "b200sk_scale_max_hash", "b200sk_reduce_device", "b200sk_run_reduced", "b200sk_enqueue_device_sharded",
 )
 IPC_HANDLE_BYTES = 64
 FXSTREAM_END = 1
@@ -75,6 +75,11 @@ class Params(C.Structure):
         ("frame", C.c_int32), ("alphabet", C.c_int32), ("want_pos", C.c_int32),
         ("max_read_len", C.c_uint32), ("m", C.c_int32), ("scale", C.c_int32), ("pos_width", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
+
+
+class ShardSpec(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("chunk_reads", C.c_uint32), ("epoch", C.c_uint32),
+                ("n_reads_global", C.c_uint64), ("state", C.c_void_p * 8)]
 
 
 def make_params(mode, k, w=0, s=0, canonical=True, circular=False, codon_table=1, frame=1,
@@ -196,6 +201,9 @@ def lib():
     L.b200sk_group_kernel_launches.argtypes = [vp]
     L.b200sk_scale_max_hash.restype = C.c_uint64
     L.b200sk_scale_max_hash.argtypes = [C.c_uint32]
+    L.b200sk_enqueue_device_sharded.restype = C.c_int
+    L.b200sk_enqueue_device_sharded.argtypes = [vp, PP, C.POINTER(ShardSpec), u8p, u64p, C.c_uint64, C.c_uint64, vp, vp, vp,
+                                                vp, C.c_uint64, vp, u32p]
     L.b200sk_run_reduced.restype = C.c_int
     L.b200sk_run_reduced.argtypes = [vp, PP, C.c_uint32, C.c_int, u8p, u64p, C.c_uint64, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64)]
@@ -362,6 +370,21 @@ class Context:
             self._h, C.byref(params), d_bases.data_ptr(), d_off.data_ptr(), n, n_bases, C.c_void_p(out_val_addr),
             out_pos.data_ptr() if out_pos is not None else None, out_off.data_ptr(),
             status.data_ptr() if status is not None else None, int(capacity), st,
+            flags.data_ptr() if flags is not None else None)
+        if rc != 0:
+            self._raise(rc)
+
+    def enqueue_device_sharded(self, params, spec, d_bases, d_off, n_bases, val_addr, pos_addr, off_addr, status_addr,
+                               capacity, flags, stream=None):
+        """One rank's part of a batch sharded over several GPUs: the output arrays are raw device addresses of the
+        ROOT's buffers (peer-mapped here), indexed globally (include/b200sketch.h: b200sk_enqueue_device_sharded)."""
+        import torch
+        n = d_off.numel() - 1
+        st = torch.cuda.current_stream(d_bases.device).cuda_stream if stream is None else stream
+        rc = lib().b200sk_enqueue_device_sharded(
+            self._h, C.byref(params), C.byref(spec), d_bases.data_ptr(), d_off.data_ptr(), n, n_bases,
+            C.c_void_p(val_addr), C.c_void_p(pos_addr) if pos_addr else None, C.c_void_p(off_addr),
+            C.c_void_p(status_addr) if status_addr else None, int(capacity), st,
             flags.data_ptr() if flags is not None else None)
         if rc != 0:
             self._raise(rc)

@@ -307,9 +307,19 @@ inline uint32_t pos_width_of(const b200sk_params &p) { return p.pos_width == 1 ?
 
 int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, const uint64_t *d_off,
             uint64_t n_reads, uint64_t n_bases, uint64_t *d_val, void *d_pos, uint64_t *d_ooff,
-            int32_t *d_status, uint64_t capacity, uint64_t out_base, cudaStream_t st, uint32_t *d_flags) {
+            int32_t *d_status, uint64_t capacity, uint64_t out_base, cudaStream_t st, uint32_t *d_flags,
+            const b200sk_shard_spec *spec = nullptr) {
     int rc = b200sk_check_params(&p);
     if (rc) return rc;
+    if (spec) {
+        if (spec->n_ranks < 1 || spec->n_ranks > B200SK_MAX_RANKS || spec->rank < 0 || spec->rank >= spec->n_ranks ||
+            spec->chunk_reads == 0 || spec->chunk_reads % 32u != 0 || (spec->epoch & 0x3fffu) == 0)
+            return B200SK_ERR_BAD_ARG;
+        for (int r = 0; r < spec->n_ranks; r++)
+            if (!spec->state[r]) return B200SK_ERR_BAD_ARG;
+        if (p.mode != B200SK_MODE_MINIMIZER && p.mode != B200SK_MODE_SYNCMER) return B200SK_ERR_UNSUPPORTED;
+        if (p.circular || p.max_read_len == 0) return B200SK_ERR_UNSUPPORTED; // one item per read, known up front
+    }
     if (!d_off || !d_ooff || (n_bases && !d_bases)) return B200SK_ERR_BAD_ARG;
     if (((uintptr_t)d_bases & 15u) != 0) return B200SK_ERR_BAD_ARG;
     if ((rc = ensure_meta(ctx))) return rc;
@@ -434,6 +444,14 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
             have_items_host = false;
         }
     }
+    if (spec) {
+        // the global tile chain needs one item per read and the warp-tile kernel (32 reads per tile)
+        if (pl.chunked || !pl.reg) return B200SK_ERR_UNSUPPORTED;
+        a.shard.n = (uint32_t)spec->n_ranks; a.shard.rank = (uint32_t)spec->rank; a.shard.epoch = spec->epoch;
+        for (int r = 0; r < spec->n_ranks; r++) a.shard.copy[r] = spec->state[r];
+        a.shard_chunk_tiles = spec->chunk_reads / 32u;
+        a.shard_n_reads = spec->n_reads_global;
+    }
     a.C = pl.C; a.span_max = pl.span_max; a.lcap = pl.lcap;
     a.keyed = pl.keyed ? 1u : 0u;
     if (pl.keyed) {
@@ -495,7 +513,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     }
     const uint32_t tile_items = pl.reg ? 32u : (uint32_t)pl.T; // the register-window kernels tile per warp
     const uint64_t n_tiles = (items_bound + tile_items - 1) / tile_items + 1;
-    if (!pl.dense) {
+    if (!pl.dense && !spec) { // (a sharded batch chains through the ranks' epoch-tagged words instead: never reset)
         CK(ctx->tile_state.reserve(n_tiles * 8));
         CK(cudaMemsetAsync(ctx->tile_state.p, 0, n_tiles * 8, st));
     }
@@ -728,6 +746,18 @@ int b200sk_enqueue_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t
     if (d_flags) CK(cudaMemsetAsync(d_flags, 0, 4, (cudaStream_t)stream));
     return enqueue(ctx, *p, d_bases, d_read_off, n_reads, n_bases, d_out_val, d_out_pos, d_out_off,
                    d_read_status, capacity, 0, (cudaStream_t)stream, d_flags);
+}
+
+int b200sk_enqueue_device_sharded(b200sk_ctx *ctx, const b200sk_params *p, const b200sk_shard_spec *spec,
+                                  const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                                  uint64_t *d_out_val, uint32_t *d_out_pos, uint64_t *d_out_off, int32_t *d_read_status,
+                                  uint64_t capacity, void *stream, uint32_t *d_flags) {
+    if (!ctx || !p || !spec) return B200SK_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (d_flags) CK(cudaMemsetAsync(d_flags, 0, 4, (cudaStream_t)stream));
+    if (n_reads == 0) return 0; // a rank without reads publishes nothing: no tile of the chain is its own
+    return enqueue(ctx, *p, d_bases, d_read_off, n_reads, n_bases, d_out_val, d_out_pos, d_out_off, d_read_status,
+                   capacity, 0, (cudaStream_t)stream, d_flags, spec);
 }
 
 int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,

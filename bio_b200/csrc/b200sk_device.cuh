@@ -169,6 +169,65 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t t
     return excl;
 }
 
+// ------------------------------------------------------------------ the same chain ACROSS GPUs
+// One batch sharded over n GPUs in chunks of consecutive tiles (chunk c belongs to rank c mod n): the tiles of all
+// ranks form ONE ordered chain, so every rank's flush lands at its exact offset in the root's output arrays.
+// Every rank keeps a full copy of the status words and a tile publishes into ALL copies (n-1 posted 8-byte stores
+// over NVLink); the look-back itself only ever polls the local copy.  Words carry an epoch so that a step never
+// has to wait for the other ranks' memset: [63:62] flag, [61:48] epoch, [47:0] value.
+#define B200SK_MAX_RANKS 8
+#define B200SK_MVAL_MASK ((1ULL << 48) - 1)
+struct PeerStates {
+    uint64_t *copy[B200SK_MAX_RANKS]; // [r]: rank r's copy as mapped here ([rank] is the local one)
+    uint32_t n, rank, epoch;
+};
+__device__ __forceinline__ uint64_t ld_state_sys(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state_sys(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t mstate_word(uint64_t flag, uint32_t epoch, uint64_t value) {
+    return (flag << 62) | ((uint64_t)(epoch & 0x3fffu) << 48) | (value & B200SK_MVAL_MASK);
+}
+__device__ __forceinline__ void mstate_store_all(const PeerStates &ps, uint64_t tile, uint64_t word) {
+    for (uint32_t r = 0; r < ps.n; r++) st_state_sys(ps.copy[r] + tile, word);
+}
+__device__ __forceinline__ void lookback_publish_multi(const PeerStates &ps, uint64_t tile, uint64_t total) {
+    if ((threadIdx.x & 31u) == 0)
+        mstate_store_all(ps, tile, mstate_word(tile == 0 ? B200SK_FLAG_INC : B200SK_FLAG_AGG, ps.epoch, total));
+}
+__device__ __forceinline__ uint64_t lookback_resolve_multi(const PeerStates &ps, uint64_t tile, uint64_t total) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0) return 0;
+    const uint64_t *state = ps.copy[ps.rank];
+    const uint64_t want_epoch = (uint64_t)(ps.epoch & 0x3fffu);
+    uint64_t excl = 0;
+    int64_t idx = (int64_t)tile - 1 - (int64_t)lane;
+    while (true) {
+        uint64_t v = mstate_word(B200SK_FLAG_INC, ps.epoch, 0); // lanes before tile 0 read as "inclusive 0"
+        if (idx >= 0) {
+            v = ld_state_sys(state + idx);
+            while ((v >> 62) == B200SK_FLAG_EMPTY || ((v >> 48) & 0x3fffu) != want_epoch) v = ld_state_sys(state + idx);
+        }
+        const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
+        uint64_t contrib = v & B200SK_MVAL_MASK;
+        if (inc) {
+            const unsigned first = __ffs(inc) - 1;
+            if (lane > first) contrib = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (inc) break;
+        idx -= 32;
+    }
+    if (lane == 0) mstate_store_all(ps, tile, mstate_word(B200SK_FLAG_INC, ps.epoch, excl + total));
+    return excl;
+}
+
 // Block-wide exclusive scan of one uint32 per thread (blockDim.x <= 1024, multiple of 32).
 // warp_sums: shared scratch of >= 33 uint32.  Returns exclusive prefix; *block_total = sum.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t *block_total) {

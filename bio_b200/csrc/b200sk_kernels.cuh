@@ -3,6 +3,7 @@
 #include <stdint.h>
 
 #include "../../include/b200sketch.h"
+#include "b200sk_device.cuh"
 
 namespace b200sk {
 
@@ -44,6 +45,12 @@ struct KArgs {
         g.protein_input = alphabet == 5; g.ill = ill;
         return g;
     }
+    // one batch sharded over several GPUs (b200sk_enqueue_device_sharded): this rank's tiles are chunks of
+    // shard_chunk_tiles consecutive tiles of the GLOBAL tile order (chunk c belongs to rank c mod n); out_val /
+    // out_pos / out_off / status are the ROOT's arrays, indexed globally.  shard.n == 0: a single GPU.
+    PeerStates shard;
+    uint32_t shard_chunk_tiles;
+    uint64_t shard_n_reads; // reads of the whole batch
     unsigned long long *rewalks; // keyed walk: items handed to the exact walk are counted here (may be null)
     uint32_t keyed;    // minimizers, W <= 16: window minimum on 32-bit keys (b200sk_sparse_reg.cu)
     uint32_t key_mask; // 0xffffffc0, as a run-time value (see make_key)

@@ -74,6 +74,7 @@ int b200sk_gather_create(b200sk_ctx *ctx, uint64_t capacity_elems, uint8_t *hand
     MCK(cudaSetDevice(b200sk::ctx_device(ctx)));
     void *p = nullptr;
     MCK(cudaMalloc(&p, (capacity_elems ? capacity_elems : 1) * 8 + 64));
+    MCK(cudaMemset(p, 0, (capacity_elems ? capacity_elems : 1) * 8 + 64)); // (status words start out empty)
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {

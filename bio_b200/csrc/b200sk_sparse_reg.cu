@@ -757,6 +757,10 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         tile = __shfl_sync(0xffffffffu, tile, 0);
         const uint64_t item0 = tile * 32ull;
         if (item0 >= n_items) break;
+        // sharded batch: local tile -> tile of the global order (and the same for reads, 32 per tile)
+        uint64_t gtile = tile;
+        if (a.shard.n) gtile = ((tile / a.shard_chunk_tiles) * a.shard.n + a.shard.rank) * a.shard_chunk_tiles + tile % a.shard_chunk_tiles;
+        const uint64_t gread = gtile * 32ull + lane; // global index of this lane's read (one item per read here)
         const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_items - item0);
         Item it;
         item_geometry<MODE>(a, item0 + lane, n_items, it);
@@ -772,7 +776,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
             tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
         }
         if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
-        if (it.valid && it.first_chunk && a.status) a.status[it.r] = it.status;
+        if (it.valid && it.first_chunk && a.status) a.status[a.shard.n ? gread : it.r] = it.status;
         bool fast = false;
         if (bytes && span_ok) {
             mbar_wait(mbar, parity);
@@ -870,7 +874,8 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         // Ordered allocation in two halves: publish the tile's count, then -- while the tiles before this one
         // finish -- scatter the staged lists into one contiguous buffer (the codes are dead now; nothing here
         // needs the prefix), and only then wait for the prefix.
-        if (!a.unordered) lookback_publish(a.tile_state, tile, total);
+        if (a.shard.n) lookback_publish_multi(a.shard, gtile, total);
+        else if (!a.unordered) lookback_publish(a.tile_state, tile, total);
         const uint32_t OB = a.sm_tile_bytes / 12u;
         uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
         uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
@@ -893,10 +898,16 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
             unsigned long long t0 = 0;
             if (lane == 0) t0 = atomicAdd(a.unordered, (unsigned long long)total);
             tb = __shfl_sync(0xffffffffu, t0, 0);
-        } else tb = lookback_resolve(a.tile_state, tile, total, a.spin_ns);
+        } else if (a.shard.n) tb = lookback_resolve_multi(a.shard, gtile, total);
+        else tb = lookback_resolve(a.tile_state, tile, total, a.spin_ns);
         const uint64_t mine = tb + excl;
-        if (it.valid && it.first_chunk) a.out_off[it.r] = a.out_base + mine;
-        if (it.valid && it.last_item) a.out_off[a.n_reads] = a.out_base + mine + cnt;
+        if (a.shard.n) { // the root's offset table, indexed by the global read
+            if (it.valid) a.out_off[gread] = a.out_base + mine;
+            if (it.valid && gread + 1 == a.shard_n_reads) a.out_off[a.shard_n_reads] = a.out_base + mine + cnt;
+        } else {
+            if (it.valid && it.first_chunk) a.out_off[it.r] = a.out_base + mine;
+            if (it.valid && it.last_item) a.out_off[a.n_reads] = a.out_base + mine + cnt;
+        }
         const bool fits = tb + total <= a.capacity;
         if (!fits && lane == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
         if (fits && total) {
@@ -908,7 +919,21 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
                     for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
-                    if (a.out_pos)
+                    if (a.out_pos && a.pos_width == 1) {
+                        // uint8 positions leave four to a 32-bit store (128-byte runs per warp instruction instead of
+                        // 32-byte ones: what a peer-mapped out_pos needs to use its NVLink packets)
+                        uint8_t *gp = reinterpret_cast<uint8_t *>(a.out_pos) + tb + r0;
+                        const uint32_t head = min(n, (4u - (uint32_t)((uintptr_t)gp & 3u)) & 3u);
+                        if (lane < head) gp[lane] = (uint8_t)obp[lane];
+                        const uint32_t nw = (n - head) >> 2;
+                        uint32_t *gw = reinterpret_cast<uint32_t *>(gp + head);
+                        for (uint32_t j = lane; j < nw; j += 32u) {
+                            const uint32_t o = head + 4u * j;
+                            gw[j] = (obp[o] & 255u) | ((obp[o + 1] & 255u) << 8) | ((obp[o + 2] & 255u) << 16) | (obp[o + 3] << 24);
+                        }
+                        const uint32_t t0 = head + 4u * nw;
+                        if (t0 + lane < n) gp[t0 + lane] = (uint8_t)obp[t0 + lane];
+                    } else if (a.out_pos)
                         for (uint32_t i = lane; i < n; i += 32u) store_pos(a.out_pos, a.pos_width, tb + r0 + i, obp[i]);
                     __syncwarp();
                 }

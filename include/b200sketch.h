@@ -243,6 +243,32 @@ int b200sk_compact_segments(b200sk_ctx *ctx, uint64_t *d_buf, const uint64_t *se
 /* cut[n_shards + 1]: shard d owns reads [cut[d], cut[d+1]), balanced by cumulative bases (long, skewed reads). */
 void b200sk_shard_by_bases(const uint64_t *read_off, uint64_t n_reads, int n_shards, uint64_t *cut);
 
+/* The fused form: ONE ordered output chain across the GPUs.  The batch is dealt out in chunks of chunk_reads
+ * consecutive reads (chunk c belongs to rank c % n_ranks; a rank holds its chunks back to back in its own HBM),
+ * every rank runs its sketching kernel over its chunks, and the kernels' single-pass output allocation (the
+ * decoupled look-back over per-tile status words) runs across all ranks at once: a tile publishes its count into
+ * every rank's copy of the status words (n-1 posted 8-byte stores over NVLink) and polls only its own copy.  Each
+ * flush therefore knows its exact place in the ROOT's arrays and stores there directly -- d_out_val, d_out_pos,
+ * d_out_off ([n_reads_global + 1]) and d_read_status ([n_reads_global]) are the root's buffers (peer-mapped on the
+ * other ranks), indexed by the global read / element.  When every rank's kernel has finished, the root holds
+ * exactly what one GPU would have produced for the whole batch: no staging copy, no compaction, no counts to
+ * exchange.  Minimizer / syncmer batches of reads of one item each (max_read_len given, <= 384), not circular.
+ * state[r]: rank r's status-word array -- ceil(n_reads_global / 32) + 1 uint64, zeroed once when allocated, never
+ * again -- as mapped in THIS process (b200sk_gather_create / _open work for any buffer).  epoch: the same on every
+ * rank, not 0, and different mod 16384 from the step before; every rank must have finished step e before any rank
+ * enqueues step e + 1 (a stream-ordered barrier of the host's choice). */
+typedef struct b200sk_shard_spec {
+    int32_t rank, n_ranks;   /* 1 <= n_ranks <= 8 */
+    uint32_t chunk_reads;    /* a multiple of 32 */
+    uint32_t epoch;
+    uint64_t n_reads_global;
+    uint64_t *state[8];
+} b200sk_shard_spec;
+int b200sk_enqueue_device_sharded(b200sk_ctx *ctx, const b200sk_params *p, const b200sk_shard_spec *spec,
+                                  const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                                  uint64_t *d_out_val, uint32_t *d_out_pos, uint64_t *d_out_off, int32_t *d_read_status,
+                                  uint64_t capacity, void *stream, uint32_t *d_flags);
+
 /* One process, several devices: what SURVEY.md 8b calls b200sk_create(ctx**, devices, n).  One context, stream and
  * worker thread per device; b200sk_group_run has the contract of b200sk_run (host pointers in, library-owned pinned
  * arrays in read order out, valid until the next call on the group) with the reads sharded over every device of

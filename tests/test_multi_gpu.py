@@ -35,7 +35,7 @@ def test_shard_by_bases_host_logic():
             b = bench.shard_bounds(n, world)
             assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
     b = bench.shard_bounds(100_000_000, 8)
-    assert all(x % bench.BLOCK == 0 for x in b)
+    assert all(x % bench.BLOCK == 0 for x in b[:-1])
 
 
 def _devices():
@@ -157,4 +157,71 @@ def test_ipc_gather_two_processes():
     got = _view(gaddr, c0 + c1, dev).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, ref["val"])
     ctx.gather_close(gaddr, True)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,chunk", [("minimizer", 64), ("minimizer", 1024), ("syncmer", 96)])
+def test_sharded_chain_two_processes(mode, chunk):
+    """b200sk_enqueue_device_sharded: two ranks (two processes, two GPUs) share ONE output chain -- their kernels'
+    look-back runs through both GPUs' status words and every flush stores at its exact place in the root's arrays.
+    The root must end up holding exactly the single-GPU output (values, uint8 positions, offsets, statuses)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (two kernels that wait for each other must run at the same time)")
+    dev = torch.device("cuda", 0)
+    n_total = 20000 + 17
+    b, o = synth.uniform_reads(n_total, 150, 91)
+    b = b.copy()
+    b[150 * 40:150 * 40 + 30] = ord("N")  # a tile that leaves the all-ACGT fast path
+    if mode == "syncmer":
+        p = cabi.make_params(cabi.MODE_SYNCMER, 21, s=11, max_read_len=150, pos_width=1)
+        ref = oracle.run_batch(b, o, oracle.MODE_SYNCMER, k=21, s=11, threads=8)
+    else:
+        p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150, pos_width=1)
+        ref = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=21, w=11, threads=8)
+    ctx = cabi.Context(0)
+    cap = int(cabi.lib().b200sk_output_bound(C.byref(p), n_total * 150, n_total, 0))
+    n_tiles = (n_total + 31) // 32
+    bufs = [ctx.gather_create(cap), ctx.gather_create(cap // 8 + 8), ctx.gather_create(n_total + 1),
+            ctx.gather_create(n_total // 2 + 8), ctx.gather_create(n_tiles + 1)]
+    (hv, val), (hp, pos), (ho, off), (hs, status), (ht, state0) = bufs
+    child = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_sharded_child.py"), "1", str(n_total), str(chunk),
+                              mode, hv.hex(), hp.hex(), ho.hex(), hs.hex(), ht.hex(), str(cap)],
+                             stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    line = child.stdout.readline()
+    assert line.startswith("HANDLE"), child.stderr.read()[-2000:]
+    state1 = ctx.gather_open(bytes.fromhex(line.split()[1]))
+    mine = [c for c in range((n_total + chunk - 1) // chunk) if c % 2 == 0]
+    lb = np.concatenate([b[c * chunk * 150:min(n_total, (c + 1) * chunk) * 150] for c in mine] + [np.zeros(64, np.uint8)])
+    n = (len(lb) - 64) // 150
+    bases = torch.from_numpy(lb).to(dev)
+    loff = torch.arange(n + 1, dtype=torch.int64, device=dev) * 150
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    child.stdin.write("GO\n")
+    child.stdin.flush()
+    for epoch in (1, 2):
+        _view(val, cap, dev).fill_(-1)
+        torch.cuda.synchronize()
+        spec = cabi.ShardSpec()
+        spec.rank, spec.n_ranks, spec.chunk_reads, spec.epoch, spec.n_reads_global = 0, 2, chunk, epoch, n_total
+        spec.state[0], spec.state[1] = state0, state1
+        ctx.enqueue_device_sharded(p, spec, bases, loff, n * 150, val, pos, off, status, cap, flags)
+        torch.cuda.synchronize()
+        assert child.stdout.readline().startswith("DONE"), child.stderr.read()[-2000:]
+        assert int(flags.item()) == 0
+        total = len(ref["val"])
+        g_off = _view(off, n_total + 1, dev).cpu().numpy().view(np.uint64)
+        assert np.array_equal(g_off, ref["off"])
+        assert np.array_equal(_view(val, total, dev).cpu().numpy().view(np.uint64), ref["val"])
+        g_pos = _view(pos, (total + 7) // 8, dev).cpu().numpy().view(np.uint8)[:total]
+        assert np.array_equal(g_pos, ref["pos"].astype(np.uint8))
+        g_st = _view(status, (n_total + 1) // 2, dev).cpu().numpy().view(np.int32)[:n_total]
+        assert np.array_equal(g_st, ref["status"])
+        child.stdin.write("NEXT\n")
+        child.stdin.flush()
+    assert child.wait(timeout=120) == 0, child.stderr.read()[-2000:]
+    ctx.gather_close(state1, False)
+    for _, a in bufs:
+        ctx.gather_close(a, True)
     ctx.close()
