@@ -65,6 +65,7 @@ class FastxInfo(C.Structure):
         ("max_read_len", C.c_uint32), ("reserved", C.c_uint32),
         ("d_bases", C.c_void_p), ("d_read_off", C.c_void_p), ("d_rec_off", C.c_void_p),
         ("d_qual_off", C.c_void_p), ("d_line_off", C.c_void_p),
+        ("alphabet", C.c_int32), ("reserved2", C.c_int32), ("first_invalid", C.c_uint64), ("d_invalid", C.c_void_p),
     ]
 
 
@@ -454,7 +455,9 @@ class Context:
                     read_off=grab(info.d_read_off, n + 1, np.uint64),
                     rec_off=grab(info.d_rec_off, n + 1, np.uint64),
                     qual_off=grab(info.d_qual_off, n, np.uint64),
-                    line_off=grab(info.d_line_off, int(info.n_lines) + 1, np.uint64))
+                    line_off=grab(info.d_line_off, int(info.n_lines) + 1, np.uint64),
+                    alphabet=int(info.alphabet), first_invalid=int(info.first_invalid),
+                    invalid=grab(info.d_invalid, n, np.uint8))
 
     def run_fastx(self, params, text, fmt=0, final=True, copy=True):
         """Host entry point: FASTA/FASTQ text (bytes / uint8 array) in, the sketches of its records out."""

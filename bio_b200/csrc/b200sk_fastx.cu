@@ -15,10 +15,10 @@
 //     that starts a quality line is not a record start because the record is then not complete (:328-340);
 //   * a last record without a final '\n' is complete (:352-364); empty lines after the last record are not
 //     a record.
-// Scope of this implementation: FASTQ records of exactly four lines (header, sequence, '+', quality -- what
-// every sequencer writes; multi-line FASTQ makes the chunk fail with B200SK_ERR_BAD_FASTQ instead of being
-// mis-parsed) and FASTA with any line structure.  Alphabet guessing / per-letter validation (reader.go:
-// 430-452) stays with the caller.
+// FASTQ records of exactly four lines (what every sequencer writes) take the parallel path (k_fq_scan); a chunk that
+// is not made of such records is parsed by the reference's general rule (k_fq_general: multi-line sequence and
+// quality, blank lines between records).  The alphabet is guessed from the first record and every letter checked
+// against it (reader.go:430-452), reported per record instead of ending the stream.
 //
 // Kernels (all memory-bound, one pass each over what they touch):
 //   k_fx_detect   first record byte and format
@@ -27,7 +27,9 @@
 //   k_fq_scan     FASTQ: per record validate + sequence length -> read_off / rec_off / qual_off (look-back scan),
 //                 then the sequence lines -> packed bases in the same pass
 //   k_fa_scan     FASTA: per line header flag + sequence bytes -> out_pos per line, read_off / rec_off per record
-//   k_fa_copy     FASTA sequence lines -> packed bases (a warp per 32 lines)
+//   k_fa_copy     FASTA (and general FASTQ) sequence lines -> packed bases (a warp per 32 lines)
+//   k_fq_general  FASTQ of any line structure: one warp walks the line table (fallback of k_fq_scan)
+//   k_fx_letters / k_fx_validate   alphabet guess from the first record, per-record validity flags
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -83,7 +85,7 @@ struct PinBuf {
 };
 
 struct FxState {
-    Buf meta, lines, outpos, bases, read_off, rec_off, qual_off, state_a, state_b;
+    Buf meta, lines, outpos, bases, read_off, rec_off, qual_off, state_a, state_b, invalid;
     Buf text;                                   // host path: the chunk in HBM
     Buf o_val, o_pos, o_off, o_status;          // host path: sketch outputs in HBM
     PinBuf h_val, h_pos, h_off, h_status, h_meta; // host path: what the caller reads
@@ -91,7 +93,9 @@ struct FxState {
 
 // meta words (u64): 0 format, 1 start0, 2 newlines, 3 line-initial '>' count, 4 last byte, 5 ticket,
 // 6 error record (min), 7 max sequence length, 8 total bases, 9 records (FASTA), 10 flags, 11 ticket 2
-enum { M_FORMAT = 0, M_START, M_NL, M_HDR, M_LAST, M_TICKET, M_BADREC, M_MAXLEN, M_TOTAL, M_NREC, M_FLAGS, M_TICKET2, M_WORDS = 16 };
+// 12 text offset where the records complete in this chunk end (general FASTQ), 13 first record with an invalid letter,
+// 16..19 the 256 bits 'byte value occurs in the first record' (alphabet guess)
+enum { M_FORMAT = 0, M_START, M_NL, M_HDR, M_LAST, M_TICKET, M_BADREC, M_MAXLEN, M_TOTAL, M_NREC, M_FLAGS, M_TICKET2, M_CONSUMED, M_INVALID, M_ABITS = 16, M_WORDS = 24 };
 
 // ------------------------------------------------------------------ kernels
 // reader.go:271-304: the first byte that is not '\n' decides
@@ -406,6 +410,141 @@ __global__ void __launch_bounds__(256) k_fa_copy(const uint8_t *__restrict__ t, 
     }
 }
 
+// FASTQ with any line structure (multi-line sequence / quality, blank lines between records): the reference's own
+// rule, reader.go:308-345 + parseRecord :396-417 -- a record runs from its header to the next line-initial '@' at
+// which the quality is exactly as long as the sequence; an '@' line met earlier belongs to the record (its quality
+// is still shorter), one met later is ErrBadFASTQFormat; inside a record everything before the first non-empty '+'
+// line is sequence, everything after it quality.  The decision at every '@' line depends on all lines before it, so
+// ONE warp walks the line table: 32 lines per trip (starts, lengths and first bytes fetched by the 32 lanes at
+// once), then the state machine over those 32 in registers.  It is the fallback of k_fq_scan -- four-line records
+// never come here.
+// Outputs: out_pos per line in k_fa_copy's format (sequence lines with their place in `bases`, every other line
+// flagged not-to-copy), read_off / rec_off / qual_off per record, meta: records, bases, longest sequence, first bad
+// record, the text offset where the records that are complete in this chunk end.
+__global__ void __launch_bounds__(32) k_fq_general(const uint8_t *__restrict__ t, const uint64_t *__restrict__ L,
+                                                   uint64_t nlines, uint64_t n_bytes, int final, unsigned long long *meta,
+                                                   uint64_t *outpos, uint64_t *read_off, uint64_t *rec_off,
+                                                   uint64_t *qual_off) {
+    const uint32_t lane = threadIdx.x;
+    // warp-uniform state
+    int phase = 0;                 // 0: before a record, 1: sequence lines, 2: quality lines
+    uint64_t rec = 0, total = 0;   // records accepted, their bases
+    uint64_t p_hdr = 0, p_qual = 0; // the pending record: header line start, first quality line start
+    uint64_t seq_len = 0, qual_len = 0, max_len = 0;
+    bool bad = false, have_qual = false;
+    auto accept = [&]() { // the pending record is complete: its sequence lines were placed at total ..
+        if (lane == 0) { read_off[rec] = total; rec_off[rec] = p_hdr; qual_off[rec] = p_qual; }
+        max_len = seq_len > max_len ? seq_len : max_len;
+        total += seq_len;
+        rec++;
+    };
+    for (uint64_t b = 0; b < nlines && !bad; b += 32) {
+        const uint64_t i = b + lane;
+        uint64_t s = 0, nx = 0;
+        uint32_t len = 0, c0 = 0;
+        if (i < nlines) {
+            s = L[i];
+            nx = L[i + 1];
+            len = line_len(t, s, nx);
+            c0 = nx - 1 > s ? t[s] : 0u; // first byte of a non-empty line
+        }
+        uint64_t my_out = 1ull << 63; // not a sequence line
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, nlines - b);
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t lj = __shfl_sync(0xffffffffu, len, j), cj = __shfl_sync(0xffffffffu, c0, j);
+            const uint64_t sj = __shfl_sync(0xffffffffu, s, j), nj = __shfl_sync(0xffffffffu, nx, j);
+            if (phase != 0 && cj == '@') { // a candidate record start (reader.go:328-340)
+                if (seq_len == qual_len) { accept(); phase = 0; }
+                else if (qual_len > seq_len) { bad = true; break; }
+                // else the quality is still short: this line belongs to the record
+            }
+            if (phase == 0) {
+                if (cj == '@') { phase = 1; p_hdr = sj; p_qual = 0; have_qual = false; seq_len = 0; qual_len = 0; }
+                else if (cj != 0) { bad = true; break; } // only empty lines may come before a record
+            } else if (phase == 1) {
+                if (lj > 0 && cj == '+') phase = 2; // (:399) quality from the next line on
+                else {
+                    if (lane == j) my_out = (total + seq_len) | ((uint64_t)((uint32_t)(nj - 1 - sj) - lj) << 62);
+                    seq_len += lj;
+                }
+            } else {
+                if (!have_qual) { have_qual = true; p_qual = sj; } // the first quality line (0: the record has none)
+                qual_len += lj;
+            }
+        }
+        if (i < nlines) outpos[i] = my_out;
+    }
+    uint64_t consumed = n_bytes;
+    if (!bad && phase != 0) {
+        if (final) { // the text ends here: the last record must be complete (reader.go:352-364)
+            if (seq_len == qual_len) accept();
+            else bad = true;
+        } else consumed = p_hdr; // it continues in the next chunk
+    }
+    if (lane == 0) {
+        read_off[rec] = total;
+        meta[M_NREC] = rec;
+        meta[M_TOTAL] = total;
+        meta[M_MAXLEN] = max_len;
+        meta[M_BADREC] = bad ? rec : ~0ULL;
+        meta[M_CONSUMED] = consumed;
+    }
+}
+
+// ------------------------------------------------------------------ alphabet (reader.go:430-452)
+// The reference guesses the alphabet from the first record (seq.GuessAlphabetLessConservatively over its first
+// 10 000 letters, seq/alphabet.go:411-452) and then checks every letter of every record against it
+// (Alphabet.IsValid, :234-300; on by default, seq/seq.go:37).  Here: the set of byte values that occur in the first
+// record's prefix, and a pass over the packed bases that flags the records holding a letter outside the set given.
+__global__ void __launch_bounds__(256) k_fx_letters(const uint8_t *__restrict__ bases, uint64_t n, unsigned long long *bits) {
+    __shared__ unsigned int w[8];
+    if (threadIdx.x < 8) w[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t b = bases[i];
+        atomicOr(&w[b >> 5], 1u << (b & 31u));
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) bits[threadIdx.x] = (unsigned long long)w[2 * threadIdx.x] | ((unsigned long long)w[2 * threadIdx.x + 1] << 32);
+}
+__global__ void __launch_bounds__(256) k_fx_validate(const uint8_t *__restrict__ bases, uint64_t n,
+                                                     const uint64_t *__restrict__ read_off, uint64_t nrec,
+                                                     unsigned long long v0, unsigned long long v1, unsigned long long v2,
+                                                     unsigned long long v3, uint8_t *__restrict__ invalid,
+                                                     unsigned long long *first_invalid) {
+    __shared__ uint8_t ok[256];
+    {
+        const uint32_t b = threadIdx.x;
+        const unsigned long long word = b < 64 ? v0 : b < 128 ? v1 : b < 192 ? v2 : v3;
+        ok[b] = (uint8_t)((word >> (b & 63u)) & 1ull);
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 16;
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i0 < n; i0 += stride) {
+        uint32_t badmask = 0;
+        if (i0 + 16 <= n) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(bases + i0);
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 16; q++) badmask |= (ok[(ws[q >> 2] >> (8 * (q & 3))) & 255u] ? 0u : 1u) << q;
+        } else {
+            for (uint32_t q = 0; i0 + q < n; q++) badmask |= (ok[bases[i0 + q]] ? 0u : 1u) << q;
+        }
+        while (badmask) { // rare: find the record of every offending byte
+            const uint32_t q = __ffs(badmask) - 1;
+            badmask &= badmask - 1;
+            const uint64_t at = i0 + q;
+            uint64_t lo = 0, hi = nrec; // largest r with read_off[r] <= at
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (read_off[mid] <= at) lo = mid; else hi = mid;
+            }
+            invalid[lo] = 1;
+            atomicMin(first_invalid, (unsigned long long)lo);
+        }
+    }
+}
+
 int fail(b200sk_ctx *ctx, cudaError_t e, const char *what) {
     char buf[256];
     snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
@@ -417,6 +556,40 @@ int fail(b200sk_ctx *ctx, cudaError_t e, const char *what) {
         cudaError_t _e = (call);                           \
         if (_e != cudaSuccess) return fail(ctx, _e, #call); \
     } while (0)
+
+// seq/alphabet.go:353-399: all letters (letters + gap + ambiguous) of the reference's alphabets, as 256-bit sets
+struct Bits256 { unsigned long long w[4]; };
+Bits256 set_of(const char *letters) {
+    Bits256 b = {{0, 0, 0, 0}};
+    for (const unsigned char *c = (const unsigned char *)letters; *c; c++) b.w[*c >> 6] |= 1ull << (*c & 63);
+    return b;
+}
+bool subset(const Bits256 &a, const Bits256 &b) {
+    for (int i = 0; i < 4; i++)
+        if (a.w[i] & ~b.w[i]) return false;
+    return true;
+}
+Bits256 letters_of(int alphabet) {
+    switch (alphabet) {
+    case B200SK_ALPHABET_DNA: return set_of("acgtACGT -.nN");
+    case B200SK_ALPHABET_DNA_REDUNDANT: return set_of("acgtryswkmbdhvACGTRYSWKMBDHV -.nN");
+    case B200SK_ALPHABET_RNA: return set_of("acguACGU -.nN");
+    case B200SK_ALPHABET_RNA_REDUNDANT: return set_of("acguryswkmbdhvACGURYSWKMBDHV -.nN");
+    case B200SK_ALPHABET_PROTEIN: return set_of("abcdefghijklmnopqrstuvwyzABCDEFGHIJKLMNOPQRSTUVWYZ -xX*_.");
+    default: { Bits256 all = {{~0ull, ~0ull, ~0ull, ~0ull}}; return all; }
+    }
+}
+// seq.GuessAlphabetLessConservatively (seq/alphabet.go:411-452): first match in the order DNA, RNA, DNAredundant,
+// RNAredundant, Protein, else Unlimit; DNA and RNA are widened to their redundant forms; no letters: Unlimit.
+int guess_alphabet(const Bits256 &present) {
+    if (!(present.w[0] | present.w[1] | present.w[2] | present.w[3])) return B200SK_ALPHABET_UNLIMIT;
+    if (subset(present, letters_of(B200SK_ALPHABET_DNA))) return B200SK_ALPHABET_DNA_REDUNDANT;
+    if (subset(present, letters_of(B200SK_ALPHABET_RNA))) return B200SK_ALPHABET_RNA_REDUNDANT;
+    if (subset(present, letters_of(B200SK_ALPHABET_DNA_REDUNDANT))) return B200SK_ALPHABET_DNA_REDUNDANT;
+    if (subset(present, letters_of(B200SK_ALPHABET_RNA_REDUNDANT))) return B200SK_ALPHABET_RNA_REDUNDANT;
+    if (subset(present, letters_of(B200SK_ALPHABET_PROTEIN))) return B200SK_ALPHABET_PROTEIN;
+    return B200SK_ALPHABET_UNLIMIT;
+}
 
 FxState *state_of(b200sk_ctx *ctx) {
     void **slot = ctx_fx_slot(ctx);
@@ -430,7 +603,7 @@ void fx_free(void *p) {
     FxState *s = static_cast<FxState *>(p);
     if (!s) return;
     for (Buf *b : {&s->meta, &s->lines, &s->outpos, &s->bases, &s->read_off, &s->rec_off, &s->qual_off, &s->state_a,
-                   &s->state_b, &s->text, &s->o_val, &s->o_pos, &s->o_off, &s->o_status})
+                   &s->state_b, &s->invalid, &s->text, &s->o_val, &s->o_pos, &s->o_off, &s->o_status})
         b->release();
     for (PinBuf *b : {&s->h_val, &s->h_pos, &s->h_off, &s->h_status, &s->h_meta}) b->release();
     delete s;
@@ -446,8 +619,13 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
                               void *stream, b200sk_fastx_info *info) {
     if (!ctx || !info || (n_bytes && !d_text)) return B200SK_ERR_BAD_ARG;
     if (((uintptr_t)d_text & 15u) != 0) return B200SK_ERR_BAD_ARG;
+    const int alpha_in = (format >> 8) & 0xff; // a chunk that continues a file: 1 + the alphabet guessed from its first record
+    format &= 0xff;
     if (format != 0 && format != B200SK_FASTX_FASTA && format != B200SK_FASTX_FASTQ) return B200SK_ERR_BAD_ARG;
+    if (alpha_in > B200SK_ALPHABET_PROTEIN + 1) return B200SK_ERR_BAD_ARG;
     memset(info, 0, sizeof(*info));
+    info->first_invalid = ~0ULL;
+    info->alphabet = alpha_in ? alpha_in - 1 : B200SK_ALPHABET_UNLIMIT;
     FCK(cudaSetDevice(ctx_device(ctx)));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx_stream(ctx);
     FxState *fx = state_of(ctx);
@@ -524,22 +702,51 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
         FCK(cudaStreamSynchronize(st));
         if (hm[M_BADREC] != ~0ULL) {
-            info->status = B200SK_ERR_BAD_FASTQ;
-            info->bad_record = hm[M_BADREC];
-            return B200SK_ERR_BAD_FASTQ;
-        }
-        const uint64_t total = nrec ? hm[M_TOTAL] : 0;
-        info->n_records = nrec;
-        info->n_bases = total;
-        info->max_read_len = (uint32_t)hm[M_MAXLEN];
-        if (final) info->consumed = n_bytes;
-        else {
-            uint64_t c = 0;
-            if (nrec) {
-                FCK(cudaMemcpyAsync(&c, L + 4 * nrec, 8, cudaMemcpyDeviceToHost, st));
-                FCK(cudaStreamSynchronize(st));
-            } else c = hm[M_START];
-            info->consumed = std::min<uint64_t>(c, n_bytes);
+            // not four lines per record: the reference's general rule (multi-line records, blank lines between
+            // records), one warp over the line table, then the FASTA copy kernel for the sequence lines
+            FCK(fx->read_off.reserve((nlines + 2) * 8));
+            FCK(fx->rec_off.reserve((nlines + 2) * 8));
+            FCK(fx->qual_off.reserve((nlines + 2) * 8));
+            FCK(fx->outpos.reserve((nlines + 2) * 8));
+            k_fq_general<<<1, 32, 0, st>>>(d_text, L, nlines, n_bytes, final, meta, (uint64_t *)fx->outpos.p,
+                                           (uint64_t *)fx->read_off.p, (uint64_t *)fx->rec_off.p,
+                                           (uint64_t *)fx->qual_off.p);
+            ctx_add_launches(ctx, 1);
+            FCK(cudaMemcpyAsync(hm, meta, M_WORDS * 8, cudaMemcpyDeviceToHost, st));
+            FCK(cudaStreamSynchronize(st));
+            if (hm[M_BADREC] != ~0ULL) {
+                info->status = B200SK_ERR_BAD_FASTQ;
+                info->bad_record = hm[M_BADREC];
+                return B200SK_ERR_BAD_FASTQ;
+            }
+            nrec = hm[M_NREC];
+            const uint64_t total = hm[M_TOTAL];
+            FCK(fx->bases.reserve(total + 64));
+            if (nlines && total) {
+                const unsigned cb = (unsigned)std::min<uint64_t>((nlines + 255) / 256, 148ull * 16);
+                // lines of the record that continues in the next chunk lie at or behind `consumed`: not copied
+                k_fa_copy<<<cb, 256, 0, st>>>(d_text, L, (const uint64_t *)fx->outpos.p, nlines,
+                                              final ? n_bytes + 2 : hm[M_CONSUMED], (uint8_t *)fx->bases.p);
+                ctx_add_launches(ctx, 1);
+            }
+            info->n_records = nrec;
+            info->n_bases = total;
+            info->max_read_len = (uint32_t)hm[M_MAXLEN];
+            info->consumed = final ? n_bytes : std::min<uint64_t>(hm[M_CONSUMED], n_bytes);
+        } else {
+            const uint64_t total = nrec ? hm[M_TOTAL] : 0;
+            info->n_records = nrec;
+            info->n_bases = total;
+            info->max_read_len = (uint32_t)hm[M_MAXLEN];
+            if (final) info->consumed = n_bytes;
+            else {
+                uint64_t c = 0;
+                if (nrec) {
+                    FCK(cudaMemcpyAsync(&c, L + 4 * nrec, 8, cudaMemcpyDeviceToHost, st));
+                    FCK(cudaStreamSynchronize(st));
+                } else c = hm[M_START];
+                info->consumed = std::min<uint64_t>(c, n_bytes);
+            }
         }
         info->d_qual_off = (uint64_t *)fx->qual_off.p;
     } else {
@@ -586,6 +793,36 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         info->d_qual_off = nullptr;
     }
     FCK(cudaMemcpyAsync((uint64_t *)fx->rec_off.p + info->n_records, &info->consumed, 8, cudaMemcpyHostToDevice, st));
+    // reader.go:430-452: alphabet of the file (guessed from its first record unless the caller passes it on from an
+    // earlier chunk), then every letter of every record checked against it
+    if (info->n_records) {
+        if (!alpha_in) {
+            uint64_t r1 = 0;
+            FCK(cudaMemcpyAsync(&r1, (uint64_t *)fx->read_off.p + 1, 8, cudaMemcpyDeviceToHost, st));
+            FCK(cudaStreamSynchronize(st));
+            k_fx_letters<<<1, 256, 0, st>>>((const uint8_t *)fx->bases.p, std::min<uint64_t>(r1, 10000), meta + M_ABITS);
+            ctx_add_launches(ctx, 1);
+            Bits256 present;
+            FCK(cudaMemcpyAsync(present.w, meta + M_ABITS, 32, cudaMemcpyDeviceToHost, st));
+            FCK(cudaStreamSynchronize(st));
+            // (a byte >= 0x80 makes the reference's ASCII set construction give up: no alphabet fits -> Unlimit)
+            info->alphabet = (present.w[2] | present.w[3]) ? B200SK_ALPHABET_UNLIMIT : guess_alphabet(present);
+        }
+        FCK(fx->invalid.reserve(info->n_records + 16));
+        FCK(cudaMemsetAsync(fx->invalid.p, 0, info->n_records, st));
+        if (info->alphabet != B200SK_ALPHABET_UNLIMIT && info->n_bases) {
+            const unsigned long long none = ~0ULL;
+            FCK(cudaMemcpyAsync(meta + M_INVALID, &none, 8, cudaMemcpyHostToDevice, st));
+            const Bits256 ok = letters_of(info->alphabet);
+            const unsigned vb = (unsigned)std::min<uint64_t>((info->n_bases / 16 + 255) / 256 + 1, 148ull * 8);
+            k_fx_validate<<<vb, 256, 0, st>>>((const uint8_t *)fx->bases.p, info->n_bases, (const uint64_t *)fx->read_off.p,
+                                              info->n_records, ok.w[0], ok.w[1], ok.w[2], ok.w[3], (uint8_t *)fx->invalid.p,
+                                              meta + M_INVALID);
+            ctx_add_launches(ctx, 1);
+            FCK(cudaMemcpyAsync(&info->first_invalid, meta + M_INVALID, 8, cudaMemcpyDeviceToHost, st));
+        }
+        info->d_invalid = (uint8_t *)fx->invalid.p;
+    }
     FCK(cudaStreamSynchronize(st));
     info->n_lines = nlines;
     info->d_bases = (uint8_t *)fx->bases.p;
@@ -721,7 +958,9 @@ struct b200sk_fxstream {
             lk.lock();
             if (rc || final) exhausted = true;
             else {
-                if (!format) format = s.info.format;
+                // later chunks continue the same file: its format, and the alphabet its first record decided
+                if (!(format & 0xff)) format = (format & ~0xff) | s.info.format;
+                if (!(format >> 8)) format |= (s.info.alphabet + 1) << 8;
                 next_start = start + s.info.consumed;
                 next_index = j + 1;
                 start_ready = true;

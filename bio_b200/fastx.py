@@ -30,15 +30,24 @@ class ErrBadFASTQFormat(Exception):  # seqio/fastx/reader.go:19
         super().__init__("fastx: bad fastq format")
 
 
-class Record:
-    """seqio/fastx/records.go:13-18 (ID, Name, Desc, Seq); Seq.Seq / Seq.Qual flattened to seq / qual."""
-    __slots__ = ("ID", "Name", "Desc", "Seq", "Qual")
+ALPHABET_NAMES = {cabi.ALPHABET_DNA_REDUNDANT: "DNAredundant", cabi.ALPHABET_DNA: "DNA",
+                  cabi.ALPHABET_RNA_REDUNDANT: "RNAredundant", cabi.ALPHABET_RNA: "RNA",
+                  cabi.ALPHABET_UNLIMIT: "Unlimit", cabi.ALPHABET_PROTEIN: "Protein"}  # seq/alphabet.go:353-399
 
-    def __init__(self, name, seq, qual):
+
+class Record:
+    """seqio/fastx/records.go:13-18 (ID, Name, Desc, Seq); Seq.Seq / Seq.Qual flattened to seq / qual.
+    Err: what Read() returns next to the record in the reference -- None, or the alphabet check's complaint
+    (parseRecord, reader.go:450-452: `seq: invalid <alphabet> letter`)."""
+    __slots__ = ("ID", "Name", "Desc", "Seq", "Qual", "Alphabet", "Err")
+
+    def __init__(self, name, seq, qual, alphabet=None, err=None):
         self.Name = name
         self.ID, self.Desc = parse_head_id_and_desc(name)
         self.Seq = seq
         self.Qual = qual
+        self.Alphabet = alphabet
+        self.Err = err
 
 
 def parse_head_id_and_desc(head):
@@ -85,6 +94,7 @@ class Reader:
         self._carry = b""
         self._eof = False
         self._format = 0
+        self._alphabet = None  # guessed from the first record of the file (reader.go:430-435), then kept
         self.IsFastq = False
         self._pending = iter(())
 
@@ -103,7 +113,8 @@ class Reader:
             host[:n] = np.frombuffer(text, dtype=np.uint8)
             d_text = torch.from_numpy(host).to(self._dev)
             try:
-                info = self._ctx.fastx_parse_device(d_text, n, self._format, final=self._eof)
+                fmt = self._format | ((self._alphabet + 1) << 8 if self._alphabet is not None else 0)
+                info = self._ctx.fastx_parse_device(d_text, n, fmt, final=self._eof)
             except cabi.SketchError as e:
                 if e.code == cabi.ERR_NOT_FASTX:
                     raise ErrNotFASTXFormat() from None
@@ -111,6 +122,8 @@ class Reader:
                     raise ErrBadFASTQFormat() from None
                 raise
             self._format = int(info.format) or self._format
+            if self._alphabet is None and int(info.n_records):
+                self._alphabet = int(info.alphabet)
             self.IsFastq = self._format == cabi.FASTX_FASTQ
             used = int(info.consumed)
             if not self._eof and used == 0 and len(fresh) == 0:
@@ -130,6 +143,7 @@ class Reader:
             n = r["n_records"]
             ro, rc, qo = r["read_off"], r["rec_off"], r["qual_off"]
             bases = r["bases"].tobytes()
+            alpha = ALPHABET_NAMES.get(r["alphabet"], "Unlimit")
             for i in range(n):
                 start = int(rc[i])
                 nl = text.find(b"\n", start)
@@ -139,7 +153,18 @@ class Reader:
                 if self.IsFastq:
                     q = int(qo[i])
                     qual = text[q:q + len(seq)]
-                yield Record(name, seq, qual)
+                    if b"\n" in qual or b"\r" in qual:  # multi-line quality: its lines joined (reader.go:403-410)
+                        parts, have = [], 0
+                        while have < len(seq) and q < len(text):
+                            e = text.find(b"\n", q)
+                            e = len(text) if e < 0 else e + 1
+                            ln = _line(text, q, e)
+                            parts.append(ln)
+                            have += len(ln)
+                            q = e
+                        qual = b"".join(parts)
+                err = "seq: invalid %s letter" % alpha if r["invalid"][i] else None
+                yield Record(name, seq, qual, alpha, err)
 
     def Read(self):
         """One record, or raises EOFError (io.EOF)."""

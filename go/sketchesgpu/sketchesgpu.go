@@ -10,7 +10,8 @@
 //	    for _, rec := range chunk.Data { b.Add(rec.Seq) }
 //	res, _ := b.MinimizerSketch(k, w, false)  // ONE cgo call: the whole batch is sketched on the GPU
 //	for i := range chunk.Data {
-//	    sk := res.Sketch(i)                   // *sketchesgpu.Sketch with the reference's method set
+//	    sk, err := res.Sketch(i)              // *sketchesgpu.Sketch with the reference's method set, or the
+//	    if err != nil { continue }            // error NewMinimizerSketch returns for that record (ErrShortSeq)
 //	    for { v, ok := sk.Next(); if !ok { break }; _ = sk.Index() }
 //	}
 //
@@ -75,7 +76,10 @@ func codeToError(rc C.int) error {
 }
 
 // Context owns one GPU (one per goroutine; not goroutine-safe, like the reference's iterators).
-type Context struct{ h *C.b200sk_ctx }
+type Context struct {
+	h   *C.b200sk_ctx
+	gen uint64 // runs so far: a Result is valid while its gen equals this
+}
 
 // NewContext binds CUDA device `device`.  There is no CPU fallback: without a device this fails.
 func NewContext(device int) (*Context, error) {
@@ -83,7 +87,7 @@ func NewContext(device int) (*Context, error) {
 	if rc := C.b200sk_create(&h, C.int(device)); rc != 0 {
 		return nil, codeToError(rc)
 	}
-	return &Context{h}, nil
+	return &Context{h: h}, nil
 }
 
 // Close releases the device buffers.
@@ -106,8 +110,33 @@ func NewBatch(ctx *Context, capBytes int) *Batch {
 		off: []C.uint64_t{0}, alpha: C.B200SK_ALPHABET_DNA_REDUNDANT}
 }
 
+// ErrMixedAlphabet: the records of one batch share one b200sk_params, so they must share one alphabet.
+var ErrMixedAlphabet = errors.New("sketchesgpu: records with different alphabets in one batch")
+
+func alphabetCode(a *seq.Alphabet) C.int32_t {
+	switch a {
+	case seq.DNA:
+		return C.B200SK_ALPHABET_DNA
+	case seq.RNA:
+		return C.B200SK_ALPHABET_RNA
+	case seq.RNAredundant:
+		return C.B200SK_ALPHABET_RNA_REDUNDANT
+	case seq.Unlimit:
+		return C.B200SK_ALPHABET_UNLIMIT
+	case seq.Protein:
+		return C.B200SK_ALPHABET_PROTEIN
+	}
+	return C.B200SK_ALPHABET_DNA_REDUNDANT
+}
+
 // Add appends one sequence (the bytes are copied: fastx.Reader reuses its buffer, reader.go:229-232).
-func (b *Batch) Add(s *seq.Seq) {
+func (b *Batch) Add(s *seq.Seq) error {
+	a := alphabetCode(s.Alphabet)
+	if len(b.off) == 1 {
+		b.alpha = a
+	} else if a != b.alpha {
+		return ErrMixedAlphabet
+	}
 	n := len(s.Seq)
 	if b.nBases+n+64 > b.cap {
 		ncap := 2*(b.nBases+n) + 64
@@ -124,18 +153,7 @@ func (b *Batch) Add(s *seq.Seq) {
 	if n > b.maxLen {
 		b.maxLen = n
 	}
-	switch s.Alphabet {
-	case seq.DNA:
-		b.alpha = C.B200SK_ALPHABET_DNA
-	case seq.RNA:
-		b.alpha = C.B200SK_ALPHABET_RNA
-	case seq.RNAredundant:
-		b.alpha = C.B200SK_ALPHABET_RNA_REDUNDANT
-	case seq.Unlimit:
-		b.alpha = C.B200SK_ALPHABET_UNLIMIT
-	case seq.Protein:
-		b.alpha = C.B200SK_ALPHABET_PROTEIN
-	}
+	return nil
 }
 
 // Reset empties the batch, keeping the buffer.
@@ -144,22 +162,34 @@ func (b *Batch) Reset() { b.nBases, b.off, b.maxLen = 0, b.off[:1], 0 }
 // Free releases the pinned buffer.
 func (b *Batch) Free() { C.b200sk_free_pinned(b.bases); b.bases = nil }
 
-// Result holds the library-owned output arrays of one run (valid until the next run on the context).
+// Result holds the library-owned output arrays of one run.  They alias memory the NEXT run on the same context
+// overwrites: every Result remembers the context's run counter and its accessors panic once it is stale.
 type Result struct {
 	val    []uint64
 	pos    []uint32
 	off    []uint64
 	status []int32
+	mode   C.int32_t
+	ctx    *Context
+	gen    uint64
+}
+
+func (r *Result) check() {
+	if r.ctx != nil && r.ctx.gen != r.gen {
+		panic("sketchesgpu: Result used after a later run on the same Context (its arrays were overwritten)")
+	}
 }
 
 func (b *Batch) run(p *C.b200sk_params) (*Result, error) {
-	if rc := C.b200sk_check_params(p); rc != 0 { // what the reference constructor returns before looking at a sequence
-		return nil, codeToError(rc)
-	}
+	// everything the checks look at is set first (a Protein batch, for one, skips the codon-table / frame checks:
+	// iterator-protein.go:68)
 	p.alphabet = b.alpha
 	p.want_pos = 1
 	p.pos_width = 4 // a production shim picks 1 or 2 when b.maxLen allows and widens in Index()
 	p.max_read_len = C.uint32_t(b.maxLen)
+	if rc := C.b200sk_check_params(p); rc != 0 { // what the reference constructor returns before looking at a sequence
+		return nil, codeToError(rc)
+	}
 	n := len(b.off) - 1
 	var v *C.uint64_t
 	var ps *C.uint32_t
@@ -170,11 +200,13 @@ func (b *Batch) run(p *C.b200sk_params) (*Result, error) {
 	if rc != 0 {
 		return nil, codeToError(rc)
 	}
+	b.ctx.gen++
 	return &Result{
 		val:    unsafe.Slice((*uint64)(unsafe.Pointer(v)), int(total)),
 		pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
 		off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), n+1),
 		status: unsafe.Slice((*int32)(unsafe.Pointer(st)), n),
+		mode:   p.mode, ctx: b.ctx, gen: b.ctx.gen,
 	}, nil
 }
 
@@ -235,39 +267,29 @@ func cbool(b bool) C.int32_t {
 	return 0
 }
 
-// Iterator replays one read's slice with the reference's method set
-// (sketches.Iterator / sketches.Sketch / sketches.ProteinIterator: Next, Index).
-type Iterator struct {
+// ---- replay types: the reference's method sets over one read's slice of a Result -------------------------------
+//
+//	sketches.Iterator               NextKmer :708, NextHash :658, NextSimHash :191, Next :762 (3 values), Index :776
+//	sketches.Sketch                 NextMinimizer sketch.go:205, NextSyncmer :312, Next :480 (2 values), Index :488
+//	sketches.ProteinIterator        Next iterator-protein.go:76, Index :93
+//	sketches.ProteinMinimizerSketch Next sketch-protein.go:106, Index :213
+//	sketches.IdxValue               sketch.go:496
+
+// IdxValue is sketches.IdxValue (sketch.go:496-499).
+type IdxValue struct {
+	Idx int    // index
+	Val uint64 // hash
+}
+
+type replay struct {
 	val []uint64
 	pos []uint32
 	i   int
-	err error // the constructor / NextKmer error of this read
+	res *Result
 }
 
-// Sketch is the same replay type under the reference's other name.
-type Sketch = Iterator
-
-// Iterator returns read i's iterator, or the error the reference constructor returns for that read
-// (ErrShortSeq ...).  For k-mer codes an illegal base is reported by Next after the codes before it
-// (iterator.go:730-748).
-func (r *Result) Iterator(i int) (*Iterator, error) {
-	st := C.int(r.status[i])
-	it := &Iterator{val: r.val[r.off[i]:r.off[i+1]], pos: r.pos[r.off[i]:r.off[i+1]]}
-	if st == C.B200SK_ERR_ILLEGAL_BASE {
-		it.err = ErrIllegalBase
-		return it, nil
-	}
-	if st != 0 {
-		return nil, codeToError(st)
-	}
-	return it, nil
-}
-
-// Sketch is Iterator under the name used for minimizers and syncmers.
-func (r *Result) Sketch(i int) (*Sketch, error) { return r.Iterator(i) }
-
-// Next returns the next element (sketches.Iterator.NextHash / Sketch.Next / ProteinIterator.Next).
-func (it *Iterator) Next() (uint64, bool) {
+func (it *replay) next() (uint64, bool) {
+	it.res.check()
 	if it.i >= len(it.val) {
 		return 0, false
 	}
@@ -276,18 +298,213 @@ func (it *Iterator) Next() (uint64, bool) {
 	return v, true
 }
 
-// NextKmer mirrors (*Iterator).NextKmer (iterator.go:708): the deferred illegal-base error comes last.
-func (it *Iterator) NextKmer() (uint64, bool, error) {
-	if it.i >= len(it.val) {
-		return 0, false, it.err
+func (it *replay) index() int { return int(it.pos[it.i-1]) }
+
+// IdxValues returns the read's whole slice as the reference's IdxValue pairs (what its users collect from a Next loop).
+func (it *replay) IdxValues() []IdxValue {
+	it.res.check()
+	out := make([]IdxValue, len(it.val))
+	for j := range it.val {
+		out[j] = IdxValue{Idx: int(it.pos[j]), Val: it.val[j]}
 	}
-	v := it.val[it.i]
-	it.i++
-	return v, true, nil
+	return out
 }
 
-// Index returns the 0-based position of the last returned element (iterator.go:776, sketch.go:488).
-func (it *Iterator) Index() int { return int(it.pos[it.i-1]) }
+// Iterator mirrors sketches.Iterator (k-mer codes, ntHash values, SimHash codes).
+type Iterator struct {
+	replay
+	mode C.int32_t
+	err  error // NextKmer's deferred illegal-base error of this read (iterator.go:730-748)
+}
+
+// Sketch mirrors sketches.Sketch (minimizers, syncmers).
+type Sketch struct {
+	replay
+	syncmer bool
+}
+
+// ProteinIterator mirrors sketches.ProteinIterator.
+type ProteinIterator struct{ replay }
+
+// ProteinMinimizerSketch mirrors sketches.ProteinMinimizerSketch.
+type ProteinMinimizerSketch struct{ replay }
+
+func (r *Result) slice(i int) (replay, error) {
+	r.check()
+	st := C.int(r.status[i])
+	rp := replay{val: r.val[r.off[i]:r.off[i+1]], pos: r.pos[r.off[i]:r.off[i+1]], res: r}
+	if st != 0 && st != C.B200SK_ERR_ILLEGAL_BASE {
+		return rp, codeToError(st) // what the reference constructor returns for this read (ErrShortSeq ...)
+	}
+	return rp, nil
+}
+
+// Iterator returns read i's iterator (batches made by KmerIterator / HashIterator / SimHashIterator), or the error
+// the reference constructor returns for that read.  For k-mer codes an illegal base is reported by NextKmer / Next
+// after the codes before it, as in the reference.
+func (r *Result) Iterator(i int) (*Iterator, error) {
+	rp, err := r.slice(i)
+	if err != nil {
+		return nil, err
+	}
+	it := &Iterator{replay: rp, mode: r.mode}
+	if C.int(r.status[i]) == C.B200SK_ERR_ILLEGAL_BASE {
+		it.err = ErrIllegalBase
+	}
+	return it, nil
+}
+
+// Sketch returns read i's sketch (batches made by MinimizerSketch / SyncmerSketch).
+func (r *Result) Sketch(i int) (*Sketch, error) {
+	rp, err := r.slice(i)
+	if err != nil {
+		return nil, err
+	}
+	return &Sketch{replay: rp, syncmer: r.mode == C.B200SK_MODE_SYNCMER}, nil
+}
+
+// ProteinIterator returns read i's iterator (batches made by ProteinIterator).
+func (r *Result) ProteinIterator(i int) (*ProteinIterator, error) {
+	rp, err := r.slice(i)
+	if err != nil {
+		return nil, err
+	}
+	return &ProteinIterator{rp}, nil
+}
+
+// ProteinMinimizerSketch returns read i's sketch (batches made by ProteinMinimizerSketch).
+func (r *Result) ProteinMinimizerSketch(i int) (*ProteinMinimizerSketch, error) {
+	rp, err := r.slice(i)
+	if err != nil {
+		return nil, err
+	}
+	return &ProteinMinimizerSketch{rp}, nil
+}
+
+// NextKmer mirrors (*Iterator).NextKmer (iterator.go:708): the deferred illegal-base error comes after the codes
+// before the k-mer that holds the illegal base.
+func (it *Iterator) NextKmer() (code uint64, ok bool, err error) {
+	code, ok = it.next()
+	if !ok {
+		return 0, false, it.err
+	}
+	return code, true, nil
+}
+
+// NextHash mirrors (*Iterator).NextHash (iterator.go:658).
+func (it *Iterator) NextHash() (code uint64, ok bool) { return it.next() }
+
+// NextSimHash mirrors (*Iterator).NextSimHash (iterator.go:191).
+func (it *Iterator) NextSimHash() (code uint64, ok bool) { return it.next() }
+
+// Next mirrors (*Iterator).Next (iterator.go:762-773): three values; only k-mer iterators ever return an error.
+func (it *Iterator) Next() (code uint64, ok bool, err error) {
+	if it.mode == C.B200SK_MODE_KMER {
+		return it.NextKmer()
+	}
+	code, ok = it.next()
+	return code, ok, nil
+}
+
+// Index mirrors (*Iterator).Index (iterator.go:776): 0-based position of the last element returned.
+func (it *Iterator) Index() int { return it.index() }
+
+// NextMinimizer mirrors (*Sketch).NextMinimizer (sketch.go:205).
+func (s *Sketch) NextMinimizer() (code uint64, ok bool) { return s.next() }
+
+// NextSyncmer mirrors (*Sketch).NextSyncmer (sketch.go:312).
+func (s *Sketch) NextSyncmer() (code uint64, ok bool) { return s.next() }
+
+// Next mirrors (*Sketch).Next (sketch.go:480): two values.
+func (s *Sketch) Next() (uint64, bool) { return s.next() }
+
+// Index mirrors (*Sketch).Index (sketch.go:488).
+func (s *Sketch) Index() int { return s.index() }
+
+// Next mirrors (*ProteinIterator).Next (iterator-protein.go:76).
+func (it *ProteinIterator) Next() (code uint64, ok bool) { return it.next() }
+
+// Index mirrors (*ProteinIterator).Index (iterator-protein.go:93).
+func (it *ProteinIterator) Index() int { return it.index() }
+
+// Next mirrors (*ProteinMinimizerSketch).Next (sketch-protein.go:106).
+func (s *ProteinMinimizerSketch) Next() (code uint64, ok bool) { return s.next() }
+
+// Index mirrors (*ProteinMinimizerSketch).Index (sketch-protein.go:213).
+func (s *ProteinMinimizerSketch) Index() int { return s.index() }
+
+// ---- multi-GPU and the reduced sketch ---------------------------------------------------------------------------
+
+// Group drives several devices from one process (b200sk_group_*): one library context and worker thread per device,
+// the batch sharded over them by cumulative bases, results in read order.
+type Group struct {
+	h   *C.b200sk_group
+	ctx Context // carries the run counter the Results check
+}
+
+// NewGroup binds the given CUDA devices (1, 2, 4 or 8 of one box).
+func NewGroup(devices []int) (*Group, error) {
+	d := make([]C.int, len(devices))
+	for i, v := range devices {
+		d[i] = C.int(v)
+	}
+	var h *C.b200sk_group
+	if rc := C.b200sk_group_create(&h, &d[0], C.int(len(d))); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	return &Group{h: h}, nil
+}
+
+// Close releases every device of the group.
+func (g *Group) Close() { C.b200sk_group_destroy(g.h); g.h = nil }
+
+// MinimizerSketch is Batch.MinimizerSketch over all devices of the group.
+func (g *Group) MinimizerSketch(b *Batch, k, w int, circular bool) (*Result, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_MINIMIZER, k: C.int32_t(k), w: C.int32_t(w), circular: cbool(circular),
+		alphabet: b.alpha, want_pos: 1, pos_width: 4, max_read_len: C.uint32_t(b.maxLen)}
+	if rc := C.b200sk_check_params(&p); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	n := len(b.off) - 1
+	var v *C.uint64_t
+	var ps *C.uint32_t
+	var o *C.uint64_t
+	var st *C.int32_t
+	var total C.uint64_t
+	if rc := C.b200sk_group_run(g.h, &p, (*C.uint8_t)(b.bases), &b.off[0], C.uint64_t(n), &v, &ps, &o, &st, &total); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	g.ctx.gen++
+	return &Result{
+		val:    unsafe.Slice((*uint64)(unsafe.Pointer(v)), int(total)),
+		pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
+		off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), n+1),
+		status: unsafe.Slice((*int32)(unsafe.Pointer(st)), n),
+		mode:   p.mode, ctx: &g.ctx, gen: g.ctx.gen,
+	}, nil
+}
+
+// MinimizerSet replaces the consumer loop of a FracMinHash / unique-k-mer tool,
+//
+//	for each record { for sk.Next() { if h <= math.MaxUint64/scale { set[h] = struct{}{} } } }; sort(keys(set))
+//
+// (the scale rule of sketches/iterator.go:180-185): the per-read arrays never leave the GPU, only the sorted distinct
+// values come back (b200sk_run_reduced).  scale <= 1 keeps every minimizer.
+func (b *Batch) MinimizerSet(k, w int, scale uint32) ([]uint64, error) {
+	p := C.b200sk_params{mode: C.B200SK_MODE_MINIMIZER, k: C.int32_t(k), w: C.int32_t(w), alphabet: b.alpha,
+		max_read_len: C.uint32_t(b.maxLen)}
+	if rc := C.b200sk_check_params(&p); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	var v *C.uint64_t
+	var total C.uint64_t
+	if rc := C.b200sk_run_reduced(b.ctx.h, &p, C.uint32_t(scale), 1, (*C.uint8_t)(b.bases), &b.off[0],
+		C.uint64_t(len(b.off)-1), &v, &total); rc != 0 {
+		return nil, codeToError(rc)
+	}
+	b.ctx.gen++
+	return unsafe.Slice((*uint64)(unsafe.Pointer(v)), int(total)), nil
+}
 
 // ---- record feeder: seqio/fastx.Reader.Read over a chunk of text (seqio/fastx/reader.go:233-471) -----------
 
@@ -355,6 +572,7 @@ func (t *TextChunk) MinimizerSketchText(n, format int, final bool, k, w int) (*F
 			pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
 			off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), nrec+1),
 			status: unsafe.Slice((*int32)(unsafe.Pointer(st)), nrec),
+			mode:   C.B200SK_MODE_MINIMIZER, // (valid until the next call on this chunk / stream)
 		},
 		Format: int(info.format), Records: nrec, Consumed: int(info.consumed), IsFastq: info.format == C.B200SK_FASTX_FASTQ,
 	}, nil
@@ -405,6 +623,7 @@ func (s *FastxStream) Next() (*FastxResult, error) {
 			pos:    unsafe.Slice((*uint32)(unsafe.Pointer(ps)), int(total)),
 			off:    unsafe.Slice((*uint64)(unsafe.Pointer(o)), nrec+1),
 			status: unsafe.Slice((*int32)(unsafe.Pointer(st)), nrec),
+			mode:   C.B200SK_MODE_MINIMIZER, // (valid until the next call on this chunk / stream)
 		},
 		Format: int(info.format), Records: nrec, Consumed: int(info.consumed), IsFastq: info.format == C.B200SK_FASTX_FASTQ,
 	}, nil

@@ -160,9 +160,11 @@ int b200sk_enqueue_device(b200sk_ctx *ctx, const b200sk_params *p,
  * reader.go:372-471).  Here a whole chunk of FASTA/FASTQ text is split into records on the device and its
  * sequences land packed in HBM in exactly the layout b200sk_run_device takes (bases + read_off), so a
  * chunk goes text -> records -> sketches without the bases ever visiting the host.
- * Supported: FASTA with any line structure; FASTQ records of four lines (B200SK_ERR_BAD_FASTQ otherwise);
- * LF or CRLF line ends; leading blank lines; a last line without newline.  Alphabet guessing and per-letter
- * validation (reader.go:430-452) are not done here. */
+ * FASTA and FASTQ with any line structure (four-line FASTQ records take a parallel path, anything else the
+ * reference's general record rule, reader.go:308-345,396-417); LF or CRLF line ends; leading blank lines; a last
+ * line without newline.  The alphabet is guessed from the first record and every letter checked against it
+ * (reader.go:430-452): b200sk_fastx_info.alphabet / first_invalid / d_invalid.  The reference's Read() returns the
+ * offending record together with an error; here the chunk is parsed to its end and the caller decides. */
 #define B200SK_FASTX_FASTA 1
 #define B200SK_FASTX_FASTQ 2
 typedef struct b200sk_fastx_info {
@@ -181,11 +183,18 @@ typedef struct b200sk_fastx_info {
     uint64_t *d_rec_off;   /* [n_records+1] text offset of each record's delimiter; [n_records] = consumed      */
     uint64_t *d_qual_off;  /* FASTQ: [n_records] text offset of the quality line; FASTA: NULL                   */
     uint64_t *d_line_off;  /* [n_lines+1] text offset of every line start                                       */
+    int32_t alphabet;      /* B200SK_ALPHABET_*: seq.GuessAlphabetLessConservatively over the first record's first
+                              10 000 letters (reader.go:430-435, seq/alphabet.go:411-452), or the one passed in      */
+    int32_t reserved2;
+    uint64_t first_invalid; /* first record holding a letter outside that alphabet (Alphabet.IsValid,
+                              seq/alphabet.go:234-300: the error Read() returns with that record), ~0 = none        */
+    uint8_t *d_invalid;    /* [n_records] 1 = the record holds such a letter                                     */
 } b200sk_fastx_info;
 
 /* d_text: the chunk in HBM, 16-byte aligned, readable up to the next 16-byte boundary past n_bytes.
  * format: 0 = detect, else B200SK_FASTX_* (a chunk that continues a file starts at a record and passes
- * the file's format).  final: 1 = the text ends here (the last record is complete), 0 = more follows (the
+ * the file's format; it also passes the file's alphabet, as (1 + info.alphabet of the first chunk) << 8, so that the
+ * guess is made once per file as in the reference).  final: 1 = the text ends here (the last record is complete), 0 = more follows (the
  * last, possibly cut, record is left for the next call: see consumed). */
 int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n_bytes, int format, int final,
                               void *stream, b200sk_fastx_info *info);

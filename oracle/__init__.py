@@ -286,3 +286,37 @@ def fastx_parse(text):
     for p in (bases, ro, rc, qo, nl):
         L.ora_fastx_free(C.cast(p, C.c_void_p))
     return out
+
+
+# ---------------------------------------------------------------- alphabet guess / validation (numpy restatement)
+# seq/alphabet.go:353-399: letters + gap + ambiguous of every alphabet the reader can guess
+ALPHABET_LETTERS = {
+    "DNA": b"acgtACGT -.nN",
+    "DNAredundant": b"acgtryswkmbdhvACGTRYSWKMBDHV -.nN",
+    "RNA": b"acguACGU -.nN",
+    "RNAredundant": b"acguryswkmbdhvACGURYSWKMBDHV -.nN",
+    "Protein": b"abcdefghijklmnopqrstuvwyzABCDEFGHIJKLMNOPQRSTUVWYZ -xX*_.",
+}
+
+
+def guess_alphabet_less_conservatively(seq_bytes, threshold=10000):
+    """seq.GuessAlphabetLessConservatively (seq/alphabet.go:411-452) over the first record's sequence."""
+    s = bytes(seq_bytes)
+    if len(s) == 0:
+        return "Unlimit"
+    present = set(s[:threshold] if threshold and len(s) > threshold else s)
+    if any(b >= 128 for b in present):
+        return "Unlimit"
+    for name in ("DNA", "RNA", "DNAredundant", "RNAredundant", "Protein"):
+        if present <= set(ALPHABET_LETTERS[name]):
+            return {"DNA": "DNAredundant", "RNA": "RNAredundant"}.get(name, name)
+    return "Unlimit"
+
+
+def alphabet_is_valid(name, seq_bytes):
+    """Alphabet.IsValid (seq/alphabet.go:234-300): every letter among the alphabet's letters; Unlimit takes all."""
+    if name == "Unlimit" or len(seq_bytes) == 0:
+        return True
+    ok = np.zeros(256, dtype=bool)
+    ok[np.frombuffer(ALPHABET_LETTERS[name], dtype=np.uint8)] = True
+    return bool(ok[np.frombuffer(bytes(seq_bytes), dtype=np.uint8)].all())

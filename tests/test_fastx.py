@@ -166,7 +166,7 @@ def test_errors_and_edges():
         with pytest.raises(cabi.SketchError) as e:
             _parse_gpu(ctx, bad)
         assert e.value.code == cabi.ERR_NOT_FASTX
-    for bad in (b"@r\nACGT\n+\nII\n", b"@r\nAC\nGT\n+\nII\nII\n", b"@r\nACGT\n+\nIIII\n@s\nAC\n"):
+    for bad in (b"@r\nACGT\n+\nII\n", b"@r\nAC\nGT\n+\nII\nIII\n", b"@r\nACGT\n+\nIIII\n@s\nAC\n"):
         with pytest.raises(cabi.SketchError) as e:
             _parse_gpu(ctx, bad)
         assert e.value.code == cabi.ERR_BAD_FASTQ
@@ -313,3 +313,132 @@ def test_fxstream_equals_one_shot():
         stream.next()
     assert ei.value.code == cabi.ERR_NOT_FASTX
     stream.close()
+
+
+def make_multiline_fastq(n, seed, width=60, crlf=False, blank_between=False, at_quals=True):
+    rng = np.random.default_rng(seed)
+    nl = b"\r\n" if crlf else b"\n"
+    out, seqs, quals = [], [], []
+    for i in range(n):
+        L = int(rng.integers(0, 400))
+        s = bytes(np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, size=L)])
+        q = bytearray(rng.integers(33, 74, size=L, dtype=np.uint8).tobytes())
+        wq = int(rng.integers(7, 90))
+        for j in range(0, L, wq):  # '@' and '+' at the start of quality lines
+            if at_quals and rng.integers(0, 3) == 0:
+                q[j] = ord("@") if rng.integers(0, 2) else ord("+")
+        seqs.append(s)
+        quals.append(bytes(q))
+        out.append(b"@r%d d" % i + nl)
+        out += [s[j:j + width] + nl for j in range(0, L, width)]
+        out.append(b"+" + (b"r%d" % i if i % 2 else b"") + nl)
+        out += [bytes(q[j:j + wq]) + nl for j in range(0, L, wq)]
+        if blank_between and rng.integers(0, 3) == 0:
+            out.append(nl)
+    return b"".join(out), seqs, quals
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(crlf=True), dict(blank_between=True), dict(width=7), dict(at_quals=False)])
+def test_multiline_fastq_parity(kw):
+    """reader.go:308-345,396-417: records of any line structure; the oracle follows the reference literally."""
+    cabi, ctx = _ctx()
+    for n, seed in ((1, 1), (40, 2), (1500, 3)):
+        text, seqs, quals = make_multiline_fastq(n, seed, **kw)
+        for t in (text, text[:-1] if not kw.get("crlf") else text, b"\n\n" + text):
+            o = oracle.fastx_parse(t)
+            assert o["status"] == 0 and o["n_records"] == n
+            info, g = _parse_gpu(ctx, t)
+            assert g["format"] == cabi.FASTX_FASTQ and g["consumed"] == len(t)
+            _same(g, o, True)
+            assert bytes(g["bases"]) == b"".join(seqs)
+    # four-line records with blank lines between them (the parallel path hands over to the general rule)
+    text, seqs = make_fastq(300, 80, 5)
+    recs = text.split(b"\n@")
+    t = b"\n\n@".join(recs)
+    o = oracle.fastx_parse(t)
+    info, g = _parse_gpu(ctx, t)
+    assert o["status"] == 0 and o["n_records"] == 300
+    _same(g, o, True)
+    # the reader mirror joins multi-line quality
+    from bio_b200 import fastx
+    text, seqs, quals = make_multiline_fastq(200, 9)
+    got = list(fastx.Reader(text, ctx=ctx, chunk_bytes=3000))
+    assert [r.Seq for r in got] == seqs and [r.Qual for r in got] == quals
+    # a quality longer than its sequence at the next record start is ErrBadFASTQFormat; a short one at the end too
+    for bad in (b"@a\nAC\nGT\n+\nIII\nIII\n@b\nA\n+\nI\n", b"@a\nAC\nGT\n+\nII\nI\n"):
+        assert oracle.fastx_parse(bad)["status"] == oracle.ERR_BAD_FASTQ
+        with pytest.raises(cabi.SketchError) as e:
+            _parse_gpu(ctx, bad)
+        assert e.value.code == cabi.ERR_BAD_FASTQ
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_multiline_fastq_streaming_chunks():
+    """consumed / carry-over with records that span many lines: any cut reproduces the whole-file parse"""
+    cabi, ctx = _ctx()
+    text, seqs, quals = make_multiline_fastq(120, 4, width=25)
+    want = oracle.fastx_parse(text)
+    for chunk in (500, 2000, 7919):
+        got, pos, fmt = [], 0, 0
+        while pos < len(text):
+            end = min(len(text), pos + chunk)
+            final = end == len(text)
+            while True:
+                info, g = _parse_gpu(ctx, text[pos:end], fmt, final)
+                if g["consumed"] or final:
+                    break
+                end = min(len(text), end + chunk)
+                final = end == len(text)
+            fmt = g["format"]
+            for i in range(g["n_records"]):
+                got.append(bytes(g["bases"][int(g["read_off"][i]):int(g["read_off"][i + 1])]))
+            pos += g["consumed"] if not final else end - pos
+        assert got == seqs and len(got) == want["n_records"]
+    ctx.close()
+
+
+def test_oracle_alphabet_rules():
+    # seq/alphabet.go:411-452
+    g = oracle.guess_alphabet_less_conservatively
+    assert g(b"ACGTNacgt") == "DNAredundant" and g(b"ACGU") == "RNAredundant" and g(b"ACGTRYK") == "DNAredundant"
+    assert g(b"ACGURY") == "RNAredundant" and g(b"MKVLAAGIVGLE") == "Protein" and g(b"ACGT!") == "Unlimit"
+    assert g(b"") == "Unlimit" and g(b"ACGT" * 3000 + b"!") == "DNAredundant"  # only the first 10 000 letters are looked at
+    assert oracle.alphabet_is_valid("DNAredundant", b"ACGTN-.") and not oracle.alphabet_is_valid("DNAredundant", b"ACGTJ")
+    assert oracle.alphabet_is_valid("Unlimit", b"!!") and oracle.alphabet_is_valid("Protein", b"MKV*")
+
+
+@pytest.mark.gpu
+def test_alphabet_guess_and_validation():
+    """reader.go:430-452: the alphabet comes from the first record, every record is checked against it"""
+    cabi, ctx = _ctx()
+    from bio_b200 import fastx
+    names = fastx.ALPHABET_NAMES
+    rng = np.random.default_rng(5)
+    cases = [(b"ACGT", {}), (b"ACGTN", {}), (b"ACGU", {}), (b"ACGTRYKM", {}), (b"MKVLAGIE", {}),
+             (b"ACGT", {3: b"J", 17: b"!", 18: b"u"}), (b"ACGU", {5: b"T"}), (b"ACGT!", {})]
+    for letters, spoil in cases:
+        seqs = []
+        for i in range(40):
+            L = int(rng.integers(1, 300))
+            sq = bytearray(np.frombuffer(letters, dtype=np.uint8)[rng.integers(0, len(letters), size=L)].tobytes())
+            if i in spoil:
+                sq[int(rng.integers(0, L))] = spoil[i][0]
+            seqs.append(bytes(sq))
+        seqs[0] = letters * 3  # the first record shows every letter of the set
+        for fastq in (False, True):
+            if fastq:
+                text = b"".join(b"@r%d\n" % i + sq + b"\n+\n" + b"I" * len(sq) + b"\n" for i, sq in enumerate(seqs))
+            else:
+                text = b"".join(b">r%d\n" % i + sq + b"\n" for i, sq in enumerate(seqs))
+            info, g = _parse_gpu(ctx, text)
+            want_alpha = oracle.guess_alphabet_less_conservatively(seqs[0])
+            assert names[g["alphabet"]] == want_alpha
+            want_bad = [not oracle.alphabet_is_valid(want_alpha, sq) for sq in seqs]
+            assert g["invalid"].astype(bool).tolist() == want_bad
+            first = want_bad.index(True) if any(want_bad) else (1 << 64) - 1
+            assert g["first_invalid"] == first
+            recs = list(fastx.Reader(text, ctx=ctx, chunk_bytes=1500))  # the alphabet travels with the later chunks
+            assert [r.Err is not None for r in recs] == want_bad and all(r.Alphabet == want_alpha for r in recs)
+    ctx.close()
