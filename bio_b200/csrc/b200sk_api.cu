@@ -460,13 +460,14 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         static const bool no_rewalk = [] { const char *e = getenv("B200SK_WALKER"); return e && strcmp(e, "norewalk") == 0; }();
         if (no_rewalk) a.keyed |= 4u; // timing experiment only: WRONG output for the items the keyed walk hands back
     }
+#ifdef B200SK_EXPERIMENTS
     {
         static const uint32_t spin = [] { const char *e = getenv("B200SK_SPIN_NS"); return e ? (uint32_t)atoi(e) : 0u; }();
         a.spin_ns = spin;
         static const bool unordered = [] { const char *e = getenv("B200SK_UNORDERED"); return e && atoi(e) != 0; }();
         a.unordered = unordered ? meta + 6 : nullptr;
     }
-    a.key_mask = 0xffffffc0u;
+#endif
     a.rewalks = meta + 5;
     a.sm_tile = pl.sm_tile; a.sm_tile_bytes = pl.sm_tile_bytes; a.sm_ring = pl.sm_ring;
     a.sm_ring_bytes = pl.sm_ring_bytes; a.sm_listv = pl.sm_listv; a.sm_listp = pl.sm_listp;

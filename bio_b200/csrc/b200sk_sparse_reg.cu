@@ -19,6 +19,9 @@
 #include "b200sk_protein.cuh"
 #include "b200sk_tile.cuh"
 
+// B200SK_EXPERIMENTS (off): the two timing experiments of DESIGN.md 5.1 -- output ranges handed out in completion order
+// (B200SK_UNORDERED=1, wrong order, same work) and a sleeping look-back poll (B200SK_SPIN_NS).  Compiled out of the
+// product: their run-time branches alone cost the headline kernel 1 %.
 namespace b200sk {
 
 // ------------------------------------------------------------------ shared-memory access
@@ -711,7 +714,10 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
 //   +0 mbarrier, +16 tile bytes, +sm_ring k-mer ring (syncmer), +sm_listv values, +sm_listp position deltas.
 // KEYED (minimizers, W <= 16): the keyed walk above with the exact walk behind it; the lists then hold values only
 // and the position bytes are absolute stream indices instead of deltas.
-template <int MODE, int W, bool KEYED>
+// SHARD: this rank's tiles are chunks of ONE tile chain shared by several GPUs (b200sk_enqueue_device_sharded): the
+// look-back runs over the ranks' replicated status words, the output arrays are the root's, indexed globally.  A
+// template parameter, not a run-time branch: kept in the single-GPU kernel it cost 5 % (registers 118 -> 122).
+template <int MODE, int W, bool KEYED, bool SHARD>
 __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
@@ -757,10 +763,12 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         tile = __shfl_sync(0xffffffffu, tile, 0);
         const uint64_t item0 = tile * 32ull;
         if (item0 >= n_items) break;
-        // sharded batch: local tile -> tile of the global order (and the same for reads, 32 per tile)
-        uint64_t gtile = tile;
-        if (a.shard.n) gtile = ((tile / a.shard_chunk_tiles) * a.shard.n + a.shard.rank) * a.shard_chunk_tiles + tile % a.shard_chunk_tiles;
-        const uint64_t gread = gtile * 32ull + lane; // global index of this lane's read (one item per read here)
+        // sharded batch: local tile -> tile of the global order (reads alike, 32 per tile).  Recomputed where it is
+        // needed instead of being kept across the walk: the single-GPU kernels must not pay registers for it.
+        auto global_tile = [&]() -> uint64_t {
+            const uint32_t ct = a.shard_chunk_tiles;
+            return ((tile / ct) * a.shard.n + a.shard.rank) * ct + tile % ct;
+        };
         const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_items - item0);
         Item it;
         item_geometry<MODE>(a, item0 + lane, n_items, it);
@@ -776,7 +784,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
             tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
         }
         if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
-        if (it.valid && it.first_chunk && a.status) a.status[a.shard.n ? gread : it.r] = it.status;
+        if (it.valid && it.first_chunk && a.status) a.status[SHARD ? global_tile() * 32ull + lane : it.r] = it.status;
         bool fast = false;
         if (bytes && span_ok) {
             mbar_wait(mbar, parity);
@@ -874,8 +882,12 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         // Ordered allocation in two halves: publish the tile's count, then -- while the tiles before this one
         // finish -- scatter the staged lists into one contiguous buffer (the codes are dead now; nothing here
         // needs the prefix), and only then wait for the prefix.
-        if (a.shard.n) lookback_publish_multi(a.shard, gtile, total);
+        if (SHARD) lookback_publish_multi(a.shard, global_tile(), total);
+#ifdef B200SK_EXPERIMENTS
         else if (!a.unordered) lookback_publish(a.tile_state, tile, total);
+#else
+        else lookback_publish(a.tile_state, tile, total);
+#endif
         const uint32_t OB = a.sm_tile_bytes / 12u;
         uint64_t *obv = reinterpret_cast<uint64_t *>(tilebuf);
         uint32_t *obp = reinterpret_cast<uint32_t *>(tilebuf + (size_t)OB * 8u);
@@ -894,14 +906,19 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         };
         if (!any_overflow && total) scatter(0);
         uint64_t tb;
+#ifdef B200SK_EXPERIMENTS
         if (a.unordered) { // timing experiment only (B200SK_UNORDERED=1): ranges in completion order, WRONG output order
             unsigned long long t0 = 0;
             if (lane == 0) t0 = atomicAdd(a.unordered, (unsigned long long)total);
             tb = __shfl_sync(0xffffffffu, t0, 0);
-        } else if (a.shard.n) tb = lookback_resolve_multi(a.shard, gtile, total);
-        else tb = lookback_resolve(a.tile_state, tile, total, a.spin_ns);
+        } else tb = lookback_resolve(a.tile_state, tile, total, a.spin_ns);
+#else
+        if (SHARD) tb = lookback_resolve_multi(a.shard, global_tile(), total);
+        else tb = lookback_resolve(a.tile_state, tile, total);
+#endif
         const uint64_t mine = tb + excl;
-        if (a.shard.n) { // the root's offset table, indexed by the global read
+        if (SHARD) { // the root's offset table, indexed by the global read
+            const uint64_t gread = global_tile() * 32ull + lane;
             if (it.valid) a.out_off[gread] = a.out_base + mine;
             if (it.valid && gread + 1 == a.shard_n_reads) a.out_off[a.shard_n_reads] = a.out_base + mine + cnt;
         } else {
@@ -919,7 +936,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
                     for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
-                    if (a.out_pos && a.pos_width == 1) {
+                    if (SHARD && a.out_pos && a.pos_width == 1) {
                         // uint8 positions leave four to a 32-bit store (128-byte runs per warp instruction instead of
                         // 32-byte ones: what a peer-mapped out_pos needs to use its NVLink packets)
                         uint8_t *gp = reinterpret_cast<uint8_t *>(a.out_pos) + tb + r0;
@@ -979,11 +996,11 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
 template <int MODE, int W> constexpr bool has_keyed() {
     return MODE == B200SK_MODE_MINIMIZER && (W == 3 || W == 5 || W == 11 || W == 15);
 }
-template <int MODE, int W>
+template <int MODE, int W, bool SHARD>
 static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
-    const void *fn = (const void *)k_sparse_warp<MODE, W, false>;
-    if constexpr (has_keyed<MODE, W>()) {
-        if (a.keyed) fn = (const void *)k_sparse_warp<MODE, W, true>;
+    const void *fn = (const void *)k_sparse_warp<MODE, W, false, SHARD>;
+    if constexpr (has_keyed<MODE, W>() && !SHARD) {
+        if (a.keyed) fn = (const void *)k_sparse_warp<MODE, W, true, false>;
     }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.sm_total);
     if (e != cudaSuccess) return e;
@@ -1001,7 +1018,7 @@ static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_
 // units (this file compiled with -DB200SK_PART=0..3, see the Makefile) so that they build in parallel;
 // part 0 also holds the dispatcher.  B200SK_FAST_BUILD (development) keeps a handful.
 #ifndef B200SK_PART
-#error "compile with -DB200SK_PART=0..4"
+#error "compile with -DB200SK_PART=0..8"
 #endif
 #ifdef B200SK_FAST_BUILD
 #define B200SK_LIST_0 B200SK_W(B200SK_MODE_MINIMIZER, 3) B200SK_W(B200SK_MODE_MINIMIZER, 5) B200SK_W(B200SK_MODE_MINIMIZER, 11)
@@ -1030,14 +1047,30 @@ static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_
 #endif
 #define B200SK_CAT2(a, b) a##b
 #define B200SK_CAT(a, b) B200SK_CAT2(a, b)
+// parts 5..8 hold the SHARD instantiations of the lists of parts 0..3 (minimizers and syncmers)
+#if B200SK_PART == 5
+#define B200SK_MY_LIST B200SK_LIST_0
+#elif B200SK_PART == 6
+#define B200SK_MY_LIST B200SK_LIST_1
+#elif B200SK_PART == 7
+#define B200SK_MY_LIST B200SK_LIST_2
+#elif B200SK_PART == 8
+#define B200SK_MY_LIST B200SK_LIST_3
+#else
 #define B200SK_MY_LIST B200SK_CAT(B200SK_LIST_, B200SK_PART)
+#endif
+#if B200SK_PART >= 5
+#define B200SK_IS_SHARD true
+#else
+#define B200SK_IS_SHARD false
+#endif
 
 // One part: launch (or, occ != nullptr, report the occupancy of) the instantiation for (mode, window) if
 // this part holds it; *has tells whether it does.
 cudaError_t B200SK_CAT(launch_sparse_reg_part, B200SK_PART)(const KArgs &a, int window, int threads, int blocks,
                                                             cudaStream_t st, int *occ, bool *has) {
     *has = true;
-#define B200SK_W(MODE, W) if (a.mode == MODE && window == W) return launch_w<MODE, W>(a, threads, blocks, st, occ);
+#define B200SK_W(MODE, W) if (a.mode == MODE && window == W) return launch_w<MODE, W, B200SK_IS_SHARD>(a, threads, blocks, st, occ);
     B200SK_MY_LIST
 #undef B200SK_W
     *has = false;
@@ -1055,6 +1088,10 @@ cudaError_t launch_sparse_reg_part1(const KArgs &, int, int, int, cudaStream_t, 
 cudaError_t launch_sparse_reg_part2(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
 cudaError_t launch_sparse_reg_part3(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
 cudaError_t launch_sparse_reg_part4(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
+cudaError_t launch_sparse_reg_part5(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
+cudaError_t launch_sparse_reg_part6(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
+cudaError_t launch_sparse_reg_part7(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
+cudaError_t launch_sparse_reg_part8(const KArgs &, int, int, int, cudaStream_t, int *, bool *);
 bool sparse_reg_has_part1(int, int);
 bool sparse_reg_has_part2(int, int);
 bool sparse_reg_has_part3(int, int);
@@ -1066,6 +1103,17 @@ static int window_of(int mode, int k, int w, int s) { return mode == B200SK_MODE
 cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ) {
     const int window = window_of(a.mode, a.k, a.w, a.s);
     bool has = false;
+    if (a.shard.n) { // one tile chain across several GPUs: the SHARD instantiations
+        cudaError_t es = launch_sparse_reg_part5(a, window, threads, blocks, st, occ, &has);
+        if (has) return es;
+        es = launch_sparse_reg_part6(a, window, threads, blocks, st, occ, &has);
+        if (has) return es;
+        es = launch_sparse_reg_part7(a, window, threads, blocks, st, occ, &has);
+        if (has) return es;
+        es = launch_sparse_reg_part8(a, window, threads, blocks, st, occ, &has);
+        if (has) return es;
+        return cudaErrorInvalidValue;
+    }
     cudaError_t e = launch_sparse_reg_part0(a, window, threads, blocks, st, occ, &has);
     if (has) return e;
     e = launch_sparse_reg_part1(a, window, threads, blocks, st, occ, &has);
