@@ -140,6 +140,10 @@ struct b200sk_ctx {
     void *fx = nullptr; // record feeder state (b200sk_fastx.cu)
     void *reduce = nullptr; // sort / unique workspace (b200sk_reduce.cu)
     uint64_t launches = 0;
+    // the scratch words above belong to ONE batch at a time: a batch enqueued on another stream than the batch before
+    // it waits for that batch on the device (enqueue), so two streams of one context cannot race on them
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     std::string last_error;
@@ -323,6 +327,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     if (!d_off || !d_ooff || (n_bases && !d_bases)) return B200SK_ERR_BAD_ARG;
     if (((uintptr_t)d_bases & 15u) != 0) return B200SK_ERR_BAD_ARG;
     if ((rc = ensure_meta(ctx))) return rc;
+    if (ctx->last_done && st != ctx->last_stream) CK(cudaStreamWaitEvent(st, ctx->last_done, 0));
     unsigned long long *meta = (unsigned long long *)ctx->meta.p;
     CK(cudaMemsetAsync(meta, 0, 64, st));
     if (n_reads == 0) {
@@ -542,6 +547,9 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(cudaEventRecord(ev1, st));
         ctx->timing_events.emplace_back(ev0, ev1);
     }
+    if (!ctx->last_done) CK(cudaEventCreateWithFlags(&ctx->last_done, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->last_done, st));
+    ctx->last_stream = st;
     return 0;
 }
 
@@ -671,6 +679,7 @@ void b200sk_destroy(b200sk_ctx *ctx) {
     for (HostBuf *b : {&ctx->h_val, &ctx->h_pos, &ctx->h_ooff, &ctx->h_status, &ctx->h_meta}) b->release();
     b200sk::fx_free(ctx->fx);
     b200sk::reduce_free(ctx->reduce);
+    if (ctx->last_done) cudaEventDestroy(ctx->last_done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

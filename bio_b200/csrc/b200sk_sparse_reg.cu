@@ -935,7 +935,15 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
                     if (r0) scatter(r0);
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
-                    for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
+                    if (SHARD) {
+                        // peer stores: every warp store starts on a 128-byte line of the root's array (the first one of a
+                        // tile is short instead) -- a 256-byte store that straddles lines travels as three partial NVLink
+                        // writes (scripts/ubench/peer_ingress.cu: 507 vs 717 GB/s into one GPU)
+                        const int32_t sh = (int32_t)((tb + r0) & 15u);
+                        for (int32_t i = (int32_t)lane - sh; i < (int32_t)n; i += 32)
+                            if (i >= 0) gv[i] = obv[i];
+                    } else
+                        for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
                     if (SHARD && a.out_pos && a.pos_width == 1) {
                         // uint8 positions leave four to a 32-bit store (128-byte runs per warp instruction instead of
                         // 32-byte ones: what a peer-mapped out_pos needs to use its NVLink packets)

@@ -96,7 +96,12 @@ typedef struct b200sk_params {
     int32_t reserved[2];
 } b200sk_params;
 
-typedef struct b200sk_ctx b200sk_ctx; /* one per caller thread and device; not thread-safe */
+/* One per caller thread and device: the HOST side of a context is not thread-safe.  On the device a context owns one
+ * set of scratch words (ticket, look-back status words, item tables) that serve ONE batch at a time: the `stream`
+ * argument of the device entry points may change from call to call -- a batch enqueued on another stream than the
+ * batch before it is ordered behind it on the device (cudaStreamWaitEvent inside the call), never raced.  For batches
+ * that should overlap on the device use one context per stream. */
+typedef struct b200sk_ctx b200sk_ctx;
 
 /* Library / device lifetime.  device = CUDA ordinal.  There is no CPU
  * fallback: without a usable device this returns B200SK_ERR_NO_DEVICE. */

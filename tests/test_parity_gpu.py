@@ -1,5 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact values, positions,
 offsets and per-read status.  Run on the B200 box: pytest -m gpu."""
+import ctypes
 import os
 
 import numpy as np
@@ -468,3 +469,37 @@ def test_protein_minimizer_low_complexity_overflow(gpu_ctx):
     for k, w, frame in ((10, 5, 1), (7, 3, -2), (16, 24, 3)):
         res, ref = run_both(gpu_ctx, cabi.MODE_PROTEIN_MINIMIZER, bases, off, k=k, w=w, frame=frame)
         assert_same(res, ref, f"k={k} w={w} frame={frame}")
+
+
+def test_two_streams_one_context(gpu_ctx):
+    """One context, batches enqueued alternately on two streams without any host synchronisation in between: the
+    context's scratch words serve one batch at a time, so the library orders the batches on the device
+    (include/b200sketch.h, b200sk_ctx) -- every batch must still be bit-exact."""
+    import torch
+    dev = torch.device("cuda:0")
+    p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=11, max_read_len=150)
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    jobs = []
+    for i in range(6):
+        b, o = synth.uniform_reads(40000 + 5000 * i, 150, 900 + i)
+        db = torch.from_numpy(np.concatenate([b, np.zeros(64, np.uint8)])).to(dev)
+        do = torch.from_numpy(o.astype(np.int64)).to(dev)
+        n = len(o) - 1
+        cap = int(cabi.lib().b200sk_output_bound(ctypes.byref(p), len(b), n, 0))
+        val = torch.zeros(cap, dtype=torch.int64, device=dev)
+        pos = torch.zeros(cap, dtype=torch.int32, device=dev)
+        ooff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        st = torch.zeros(n, dtype=torch.int32, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        jobs.append((b, o, db, do, val, pos, ooff, st, flags))
+    torch.cuda.synchronize()
+    for i, (b, o, db, do, val, pos, ooff, st, flags) in enumerate(jobs):
+        gpu_ctx.enqueue_device(p, db, do, len(b), val, pos, ooff, st, flags, stream=streams[i & 1].cuda_stream)
+    torch.cuda.synchronize()
+    for i, (b, o, db, do, val, pos, ooff, st, flags) in enumerate(jobs):
+        ref = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, threads=8, k=21, w=11)
+        t = int(ooff[-1].item())
+        assert int(flags.item()) == 0
+        res = dict(val=val[:t].cpu().numpy().view(np.uint64), pos=pos[:t].cpu().numpy().view(np.uint32),
+                   off=ooff.cpu().numpy().view(np.uint64), status=st.cpu().numpy(), total=t)
+        assert_same(res, ref, f"batch {i} on stream {i & 1}")
