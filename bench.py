@@ -456,6 +456,25 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         # the same step gathering the uint64 arrays (+ offsets, statuses) only -- what BASELINE.json's north star names
         vo_ms = allmax(timed(torch, lambda: step(False), max(args.steps // 2, 3), 1, barrier))
+        # diagnostic: the same chain with every rank storing into arrays of its OWN (same global indices, nothing but
+        # the status words crosses NVLink) -- what the coupling of the ranks costs without the gather's traffic
+        l_val = torch.empty(cap_total, dtype=torch.int64, device=dev)
+        l_off = torch.empty(args.reads + 1, dtype=torch.int64, device=dev)
+        l_st = torch.empty(args.reads, dtype=torch.int32, device=dev)
+
+        def step_local():
+            epoch[0] += 1
+            spec = cabi.ShardSpec()
+            spec.rank, spec.n_ranks, spec.chunk_reads, spec.n_reads_global = rank, world, CHUNK, args.reads
+            spec.epoch = epoch[0] % 16383 + 1
+            for r in range(world):
+                spec.state[r] = states[r]
+            ctx.enqueue_device_sharded(ps_nopos, spec, bases, off, nb, l_val.data_ptr(), 0, l_off.data_ptr(),
+                                       l_st.data_ptr(), cap_total, flags)
+            dist.all_reduce(token)
+
+        chain_ms = allmax(timed(torch, step_local, max(args.steps // 2, 3), 1, barrier))
+        del l_val, l_off, l_st
         nvbytes = (total_out - n_out) * (9 if args.gather_pos else 8) + (args.reads - n) * 12 if rank == 0 else 0
         nvbytes = allsum_i64(nvbytes)
         gather = {"how": "one output chain across the GPUs: the sketching kernels' look-back runs through every rank's copy "
@@ -465,6 +484,7 @@ def run_ours(args, rank, world, local_rank):
                   "gathered": "uint64 values" + (" + uint8 positions" if args.gather_pos else "") + " + per-read offsets and statuses, all on rank 0",
                   "bytes_into_rank0_over_nvlink": nvbytes, "ingress_GBps": nvbytes / (ms_step * 1e-3) / 1e9,
                   "kernels_local_ms": res_ms_max, "gathered_checksum_ok": gsum_ok, "chunk_reads": CHUNK,
+                  "chain_only_ms": chain_ms,
                   "values_only": {"ms_per_step": vo_ms, "value": args.reads * READ_LEN / (vo_ms * 1e-3), "unit": "bases/s",
                                   "what": "the same step without the uint8 positions (uint64 arrays + offsets + statuses)"}}
         for a in opened:

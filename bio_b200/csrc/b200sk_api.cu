@@ -454,6 +454,8 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         if (pl.chunked || !pl.reg) return B200SK_ERR_UNSUPPORTED;
         a.shard.n = (uint32_t)spec->n_ranks; a.shard.rank = (uint32_t)spec->rank; a.shard.epoch = spec->epoch;
         for (int r = 0; r < spec->n_ranks; r++) a.shard.copy[r] = spec->state[r];
+        static const uint32_t poll_ns = [] { const char *e = getenv("B200SK_CHAIN_POLL_NS"); return e ? (uint32_t)atoi(e) : 1000u; }();
+        a.shard.poll_ns = poll_ns; // tuning knob; the default is the measured optimum
         a.shard_chunk_tiles = spec->chunk_reads / 32u;
         a.shard_n_reads = spec->n_reads_global;
     }

@@ -82,6 +82,17 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
         : "memory");
 }
 
+// 1-D bulk shared->global copy (dst/src 16-byte aligned, bytes a multiple of 16), tracked by the issuing thread's
+// bulk async-groups: commit, then wait until the sources have been READ (the buffer may be reused) or until the
+// copies are complete.
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ ordered allocation
 // status word per tile: [63:62] flag, [61:0] value.
 #define B200SK_FLAG_EMPTY 0ULL
@@ -180,6 +191,7 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t t
 struct PeerStates {
     uint64_t *copy[B200SK_MAX_RANKS]; // [r]: rank r's copy as mapped here ([rank] is the local one)
     uint32_t n, rank, epoch;
+    uint32_t poll_ns; // back-off between two polls of a status word that is not there yet
 };
 __device__ __forceinline__ uint64_t ld_state_sys(const uint64_t *p) {
     uint64_t v;
@@ -210,7 +222,12 @@ __device__ __forceinline__ uint64_t lookback_resolve_multi(const PeerStates &ps,
         uint64_t v = mstate_word(B200SK_FLAG_INC, ps.epoch, 0); // lanes before tile 0 read as "inclusive 0"
         if (idx >= 0) {
             v = ld_state_sys(state + idx);
-            while ((v >> 62) == B200SK_FLAG_EMPTY || ((v >> 48) & 0x3fffu) != want_epoch) v = ld_state_sys(state + idx);
+            // a rank that is ahead of the chain waits here with every warp it has: back off between polls, or thousands
+            // of warps hammer the few L2 lines of the chain's front -- the very lines the peers' status stores must reach
+            while ((v >> 62) == B200SK_FLAG_EMPTY || ((v >> 48) & 0x3fffu) != want_epoch) {
+                __nanosleep(ps.poll_ns);
+                v = ld_state_sys(state + idx);
+            }
         }
         const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == B200SK_FLAG_INC);
         uint64_t contrib = v & B200SK_MVAL_MASK;

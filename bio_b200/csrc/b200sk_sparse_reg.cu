@@ -762,7 +762,10 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         if (lane == 0) tile = atomicAdd(a.ticket, 1ULL);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         const uint64_t item0 = tile * 32ull;
-        if (item0 >= n_items) break;
+        if (item0 >= n_items) {
+            if (SHARD && lane == 0) bulk_wait_all(); // every bulk store of this warp has been written
+            break;
+        }
         // sharded batch: local tile -> tile of the global order (reads alike, 32 per tile).  Recomputed where it is
         // needed instead of being kept across the walk: the single-GPU kernels must not pay registers for it.
         auto global_tile = [&]() -> uint64_t {
@@ -778,6 +781,10 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
         const uint64_t span = hi > lo_al ? hi - lo_al : 0;
         const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
         const bool span_ok = bytes <= a.sm_tile_bytes;
+        if (SHARD) { // the previous tile's bulk stores must have read the buffer
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+        }
         if (lane == 0 && bytes && span_ok) {
             fence_proxy_async(); // the previous tile's generic-proxy writes to this buffer precede the async write
             mbar_expect_tx(mbar, bytes);
@@ -904,7 +911,7 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
             }
             __syncwarp();
         };
-        if (!any_overflow && total) scatter(0);
+        if (!SHARD && !any_overflow && total) scatter(0); // SHARD scatters after the prefix is known (alignment, below)
         uint64_t tb;
 #ifdef B200SK_EXPERIMENTS
         if (a.unordered) { // timing experiment only (B200SK_UNORDERED=1): ranges in completion order, WRONG output order
@@ -931,34 +938,62 @@ __global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
             if (!any_overflow) {
                 // stream the buffer out coalesced; a tile with more elements than the buffer holds takes
                 // further scatter + copy rounds
+                if constexpr (SHARD) {
+                    // The arrays are the root's (peer memory for every other rank).  Plain st.global into a saturated
+                    // NVLink backs up into the LSU pipe the walking warps load their tables through, so the tile leaves
+                    // as BULK stores (cp.async.bulk shared -> global: the copy engine's queue, not the LSU's): the
+                    // elements are scattered so that shared and global addresses agree modulo 16 bytes, a lane stores
+                    // the few elements before / after the 16-byte-aligned body, lane 0 issues one bulk store per array.
+                    const uint32_t pw = a.out_pos ? a.pos_width : 0u;
+                    const uint32_t OBS = (a.sm_tile_bytes - 48u) / (8u + pw); // entries per round (+1 value, +16 B of positions of shift)
+                    uint8_t *pb = tilebuf + (((OBS + 1u) * 8u + 15u) & ~15u);
+                    for (uint32_t r0 = 0; r0 < total; r0 += OBS) {
+                        const uint32_t n = min(OBS, total - r0);
+                        const uint64_t g0 = tb + r0; // global element index of entry 0 of this round
+                        const uint32_t vs = (uint32_t)((uintptr_t)(a.out_val + g0) >> 3) & 1u;
+                        const uint32_t pmask = pw ? 16u / pw - 1u : 0u;
+                        const uint32_t ps = pw ? (uint32_t)(((uintptr_t)a.out_pos + g0 * pw) & 15u) / pw : 0u;
+                        if (lane == 0) bulk_wait_read(); // the round before has left the buffer
+                        __syncwarp();
+                        {
+                            uint32_t pos = it.q0 - 1u;
+                            for (uint32_t j = 0; j < sink.cnt; j++) {
+                                pos += listp[j * 32u + lane];
+                                const uint32_t o = excl + j - skip - r0;
+                                if (j >= skip && o < OBS) {
+                                    obv[o + vs] = listv[j * 32u + lane];
+                                    if (pw == 1) pb[o + ps] = (uint8_t)pos;
+                                    else if (pw == 2) reinterpret_cast<uint16_t *>(pb)[o + ps] = (uint16_t)pos;
+                                    else if (pw == 4) reinterpret_cast<uint32_t *>(pb)[o + ps] = pos;
+                                }
+                            }
+                        }
+                        fence_proxy_async(); // these generic-proxy writes precede the bulk store's reads
+                        __syncwarp();
+                        // values: head (g0 odd), 16-byte-aligned body, tail
+                        uint64_t *gv = a.out_val + g0;
+                        const uint32_t vh = min(n, vs), vb = (n - vh) & ~1u;
+                        if (lane == 0 && vh) gv[0] = obv[vs];
+                        if (lane == 1 && vh + vb < n) gv[n - 1] = obv[vs + n - 1];
+                        if (lane == 0 && vb) bulk_store(gv + vh, obv + vs + vh, vb * 8u);
+                        if (pw) {
+                            uint8_t *gp = reinterpret_cast<uint8_t *>(a.out_pos) + g0 * pw;
+                            const uint32_t ph = min(n, (pmask + 1u - ps) & pmask), pbody = (n - ph) & ~pmask;
+                            // head and tail elements: at most 15 each, one per lane, moved as bytes
+                            const uint32_t hb = ph * pw, tb0 = (ph + pbody) * pw, tbn = n * pw - tb0;
+                            for (uint32_t i = lane; i < hb; i += 32u) gp[i] = pb[ps * pw + i];
+                            for (uint32_t i = lane; i < tbn; i += 32u) gp[tb0 + i] = pb[ps * pw + tb0 + i];
+                            if (lane == 0 && pbody) bulk_store(gp + hb, pb + ps * pw + hb, pbody * pw);
+                        }
+                        if (lane == 0) bulk_commit();
+                    }
+                } else
                 for (uint32_t r0 = 0; r0 < total; r0 += OB) {
                     if (r0) scatter(r0);
                     const uint32_t n = min(OB, total - r0);
                     uint64_t *gv = a.out_val + tb + r0;
-                    if (SHARD) {
-                        // peer stores: every warp store starts on a 128-byte line of the root's array (the first one of a
-                        // tile is short instead) -- a 256-byte store that straddles lines travels as three partial NVLink
-                        // writes (scripts/ubench/peer_ingress.cu: 507 vs 717 GB/s into one GPU)
-                        const int32_t sh = (int32_t)((tb + r0) & 15u);
-                        for (int32_t i = (int32_t)lane - sh; i < (int32_t)n; i += 32)
-                            if (i >= 0) gv[i] = obv[i];
-                    } else
-                        for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
-                    if (SHARD && a.out_pos && a.pos_width == 1) {
-                        // uint8 positions leave four to a 32-bit store (128-byte runs per warp instruction instead of
-                        // 32-byte ones: what a peer-mapped out_pos needs to use its NVLink packets)
-                        uint8_t *gp = reinterpret_cast<uint8_t *>(a.out_pos) + tb + r0;
-                        const uint32_t head = min(n, (4u - (uint32_t)((uintptr_t)gp & 3u)) & 3u);
-                        if (lane < head) gp[lane] = (uint8_t)obp[lane];
-                        const uint32_t nw = (n - head) >> 2;
-                        uint32_t *gw = reinterpret_cast<uint32_t *>(gp + head);
-                        for (uint32_t j = lane; j < nw; j += 32u) {
-                            const uint32_t o = head + 4u * j;
-                            gw[j] = (obp[o] & 255u) | ((obp[o + 1] & 255u) << 8) | ((obp[o + 2] & 255u) << 16) | (obp[o + 3] << 24);
-                        }
-                        const uint32_t t0 = head + 4u * nw;
-                        if (t0 + lane < n) gp[t0 + lane] = (uint8_t)obp[t0 + lane];
-                    } else if (a.out_pos)
+                    for (uint32_t i = lane; i < n; i += 32u) gv[i] = obv[i];
+                    if (a.out_pos)
                         for (uint32_t i = lane; i < n; i += 32u) store_pos(a.out_pos, a.pos_width, tb + r0 + i, obp[i]);
                     __syncwarp();
                 }

@@ -225,3 +225,57 @@ def test_sharded_chain_two_processes(mode, chunk):
     for _, a in bufs:
         ctx.gather_close(a, True)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["minimizer", "syncmer"])
+@pytest.mark.parametrize("pw,want_pos", [(1, True), (2, True), (0, True), (0, False)])
+def test_sharded_chain_single_rank_bulk_stores(mode, pw, want_pos):
+    """The SHARD kernels on ONE rank (a chain of one GPU): their flush leaves as bulk shared->global stores with a
+    16-byte-aligned body and per-lane head / tail elements -- every position width, output arrays that start at odd
+    element addresses, and a second batch behind the first (out_base-free, same arrays)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n_total = 9000 + 5
+    b, o = synth.uniform_reads(n_total, 150, 123)
+    b = b.copy()
+    b[150 * 77:150 * 77 + 40] = ord("N")
+    b[150 * 500:150 * 501] = ord("A")  # a low-complexity read: list overflow path
+    kw = dict(k=21, s=11) if mode == "syncmer" else dict(k=21, w=11)
+    omode = oracle.MODE_SYNCMER if mode == "syncmer" else oracle.MODE_MINIMIZER
+    p = cabi.make_params(cabi.MODE_SYNCMER if mode == "syncmer" else cabi.MODE_MINIMIZER, max_read_len=150,
+                         pos_width=pw, want_pos=want_pos, **kw)
+    ref = oracle.run_batch(b, o, omode, threads=8, **kw)
+    total = len(ref["val"])
+    ctx = cabi.Context(0)
+    cap = int(cabi.lib().b200sk_output_bound(C.byref(p), n_total * 150, n_total, 0))
+    bases = torch.from_numpy(np.concatenate([b, np.zeros(64, np.uint8)])).to(dev)
+    loff = torch.arange(n_total + 1, dtype=torch.int64, device=dev) * 150
+    n_tiles = (n_total + 31) // 32
+    pdt = {1: torch.uint8, 2: torch.int16}.get(pw, torch.int32)
+    for shift in (0, 1, 3):  # output arrays starting `shift` elements into their allocations
+        val = torch.full((cap + 8,), -1, dtype=torch.int64, device=dev)
+        pos = torch.zeros(cap + 8, dtype=pdt, device=dev)
+        off = torch.zeros(n_total + 1, dtype=torch.int64, device=dev)
+        status = torch.zeros(n_total, dtype=torch.int32, device=dev)
+        state = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        for epoch in (1, 2):
+            spec = cabi.ShardSpec()
+            spec.rank, spec.n_ranks, spec.chunk_reads, spec.epoch, spec.n_reads_global = 0, 1, 96, epoch, n_total
+            spec.state[0] = state.data_ptr()
+            ctx.enqueue_device_sharded(p, spec, bases, loff, n_total * 150, val[shift:].data_ptr(),
+                                       pos[shift:].data_ptr() if want_pos else 0, off.data_ptr(), status.data_ptr(),
+                                       cap, flags)
+            torch.cuda.synchronize()
+            assert int(flags.item()) == 0
+            assert np.array_equal(off.cpu().numpy().view(np.uint64), ref["off"])
+            assert np.array_equal(val[shift:shift + total].cpu().numpy().view(np.uint64), ref["val"])
+            assert int(val[shift + total].item()) == -1 and (shift == 0 or int(val[shift - 1].item()) == -1)
+            if want_pos:
+                npdt = {1: np.uint8, 2: np.uint16}.get(pw, np.uint32)
+                g = pos[shift:shift + total].cpu().numpy().view(npdt)
+                assert np.array_equal(g, ref["pos"].astype(npdt))
+                assert int(pos[shift + total].item()) == 0
+            assert np.array_equal(status.cpu().numpy(), ref["status"])
+    ctx.close()
