@@ -50,6 +50,7 @@ EXPORTS = (
     "b200sk_shard_by_bases", "b200sk_group_create", "b200sk_group_destroy", "b200sk_group_size", "b200sk_group_run",
     "b200sk_group_last_error", "b200sk_group_kernel_launches",
     "b200sk_scale_max_hash", "b200sk_reduce_device", "b200sk_run_reduced", "b200sk_enqueue_device_sharded",
+    "b200sk_enqueue_device_frames",
 )
 IPC_HANDLE_BYTES = 64
 FXSTREAM_END = 1
@@ -117,9 +118,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if _needs_build():
+    alt = os.environ.get("B200SK_LIB_PATH")  # development only: an A/B build of the same library (scripts/ab_build.sh)
+    if not alt and _needs_build():
         build()
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(alt or LIB_PATH)
     vp, u8p, u64p, u32p, i32p = (C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
     PP = C.POINTER(Params)
     L.b200sk_version.restype = C.c_int
@@ -205,6 +207,8 @@ def lib():
     L.b200sk_enqueue_device_sharded.restype = C.c_int
     L.b200sk_enqueue_device_sharded.argtypes = [vp, PP, C.POINTER(ShardSpec), u8p, u64p, C.c_uint64, C.c_uint64, vp, vp, vp,
                                                 vp, C.c_uint64, vp, u32p]
+    L.b200sk_enqueue_device_frames.restype = C.c_int
+    L.b200sk_enqueue_device_frames.argtypes = [vp, PP, u8p, u64p, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, vp, u32p]
     L.b200sk_run_reduced.restype = C.c_int
     L.b200sk_run_reduced.argtypes = [vp, PP, C.c_uint32, C.c_int, u8p, u64p, C.c_uint64, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64)]
@@ -387,6 +391,21 @@ class Context:
             C.c_void_p(val_addr), C.c_void_p(pos_addr) if pos_addr else None, C.c_void_p(off_addr),
             C.c_void_p(status_addr) if status_addr else None, int(capacity), st,
             flags.data_ptr() if flags is not None else None)
+        if rc != 0:
+            self._raise(rc)
+
+    def enqueue_device_frames(self, params, d_bases, d_off, n_bases, out_vals, out_offs, statuses, flags, stream=None):
+        """ProteinIterator over all six frames (1, 2, 3, -1, -2, -3) of every read: six value / offset / status
+        tensors in, one call (include/b200sketch.h: b200sk_enqueue_device_frames)."""
+        import torch
+        n = d_off.numel() - 1
+        st = torch.cuda.current_stream(d_bases.device).cuda_stream if stream is None else stream
+        vals = (C.c_void_p * 6)(*[t.data_ptr() for t in out_vals])
+        offs = (C.c_void_p * 6)(*[t.data_ptr() for t in out_offs])
+        sts = (C.c_void_p * 6)(*[t.data_ptr() for t in statuses]) if statuses is not None else None
+        rc = lib().b200sk_enqueue_device_frames(
+            self._h, C.byref(params), d_bases.data_ptr(), d_off.data_ptr(), n, n_bases, vals, offs, sts,
+            min(t.numel() for t in out_vals), st, flags.data_ptr() if flags is not None else None)
         if rc != 0:
             self._raise(rc)
 

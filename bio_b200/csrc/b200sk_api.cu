@@ -26,6 +26,8 @@ cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint
                                  cudaStream_t st, uint64_t n_bases);
 cudaError_t launch_dense(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
 bool build_codon_aux(int id, uint8_t *aux);
+cudaError_t launch_protein6_warp(const KArgs &a, cudaStream_t st); // b200sk_nthash.cu
+bool nthash_warp_fits(uint32_t span_max);
 cudaError_t launch_filter_scale(const uint64_t *in, uint64_t n, uint64_t max_hash, uint64_t *out, uint64_t capacity,
                                 unsigned long long *count, cudaStream_t st);
 cudaError_t launch_scan_geom(const uint64_t *off, uint64_t n_reads, const ReadGeom &g, uint64_t *out,
@@ -770,6 +772,91 @@ int b200sk_enqueue_device_sharded(b200sk_ctx *ctx, const b200sk_params *p, const
     if (n_reads == 0) return 0; // a rank without reads publishes nothing: no tile of the chain is its own
     return enqueue(ctx, *p, d_bases, d_read_off, n_reads, n_bases, d_out_val, d_out_pos, d_out_off, d_read_status,
                    capacity, 0, (cudaStream_t)stream, d_flags, spec);
+}
+
+// All six frames of ProteinIterator over one batch.  Reads of one item each (max_read_len hint), k <= 16, nucleotide
+// input: six offset scans (one per frame: counts follow from the lengths) and ONE sketching launch that fetches and
+// rewrites every tile of reads once and walks it six times (k_protein6_warp).  Anything else: six ordinary batches.
+int b200sk_enqueue_device_frames(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,
+                                 const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                                 uint64_t *const *d_out_val, uint64_t *const *d_out_off, int32_t *const *d_read_status,
+                                 uint64_t capacity, void *stream, uint32_t *d_flags) {
+    if (!ctx || !p || !d_out_val || !d_out_off || !d_read_off) return B200SK_ERR_BAD_ARG;
+    if (p->mode != B200SK_MODE_PROTEIN) return B200SK_ERR_BAD_ARG;
+    static const int kFrames[6] = {1, 2, 3, -1, -2, -3};
+    for (int fi = 0; fi < 6; fi++)
+        if (!d_out_off[fi] || (capacity && !d_out_val[fi])) return B200SK_ERR_BAD_ARG;
+    b200sk_params q = *p;
+    q.want_pos = 0; // Index() of a dense mode is the running position
+    q.circular = 0;
+    q.frame = 1;
+    int rc = b200sk_check_params(&q);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_flags) CK(cudaMemsetAsync(d_flags, 0, 4, st));
+    const bool fused = q.alphabet != B200SK_ALPHABET_PROTEIN && q.k <= 16 && q.max_read_len != 0 &&
+                       q.max_read_len <= kSingleMaxLen && nthash_warp_fits(q.max_read_len) && n_reads != 0 &&
+                       ((uintptr_t)d_bases & 15u) == 0;
+    if (!fused) {
+        for (int fi = 0; fi < 6; fi++) {
+            q.frame = kFrames[fi];
+            rc = enqueue(ctx, q, d_bases, d_read_off, n_reads, n_bases, d_out_val[fi], nullptr, d_out_off[fi],
+                         d_read_status ? d_read_status[fi] : nullptr, capacity, 0, st, d_flags);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    if ((rc = ensure_meta(ctx))) return rc;
+    if (ctx->last_done && st != ctx->last_stream) CK(cudaStreamWaitEvent(st, ctx->last_done, 0));
+    unsigned long long *meta = (unsigned long long *)ctx->meta.p;
+    CK(cudaMemsetAsync(meta, 0, 64, st));
+    if (ctx->aux_table != q.codon_table) {
+        ctx->aux_host.resize(4608);
+        if (!build_codon_aux(q.codon_table, ctx->aux_host.data())) return B200SK_ERR_CODON_TABLE;
+        CK(ctx->aux.reserve(4608));
+        CK(cudaMemcpyAsync(ctx->aux.p, ctx->aux_host.data(), 4608, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st)); // aux_host may be rebuilt by a later call
+        ctx->aux_table = q.codon_table;
+    }
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bases = d_bases; a.off = d_read_off; a.n_reads = n_reads; a.n_items = n_reads;
+    a.mode = q.mode; a.k = q.k; a.canonical = q.canonical; a.alphabet = q.alphabet;
+    a.aux = (const uint8_t *)ctx->aux.p;
+    a.capacity = capacity; a.out_base = 0; a.pos_width = 4;
+    a.flags = d_flags ? d_flags : (uint32_t *)(meta + 1);
+    a.C = 1; a.span_max = q.max_read_len;
+    const size_t sbytes = ((n_reads + 1023) / 1024 + 1) * 8;
+    CK(ctx->scan_state.reserve(sbytes));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->timing) {
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaEventRecord(ev0, st));
+    }
+    for (int fi = 0; fi < 6; fi++) { // offsets and statuses of every frame follow from the read lengths
+        a.frame = kFrames[fi];
+        a.out_off = d_out_off[fi];
+        a.status = d_read_status ? d_read_status[fi] : nullptr;
+        CK(cudaMemsetAsync(ctx->scan_state.p, 0, sbytes, st));
+        CK(cudaMemsetAsync(meta + 4, 0, 8, st));
+        CK(launch_scan_counts(a, (uint64_t *)ctx->scan_state.p, meta + 4, st));
+        a.fr_val[fi] = d_out_val[fi];
+        a.fr_off[fi] = d_out_off[fi];
+    }
+    a.frame = 1; a.out_off = nullptr; a.status = nullptr;
+    a.ticket = meta + 0;
+    CK(launch_protein6_warp(a, st));
+    ctx->launches += 7;
+    if (ctx->timing) {
+        CK(cudaEventRecord(ev1, st));
+        ctx->timing_events.emplace_back(ev0, ev1);
+    }
+    if (!ctx->last_done) CK(cudaEventCreateWithFlags(&ctx->last_done, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->last_done, st));
+    ctx->last_stream = st;
+    return 0;
 }
 
 int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,

@@ -56,6 +56,9 @@ struct KArgs {
     uint32_t key_mask; // 0xffffffc0, as a run-time value (see make_key)
     uint32_t spin_ns;  // look-back poll interval (0 = busy poll)
     unsigned long long *unordered; // timing experiment: allocate output ranges in completion order (null = ordered)
+    // all six frames of ProteinIterator in one launch (b200sk_enqueue_device_frames): [i] = frame 1, 2, 3, -1, -2, -3
+    uint64_t *fr_val[6];
+    const uint64_t *fr_off[6];
     uint32_t C;        // positions per chunk
     uint32_t span_max; // max bases one item touches
     uint32_t lcap;     // staged outputs per item (sparse modes)

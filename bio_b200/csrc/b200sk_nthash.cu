@@ -473,7 +473,202 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
     }
 }
 
+// ProteinIterator.Next (sketches/iterator-protein.go:46-90) for ALL SIX frames of every read in one launch
+// (BASELINE.json config 5: "ProteinIterator k=11 over 6-frame-translated reads").  Same tiles, tables, register
+// window and row flush as KIND_PROTEIN above, but a tile's reads are fetched ONCE (one TMA bulk copy of the whole
+// reads), rewritten to 2-bit classes once, and walked six times -- frame 1, 2, 3 down the forward strand, -1, -2, -3
+// down the reverse complement (seq/codon_tables.go:205-285) -- each frame into its own value array at the offsets
+// k_scan_reads wrote for it.  Against six launches: a sixth of the input traffic, tile set-up and conversion.
+// Reads of one item each (the caller checks), k <= 16, values only.
+// K: the k-mer size as a compile-time constant (1..16), so that wyhash's byte shuffles, shifts and its length word fold
+// into immediates (the run-time-k block spends a fifth of its instructions on them, an indirect branch per k-mer included).
+template <int DIR, bool FAST>
+__device__ __forceinline__ void protein_warm(const uint8_t *smem, uint32_t cb, uint32_t k, uint64_t &wlo, uint64_t &whi) {
+    for (uint32_t t = 0; t + 1 < k; t++) { // the k-1 amino acids before the first k-mer is complete
+        const uint64_t aa = protein_aa<DIR, FAST>(smem, cb, t);
+        wlo = (wlo >> 8) | (whi << 56);
+        whi = (whi >> 8) | (aa << 56);
+    }
+}
+template <int K>
+__global__ void __launch_bounds__(768, 1) k_protein6_warp(const KArgs a, uint32_t tile_bytes_cap, uint32_t warp_stride) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    constexpr uint32_t k = (uint32_t)K;
+    for (uint32_t i = tid; i < 4608; i += blockDim.x) smem[i] = a.aux[i];
+    __syncthreads();
+    if (tid < 64) {
+        const char letter[4] = {'A', 'C', 'T', 'G'};
+        const uint32_t c0 = tid >> 4, c1 = (tid >> 2) & 3u, c2 = tid & 3u;
+        smem[4608 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c0], (uint32_t)letter[c1], (uint32_t)letter[c2]);
+        smem[4672 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c0 ^ 2u], (uint32_t)letter[c1 ^ 2u], (uint32_t)letter[c2 ^ 2u]);
+    }
+    const uint32_t region = NH_TABLES + wid * warp_stride;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
+    const uint32_t s_tile = region + 16;
+    uint8_t *tilebuf = smem + s_tile;
+    const uint32_t s_stage = s_tile + tile_bytes_cap;
+    const uint32_t s_desc = s_stage + NH_STAGE;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint64_t n_reads = a.n_reads;
+    bool over = false;
+#pragma unroll
+    for (int fi = 0; fi < 6; fi++) over |= a.fr_off[fi][n_reads] > a.capacity;
+    if (over) {
+        if (blockIdx.x == 0 && tid == 0) atomicOr(a.flags, B200SK_FLAG_CAPACITY);
+        return;
+    }
+    ReadGeom g = a.geom();
+    uint32_t parity = 0;
+    for (;;) {
+        uint64_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.ticket, 1ULL);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        const uint64_t r0 = tile * 32ull;
+        if (r0 >= n_reads) break;
+        const uint32_t nvalid = (uint32_t)min((uint64_t)32, n_reads - r0);
+        const uint64_t r = r0 + lane;
+        const bool valid = lane < nvalid;
+        const uint64_t o0 = valid ? a.off[r] : 0, L = valid ? a.off[r + 1] - o0 : 0;
+        const uint64_t lo = __shfl_sync(0xffffffffu, o0, 0);
+        const uint64_t hi = __shfl_sync(0xffffffffu, o0 + L, (int)nvalid - 1);
+        const uint64_t lo_al = lo & ~15ULL;
+        const uint64_t span = hi > lo_al ? hi - lo_al : 0;
+        const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
+        const bool span_ok = bytes + 16u <= tile_bytes_cap;
+        if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
+        bool fast = false;
+        if (bytes && span_ok) {
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(mbar, bytes);
+                tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            uint32_t bad = 0;
+            for (uint32_t o = lane * 16u; o < bytes; o += 512u) {
+                uint4 v = *reinterpret_cast<uint4 *>(tilebuf + o);
+                v.x = fast_word(v.x, bad); v.y = fast_word(v.y, bad);
+                v.z = fast_word(v.z, bad); v.w = fast_word(v.w, bad);
+                v.x = (v.x >> 3) & 0x03030303u; v.y = (v.y >> 3) & 0x03030303u; // plain classes 0..3
+                v.z = (v.z >> 3) & 0x03030303u; v.w = (v.w >> 3) & 0x03030303u;
+                *reinterpret_cast<uint4 *>(tilebuf + o) = v;
+            }
+            fast = !__any_sync(0xffffffffu, bad != 0);
+            if (!fast) { // some other byte: the original bytes again, CodonTable.Get over the IUPAC matrix
+                __syncwarp();
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(mbar, bytes);
+                    tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
+                }
+                mbar_wait(mbar, parity);
+                parity ^= 1u;
+            }
+        }
+        __syncwarp();
+        const uint32_t sb0 = s_tile + (uint32_t)(o0 - lo_al); // the read's first base
+        const uint32_t s_row = s_stage + lane * NH_ROW;
+        for (int fi = 0; fi < 6; fi++) {
+            const int frame = fi < 3 ? fi + 1 : 2 - fi; // 1, 2, 3, -1, -2, -3
+            g.frame = frame;
+            int32_t st;
+            const uint32_t nstep = (valid && span_ok) ? read_positions(g, r, L, L, &st) : 0u;
+            uint64_t *g0 = a.fr_val[fi] + (valid ? a.fr_off[fi][r] : 0);
+            const uint32_t shift = nstep ? (uint32_t)((reinterpret_cast<uintptr_t>(g0) >> 3) & 3u) : 0u;
+            const uint32_t vend = shift + nstep;
+            *reinterpret_cast<uint64_t *>(smem + s_desc + lane * 8u) = reinterpret_cast<uint64_t>(g0 - shift);
+            uint32_t maxv = vend;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, o));
+            // cb: the first base of amino acid 0 (forward) / the base the first codon runs down from (reverse)
+            const uint32_t cb = !nstep ? s_tile + 8u : frame > 0 ? sb0 + (uint32_t)(frame - 1) : sb0 + (uint32_t)L - (uint32_t)(-frame);
+            uint64_t wlo = 0, whi = 0;
+            if (nstep) {
+                if (frame > 0) { if (fast) protein_warm<1, true>(smem, cb, k, wlo, whi); else protein_warm<1, false>(smem, cb, k, wlo, whi); }
+                else { if (fast) protein_warm<2, true>(smem, cb, k, wlo, whi); else protein_warm<2, false>(smem, cb, k, wlo, whi); }
+            }
+            const uint32_t last_block = vend ? ((vend - 1) / 16u) * 16u : 0u;
+            __syncwarp();
+            uint64_t *rowdst[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) rowdst[i] = reinterpret_cast<uint64_t *>(lds64(smem, s_desc + (4u * i + (lane >> 3)) * 8u));
+            for (uint32_t v0 = 0; v0 < maxv; v0 += 16u) {
+                const uint32_t vl = min(v0, last_block); // finished lanes re-read their own last block
+                const uint32_t lo_s = v0 == 0 ? shift : 0u;
+                const uint32_t hi_s = vend > v0 ? min(16u, vend - v0) : 0u;
+                const bool full = __all_sync(0xffffffffu, lo_s == 0u && hi_s == 16u && shift == 0u) ||
+                                  (v0 != 0 && __all_sync(0xffffffffu, hi_s == 16u));
+                const uint32_t t0 = vl - shift + k - 1u; // amino-acid index of slot 0's newest amino acid
+#define B200SK_PBLOCK(DIR, FAST_)                                                                          \
+    if (full) block16_protein<DIR, FAST_, true>(smem, cb, t0, lo_s, hi_s, s_row, k, wlo, whi);             \
+    else block16_protein<DIR, FAST_, false>(smem, cb, t0, lo_s, hi_s, s_row, k, wlo, whi);
+                if (frame > 0) { if (fast) { B200SK_PBLOCK(1, true) } else { B200SK_PBLOCK(1, false) } }
+                else { if (fast) { B200SK_PBLOCK(2, true) } else { B200SK_PBLOCK(2, false) } }
+#undef B200SK_PBLOCK
+                __syncwarp();
+                const uint32_t half = lane >> 4, e = lane & 15u;
+                if (full) {
+                    const uint32_t q = lane >> 3, e2 = (lane & 7u) * 2u;
+#pragma unroll
+                    for (uint32_t i = 0; i < 8u; i++) {
+                        const uint32_t src = 4u * i + q;
+                        ulonglong2 v;
+                        v.x = lds64(smem, s_stage + src * NH_ROW + e2 * 8u);
+                        v.y = lds64(smem, s_stage + src * NH_ROW + e2 * 8u + 8u);
+                        *reinterpret_cast<ulonglong2 *>(rowdst[i] + v0 + e2) = v;
+                    }
+                } else {
+                    const uint32_t lohi = lo_s | (hi_s << 8);
+                    for (uint32_t i = 0; i < 16u; i++) {
+                        const uint32_t src = 2u * i + half;
+                        const uint32_t lh = __shfl_sync(0xffffffffu, lohi, (int)src);
+                        if (e >= (lh & 0xffu) && e < (lh >> 8)) {
+                            uint64_t *dst = reinterpret_cast<uint64_t *>(lds64(smem, s_desc + src * 8u));
+                            dst[v0 + e] = lds64(smem, s_stage + src * NH_ROW + e * 8u);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 } // namespace
+
+cudaError_t launch_protein6_warp(const KArgs &a, cudaStream_t st) {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    const uint32_t tile_cap = ((32u * a.span_max + 32u + 15u) & ~15u) + 16u;
+    const uint32_t stride = (16u + tile_cap + NH_STAGE + NH_DESC + 15u) & ~15u;
+    int nw = (int)((227u * 1024u - NH_TABLES) / stride);
+    if (nw > 24) nw = 24;
+    if (nw < 1) return cudaErrorInvalidValue;
+    const uint32_t sm_total = NH_TABLES + (uint32_t)nw * stride;
+    void (*fn)(const KArgs, uint32_t, uint32_t) = nullptr;
+    switch (a.k) {
+#define B200SK_P6(K) case K: fn = k_protein6_warp<K>; break;
+        B200SK_P6(1) B200SK_P6(2) B200SK_P6(3) B200SK_P6(4) B200SK_P6(5) B200SK_P6(6) B200SK_P6(7) B200SK_P6(8)
+        B200SK_P6(9) B200SK_P6(10) B200SK_P6(11) B200SK_P6(12) B200SK_P6(13) B200SK_P6(14) B200SK_P6(15) B200SK_P6(16)
+#undef B200SK_P6
+    default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total);
+    if (e != cudaSuccess) return e;
+    fn<<<sm_count, nw * 32, sm_total, st>>>(a, tile_cap, stride);
+    return cudaGetLastError();
+}
 
 // occ != nullptr: the grid is sized here, report 1.
 cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ) {

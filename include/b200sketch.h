@@ -283,6 +283,20 @@ int b200sk_enqueue_device_sharded(b200sk_ctx *ctx, const b200sk_params *p, const
                                   uint64_t *d_out_val, uint32_t *d_out_pos, uint64_t *d_out_off, int32_t *d_read_status,
                                   uint64_t capacity, void *stream, uint32_t *d_flags);
 
+/* All six reading frames of a batch in one call: replaces the six loops
+ *     for _, frame := range []int{1, 2, 3, -1, -2, -3} {
+ *         it, err := sketches.NewProteinIterator(record.Seq, k, codonTable, frame); for { v, ok := it.Next() } }
+ * (sketches/iterator-protein.go:46-90; the frames of seq/codon_tables.go:205-285) -- BASELINE.json config 5.
+ * p->mode must be B200SK_MODE_PROTEIN; p->frame and p->want_pos are ignored (Index() of a dense mode is the running
+ * position).  [i] of every array argument belongs to frame 1, 2, 3, -1, -2, -3 in this order: d_out_val[i] (capacity
+ * elements each), d_out_off[i] (n_reads + 1), d_read_status[i] (n_reads; the array or single entries may be null).
+ * With a max_read_len hint of at most 384, k <= 16 and nucleotide input the reads are fetched and decoded ONCE and
+ * walked six times by one kernel; any other batch runs as six ordinary batches behind this entry point. */
+int b200sk_enqueue_device_frames(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,
+                                 const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                                 uint64_t *const *d_out_val, uint64_t *const *d_out_off, int32_t *const *d_read_status,
+                                 uint64_t capacity, void *stream, uint32_t *d_flags);
+
 /* One process, several devices: what SURVEY.md 8b calls b200sk_create(ctx**, devices, n).  One context, stream and
  * worker thread per device; b200sk_group_run has the contract of b200sk_run (host pointers in, library-owned pinned
  * arrays in read order out, valid until the next call on the group) with the reads sharded over every device of

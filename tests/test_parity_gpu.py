@@ -503,3 +503,43 @@ def test_two_streams_one_context(gpu_ctx):
         res = dict(val=val[:t].cpu().numpy().view(np.uint64), pos=pos[:t].cpu().numpy().view(np.uint32),
                    off=ooff.cpu().numpy().view(np.uint64), status=st.cpu().numpy(), total=t)
         assert_same(res, ref, f"batch {i} on stream {i & 1}")
+
+
+@pytest.mark.parametrize("k,table,alphabet,hint", [(11, 1, b"ACGT", 150), (11, 11, b"ACGTNacgtRYKMSWBDHVU", 150),
+                                                    (16, 1, b"ACGT", 150), (5, 4, b"ACGTacgt", 384),
+                                                    (20, 1, b"ACGT", 150), (11, 1, b"ACGT", 0)])
+def test_protein_six_frames_one_call(gpu_ctx, k, table, alphabet, hint):
+    """b200sk_enqueue_device_frames: ProteinIterator over the six frames of every read (BASELINE.json config 5) -- the
+    fused kernel (hint <= 384, k <= 16) and the six-batch path behind the same entry point, against the oracle frame
+    by frame: values, offsets, statuses; ragged reads (too short for some frames, empty), IUPAC and lower case."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(31 + k)
+    top = hint if hint else 150
+    lens = np.concatenate([np.full(3000, top), rng.integers(0, top + 1, size=2000), [0, 1, 2, 3 * k - 1, 3 * k, 3 * k + 1, 3 * k + 2]])
+    if hint == 0:
+        lens = np.concatenate([lens, synth.ont_like_lengths(20, 5, mean=1500)])
+    b, o = synth.ragged_reads(lens, 77 + k, alphabet=alphabet)
+    n = len(o) - 1
+    p = cabi.make_params(cabi.MODE_PROTEIN, k, codon_table=table, max_read_len=hint, want_pos=False)
+    db = torch.from_numpy(np.concatenate([b, np.zeros(64, np.uint8)])).to(dev)
+    do = torch.from_numpy(o.astype(np.int64)).to(dev)
+    cap = int(cabi.lib().b200sk_output_bound(ctypes.byref(p), len(b), n, 1)) + 8
+    vals = [torch.full((cap,), -1, dtype=torch.int64, device=dev) for _ in range(6)]
+    offs = [torch.zeros(n + 1, dtype=torch.int64, device=dev) for _ in range(6)]
+    sts = [torch.full((n,), 99, dtype=torch.int32, device=dev) for _ in range(6)]
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    l0 = gpu_ctx.kernel_launches()
+    gpu_ctx.enqueue_device_frames(p, db, do, len(b), vals, offs, sts, flags)
+    torch.cuda.synchronize()
+    launches = gpu_ctx.kernel_launches() - l0
+    assert int(flags.item()) == 0
+    if hint and k <= 16:
+        assert launches == 7  # six offset scans + ONE sketching launch
+    for fi, frame in enumerate((1, 2, 3, -1, -2, -3)):
+        ref = oracle.run_batch(b, o, oracle.MODE_PROTEIN, threads=8, k=k, codon_table=table, frame=frame)
+        t = int(offs[fi][-1].item())
+        res = dict(val=vals[fi][:t].cpu().numpy().view(np.uint64), pos=None, off=offs[fi].cpu().numpy().view(np.uint64),
+                   status=sts[fi].cpu().numpy(), total=t)
+        assert_same(res, ref, f"frame {frame}")
+        assert int(vals[fi][t].item()) == -1
