@@ -50,7 +50,7 @@ EXPORTS = (
     "b200sk_shard_by_bases", "b200sk_group_create", "b200sk_group_destroy", "b200sk_group_size", "b200sk_group_run",
     "b200sk_group_last_error", "b200sk_group_kernel_launches",
     "b200sk_scale_max_hash", "b200sk_reduce_device", "b200sk_run_reduced", "b200sk_enqueue_device_sharded",
-    "b200sk_enqueue_device_frames",
+    "b200sk_enqueue_device_frames", "b200sk_run_frames",
 )
 IPC_HANDLE_BYTES = 64
 FXSTREAM_END = 1
@@ -209,6 +209,8 @@ def lib():
                                                 vp, C.c_uint64, vp, u32p]
     L.b200sk_enqueue_device_frames.restype = C.c_int
     L.b200sk_enqueue_device_frames.argtypes = [vp, PP, u8p, u64p, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, vp, u32p]
+    L.b200sk_run_frames.restype = C.c_int
+    L.b200sk_run_frames.argtypes = [vp, PP, u8p, u64p, C.c_uint64, vp, vp, vp, vp]
     L.b200sk_run_reduced.restype = C.c_int
     L.b200sk_run_reduced.argtypes = [vp, PP, C.c_uint32, C.c_int, u8p, u64p, C.c_uint64, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64)]
@@ -408,6 +410,27 @@ class Context:
             min(t.numel() for t in out_vals), st, flags.data_ptr() if flags is not None else None)
         if rc != 0:
             self._raise(rc)
+
+    def run_frames(self, params, bases, read_off, copy=True):
+        """Host entry point of the six-frame ProteinIterator call: a list of six dicts (val, off, status, total) for
+        frames 1, 2, 3, -1, -2, -3 (include/b200sketch.h: b200sk_run_frames)."""
+        import numpy as np
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n = len(read_off) - 1
+        ov, oo, os_ = (C.c_void_p * 6)(), (C.c_void_p * 6)(), (C.c_void_p * 6)()
+        tot = (C.c_uint64 * 6)()
+        rc = lib().b200sk_run_frames(self._h, C.byref(params), bases.ctypes.data, read_off.ctypes.data, n, ov, oo, os_, tot)
+        if rc != 0:
+            self._raise(rc)
+
+        def view(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dtype=dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dt).itemsize,)).view(dt)
+            return a.copy() if copy else a
+        return [dict(val=view(ov[i], int(tot[i]), np.uint64), pos=None, off=view(oo[i], n + 1, np.uint64),
+                     status=view(os_[i], n, np.int32), total=int(tot[i])) for i in range(6)]
 
     def run_reduced(self, params, bases, read_off, scale=1, unique=True, copy=True):
         """Host entry point with the reduction inside: returns the sorted (distinct) values <= MaxUint64/scale."""

@@ -859,6 +859,72 @@ int b200sk_enqueue_device_frames(b200sk_ctx *ctx, const b200sk_params *p, const 
     return 0;
 }
 
+// Host entry point of the six-frame call: the batch goes to the device ONCE, the six frames' sketches come back in
+// library-owned pinned arrays (valid until the next b200sk_run* on this context).  One copy in, one launch group, six
+// copies out on the context's stream; the values dominate the PCIe traffic (8 B per amino-acid k-mer and frame).
+int b200sk_run_frames(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
+                      uint64_t n_reads, uint64_t **out_val, uint64_t **out_off, int32_t **read_status, uint64_t *n_out) {
+    if (!ctx || !p || !read_off || !out_val || !out_off || !n_out) return B200SK_ERR_BAD_ARG;
+    if (p->mode != B200SK_MODE_PROTEIN) return B200SK_ERR_BAD_ARG;
+    int rc = b200sk_check_params(p);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    const uint64_t b0 = read_off[0], n_bases = read_off[n_reads] - b0;
+    if (n_bases && !bases) return B200SK_ERR_BAD_ARG;
+    const uint64_t cap = b200sk_output_bound(p, n_bases, n_reads, 1) + 8; // per frame
+    CK(ctx->d_bases.reserve(n_bases + 64));
+    CK(ctx->d_off.reserve((n_reads + 1) * 8));
+    CK(ctx->d_val.reserve(6 * cap * 8));
+    CK(ctx->d_ooff.reserve(6 * (n_reads + 1) * 8));
+    CK(ctx->d_status.reserve(6 * (n_reads + 1) * 4));
+    CK(ctx->h_ooff.reserve(6 * (n_reads + 1) * 8));
+    CK(ctx->h_status.reserve(6 * (n_reads + 1) * 4));
+    CK(ctx->h_meta.reserve(64));
+    const uint64_t *offs = read_off;
+    std::vector<uint64_t> rebased;
+    if (b0) { // offsets relative to the first base of the batch
+        rebased.resize(n_reads + 1);
+        for (uint64_t i = 0; i <= n_reads; i++) rebased[i] = read_off[i] - b0;
+        offs = rebased.data();
+    }
+    CK(cudaMemsetAsync((uint8_t *)ctx->d_bases.p + n_bases, 0, 64, st)); // the TMA tile may read up to 16 bytes past the end
+    if (n_bases) CK(cudaMemcpyAsync(ctx->d_bases.p, bases + b0, n_bases, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off.p, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint64_t *dv[6], *doff[6];
+    int32_t *dst[6];
+    for (int fi = 0; fi < 6; fi++) {
+        dv[fi] = (uint64_t *)ctx->d_val.p + fi * cap;
+        doff[fi] = (uint64_t *)ctx->d_ooff.p + fi * (n_reads + 1);
+        dst[fi] = (int32_t *)ctx->d_status.p + fi * (n_reads + 1);
+    }
+    uint32_t *d_flags = (uint32_t *)ctx->d_status.p + 6 * (n_reads + 1) - 1; // the last (unused) status slot
+    rc = b200sk_enqueue_device_frames(ctx, p, (const uint8_t *)ctx->d_bases.p, (const uint64_t *)ctx->d_off.p, n_reads,
+                                      n_bases, dv, doff, dst, cap, st, d_flags);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_ooff.p, ctx->d_ooff.p, 6 * (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, 6 * (n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); // the offset tables hold the totals
+    const uint32_t flags = ((const uint32_t *)ctx->h_status.p)[6 * (n_reads + 1) - 1];
+    if (flags & B200SK_FLAG_SPAN) return B200SK_ERR_BAD_ARG; // max_read_len hint smaller than a read
+    if (flags & B200SK_FLAG_CAPACITY) return B200SK_ERR_CAPACITY;
+    uint64_t total = 0, start[6];
+    for (int fi = 0; fi < 6; fi++) {
+        n_out[fi] = ((const uint64_t *)ctx->h_ooff.p)[fi * (n_reads + 1) + n_reads];
+        start[fi] = total;
+        total += n_out[fi];
+    }
+    CK(ctx->h_val.reserve((total + 1) * 8));
+    for (int fi = 0; fi < 6; fi++) {
+        if (n_out[fi]) CK(cudaMemcpyAsync((uint64_t *)ctx->h_val.p + start[fi], dv[fi], n_out[fi] * 8, cudaMemcpyDeviceToHost, st));
+        out_val[fi] = (uint64_t *)ctx->h_val.p + start[fi];
+        out_off[fi] = (uint64_t *)ctx->h_ooff.p + fi * (n_reads + 1);
+        if (read_status) read_status[fi] = (int32_t *)ctx->h_status.p + fi * (n_reads + 1);
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int b200sk_run_device(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *d_bases,
                       const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, uint64_t *d_out_val,
                       uint32_t *d_out_pos, uint64_t *d_out_off, int32_t *d_read_status, uint64_t capacity,

@@ -162,6 +162,14 @@ __device__ __forceinline__ void block16_protein(uint8_t *smem, uint32_t cb, uint
     }
 }
 
+template <int DIR, bool FAST>
+__device__ __forceinline__ void protein_warm(const uint8_t *smem, uint32_t cb, uint32_t k, uint64_t &wlo, uint64_t &whi) {
+    for (uint32_t t = 0; t + 1 < k; t++) { // the k-1 amino acids before the first k-mer is complete
+        const uint64_t aa = protein_aa<DIR, FAST>(smem, cb, t);
+        wlo = (wlo >> 8) | (whi << 56);
+        whi = (whi >> 8) | (aa << 56);
+    }
+}
 struct NItem {
     uint64_t gb0, obase;
     uint32_t nb, nstep, p0; // p0: Index() of the item's first element
@@ -204,11 +212,12 @@ __device__ __forceinline__ void nthash_item(const KArgs &a, const ReadGeom &g, u
     it.gb0 = o0 + p0;
 }
 
-template <int KIND, bool CANON>
+// KC: KIND_PROTEIN only -- the k-mer size as a compile-time constant (1..16; 0 = a.k), see k_protein6_warp
+template <int KIND, bool CANON, int KC = 0>
 __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t tile_bytes_cap, uint32_t warp_stride) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const int k = a.k;
+    const int k = KC ? KC : a.k;
     if (KIND == KIND_PROTEIN) {
         // the aux block (codon matrix over IUPAC codes, base2code, pair letters), then the 64-entry tables of the
         // all-ACGT fast path: class = (byte >> 1) & 3 -> a, c, t, g; complement = class ^ 2
@@ -349,15 +358,11 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
         const int pdir = KIND != KIND_PROTEIN ? 0 : g.protein_input ? 0 : a.frame > 0 ? 1 : 2;
         const uint32_t cb = pdir == 2 ? sb + it.nb - 1u : sb;
         if (KIND == KIND_PROTEIN) {
-            if (nstep)
-                for (uint32_t t = 0; t + 1 < (uint32_t)k; t++) {
-                    uint64_t aa;
-                    if (pdir == 0) aa = protein_aa<0, false>(smem, cb, t);
-                    else if (pdir == 1) aa = fast ? protein_aa<1, true>(smem, cb, t) : protein_aa<1, false>(smem, cb, t);
-                    else aa = fast ? protein_aa<2, true>(smem, cb, t) : protein_aa<2, false>(smem, cb, t);
-                    fh = (fh >> 8) | (rh << 56);
-                    rh = (rh >> 8) | (aa << 56);
-                }
+            if (nstep) {
+                if (pdir == 0) protein_warm<0, false>(smem, cb, (uint32_t)k, fh, rh);
+                else if (pdir == 1) { if (fast) protein_warm<1, true>(smem, cb, (uint32_t)k, fh, rh); else protein_warm<1, false>(smem, cb, (uint32_t)k, fh, rh); }
+                else { if (fast) protein_warm<2, true>(smem, cb, (uint32_t)k, fh, rh); else protein_warm<2, false>(smem, cb, (uint32_t)k, fh, rh); }
+            }
         } else if (KIND == KIND_KMER) {
             if (nstep)
                 for (int j = 0; j < k - 1; j++) {
@@ -482,14 +487,6 @@ __global__ void __launch_bounds__(768, 1) k_nthash_warp(const KArgs a, uint32_t 
 // Reads of one item each (the caller checks), k <= 16, values only.
 // K: the k-mer size as a compile-time constant (1..16), so that wyhash's byte shuffles, shifts and its length word fold
 // into immediates (the run-time-k block spends a fifth of its instructions on them, an indirect branch per k-mer included).
-template <int DIR, bool FAST>
-__device__ __forceinline__ void protein_warm(const uint8_t *smem, uint32_t cb, uint32_t k, uint64_t &wlo, uint64_t &whi) {
-    for (uint32_t t = 0; t + 1 < k; t++) { // the k-1 amino acids before the first k-mer is complete
-        const uint64_t aa = protein_aa<DIR, FAST>(smem, cb, t);
-        wlo = (wlo >> 8) | (whi << 56);
-        whi = (whi >> 8) | (aa << 56);
-    }
-}
 template <int K>
 __global__ void __launch_bounds__(768, 1) k_protein6_warp(const KArgs a, uint32_t tile_bytes_cap, uint32_t warp_stride) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -687,7 +684,15 @@ cudaError_t launch_nthash_warp(const KArgs &a, cudaStream_t st, int *occ) {
     if (nw < 1) return cudaErrorInvalidValue;
     const uint32_t sm_total = NH_TABLES + (uint32_t)nw * stride;
     void (*fn)(const KArgs, uint32_t, uint32_t);
-    if (a.mode == B200SK_MODE_PROTEIN) fn = k_nthash_warp<KIND_PROTEIN, true>;
+    if (a.mode == B200SK_MODE_PROTEIN) {
+        switch (a.k) {
+#define B200SK_PK(K) case K: fn = k_nthash_warp<KIND_PROTEIN, true, K>; break;
+            B200SK_PK(1) B200SK_PK(2) B200SK_PK(3) B200SK_PK(4) B200SK_PK(5) B200SK_PK(6) B200SK_PK(7) B200SK_PK(8)
+            B200SK_PK(9) B200SK_PK(10) B200SK_PK(11) B200SK_PK(12) B200SK_PK(13) B200SK_PK(14) B200SK_PK(15) B200SK_PK(16)
+#undef B200SK_PK
+        default: return cudaErrorInvalidValue;
+        }
+    }
     else if (a.mode == B200SK_MODE_KMER) fn = k_nthash_warp<KIND_KMER, true>;
     else fn = a.canonical ? k_nthash_warp<KIND_NTHASH, true> : k_nthash_warp<KIND_NTHASH, false>;
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total);

@@ -250,6 +250,39 @@ func (b *Batch) ProteinIterator(k, codonTable, frame int) (*Result, error) {
 	return b.run(&p)
 }
 
+// ProteinFrames == six sketches.NewProteinIterator loops, frame 1, 2, 3, -1, -2, -3 in this order, over every read
+// (iterator-protein.go:46-90; BASELINE.json config 5) through ONE library call: the batch crosses PCIe once and, for
+// reads of at most 384 bases and k <= 16, is fetched and decoded once on the device (b200sk_run_frames).
+// Results[i].ProteinIterator(r) replays frame i of read r.  The six Results share the context's output arrays and
+// become stale together at the next run.
+func (b *Batch) ProteinFrames(k, codonTable int) ([6]*Result, error) {
+	var out [6]*Result
+	p := C.b200sk_params{mode: C.B200SK_MODE_PROTEIN, k: C.int32_t(k), codon_table: C.int32_t(codonTable), frame: 1}
+	p.alphabet = b.alpha
+	p.max_read_len = C.uint32_t(b.maxLen)
+	if rc := C.b200sk_check_params(&p); rc != 0 {
+		return out, codeToError(rc)
+	}
+	n := len(b.off) - 1
+	var v, o [6]*C.uint64_t
+	var st [6]*C.int32_t
+	var total [6]C.uint64_t
+	rc := C.b200sk_run_frames(b.ctx.h, &p, (*C.uint8_t)(b.bases), &b.off[0], C.uint64_t(n), &v[0], &o[0], &st[0], &total[0])
+	if rc != 0 {
+		return out, codeToError(rc)
+	}
+	b.ctx.gen++
+	for i := range out {
+		out[i] = &Result{
+			val:    unsafe.Slice((*uint64)(unsafe.Pointer(v[i])), int(total[i])),
+			off:    unsafe.Slice((*uint64)(unsafe.Pointer(o[i])), n+1),
+			status: unsafe.Slice((*int32)(unsafe.Pointer(st[i])), n),
+			mode:   p.mode, ctx: b.ctx, gen: b.ctx.gen, // pos == nil: Index() is the running position (replay.index)
+		}
+	}
+	return out, nil
+}
+
 // ProteinMinimizerSketch == sketches.NewProteinMinimizerSketch (sketch-protein.go:62).
 func (b *Batch) ProteinMinimizerSketch(k, codonTable, frame, w int) (*Result, error) {
 	if w > (1<<31)-1 {
@@ -298,14 +331,25 @@ func (it *replay) next() (uint64, bool) {
 	return v, true
 }
 
-func (it *replay) index() int { return int(it.pos[it.i-1]) }
+// index: what Index() returns after the last Next().  Results without a position array (ProteinFrames: a dense mode,
+// values only) count it: the i-th element of a dense iterator sits at position i.
+func (it *replay) index() int {
+	if it.pos == nil {
+		return it.i - 1
+	}
+	return int(it.pos[it.i-1])
+}
 
 // IdxValues returns the read's whole slice as the reference's IdxValue pairs (what its users collect from a Next loop).
 func (it *replay) IdxValues() []IdxValue {
 	it.res.check()
 	out := make([]IdxValue, len(it.val))
 	for j := range it.val {
-		out[j] = IdxValue{Idx: int(it.pos[j]), Val: it.val[j]}
+		idx := j
+		if it.pos != nil {
+			idx = int(it.pos[j])
+		}
+		out[j] = IdxValue{Idx: idx, Val: it.val[j]}
 	}
 	return out
 }
@@ -332,7 +376,10 @@ type ProteinMinimizerSketch struct{ replay }
 func (r *Result) slice(i int) (replay, error) {
 	r.check()
 	st := C.int(r.status[i])
-	rp := replay{val: r.val[r.off[i]:r.off[i+1]], pos: r.pos[r.off[i]:r.off[i+1]], res: r}
+	rp := replay{val: r.val[r.off[i]:r.off[i+1]], res: r}
+	if r.pos != nil {
+		rp.pos = r.pos[r.off[i]:r.off[i+1]]
+	}
 	if st != 0 && st != C.B200SK_ERR_ILLEGAL_BASE {
 		return rp, codeToError(st) // what the reference constructor returns for this read (ErrShortSeq ...)
 	}

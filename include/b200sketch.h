@@ -297,6 +297,12 @@ int b200sk_enqueue_device_frames(b200sk_ctx *ctx, const b200sk_params *p, const 
                                  uint64_t *const *d_out_val, uint64_t *const *d_out_off, int32_t *const *d_read_status,
                                  uint64_t capacity, void *stream, uint32_t *d_flags);
 
+/* The same from host memory (the contract of b200sk_run: record bytes + offsets in, library-owned pinned arrays out,
+ * valid until the next b200sk_run* on this context): the batch crosses PCIe once for all six frames.
+ * out_val[i] / out_off[i] / read_status[i] / n_out[i]: frame 1, 2, 3, -1, -2, -3 (read_status may be null). */
+int b200sk_run_frames(b200sk_ctx *ctx, const b200sk_params *p, const uint8_t *bases, const uint64_t *read_off,
+                      uint64_t n_reads, uint64_t **out_val, uint64_t **out_off, int32_t **read_status, uint64_t *n_out);
+
 /* One process, several devices: what SURVEY.md 8b calls b200sk_create(ctx**, devices, n).  One context, stream and
  * worker thread per device; b200sk_group_run has the contract of b200sk_run (host pointers in, library-owned pinned
  * arrays in read order out, valid until the next call on the group) with the reads sharded over every device of

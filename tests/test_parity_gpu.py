@@ -543,3 +543,19 @@ def test_protein_six_frames_one_call(gpu_ctx, k, table, alphabet, hint):
                    status=sts[fi].cpu().numpy(), total=t)
         assert_same(res, ref, f"frame {frame}")
         assert int(vals[fi][t].item()) == -1
+
+
+@pytest.mark.parametrize("k,hint", [(11, 150), (7, 0)])
+def test_protein_six_frames_host_entry(gpu_ctx, k, hint):
+    """b200sk_run_frames: the host form of the six-frame call (one copy in, six sketches out), a batch that does not
+    start at offset 0 included."""
+    lens = np.concatenate([np.full(2000, 150), np.random.default_rng(3).integers(0, 151, size=1500), [0, 3 * k - 1, 3 * k]])
+    b, o = synth.ragged_reads(lens, 321, alphabet=b"ACGTACGTACGTN")
+    p = cabi.make_params(cabi.MODE_PROTEIN, k, max_read_len=hint, want_pos=False)
+    for skip in (0, 5):  # skip > 0: read_off[0] != 0
+        res = gpu_ctx.run_frames(p, b, o[skip:])
+        for fi, frame in enumerate((1, 2, 3, -1, -2, -3)):
+            ref = oracle.run_batch(b[int(o[skip]):], o[skip:] - o[skip], oracle.MODE_PROTEIN, threads=8, k=k, frame=frame)
+            assert_same(res[fi], ref, f"frame {frame} skip {skip}")
+    with pytest.raises(cabi.SketchError):
+        gpu_ctx.run_frames(cabi.make_params(cabi.MODE_NTHASH, 21), b, o)
