@@ -21,6 +21,7 @@ cudaError_t launch_main(const KArgs &a, int threads, int blocks, cudaStream_t st
 int main_kernel_occupancy(const KArgs &a, int threads);
 cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStream_t st, int *occ);
 bool sparse_reg_supported(int mode, int k, int w, int s);
+int sparse_reg_max_warps(int mode, int k, int w, int s);
 cudaError_t launch_scan_counts(const KArgs &a, uint64_t *tile_state, unsigned long long *ticket, cudaStream_t st);
 cudaError_t launch_first_illegal(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *ill,
                                  cudaStream_t st, uint64_t n_bases);
@@ -271,7 +272,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
             const uint32_t pos_bytes = (c.lcap + 1) * 32u; // one position byte per slot and lane
             c.sm_ring_bytes = up16(c.sm_listp + pos_bytes); // per-warp stride
             int nw = (int)((232448u - 1024u - c.sm_tile) / c.sm_ring_bytes);
-            if (nw > 16) nw = 16;
+            if (nw > sparse_reg_max_warps(mode, k, w, s)) nw = sparse_reg_max_warps(mode, k, w, s);
             {
                 static const int cap_nw = [] { const char *e = getenv("B200SK_MAX_WARPS"); return e ? atoi(e) : 0; }();
                 if (cap_nw > 0 && nw > cap_nw) nw = cap_nw; // testing knob: occupancy sweep
@@ -458,6 +459,8 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         for (int r = 0; r < spec->n_ranks; r++) a.shard.copy[r] = spec->state[r];
         static const uint32_t poll_ns = [] { const char *e = getenv("B200SK_CHAIN_POLL_NS"); return e ? (uint32_t)atoi(e) : 1000u; }();
         a.shard.poll_ns = poll_ns; // tuning knob; the default is the measured optimum
+        static const uint32_t poll_free = [] { const char *e = getenv("B200SK_CHAIN_POLL_FREE"); return e ? (uint32_t)atoi(e) : 0u; }();
+        a.shard.poll_free = poll_free;
         a.shard_chunk_tiles = spec->chunk_reads / 32u;
         a.shard_n_reads = spec->n_reads_global;
     }

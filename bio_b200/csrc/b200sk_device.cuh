@@ -191,7 +191,8 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *state, uint64_t t
 struct PeerStates {
     uint64_t *copy[B200SK_MAX_RANKS]; // [r]: rank r's copy as mapped here ([rank] is the local one)
     uint32_t n, rank, epoch;
-    uint32_t poll_ns; // back-off between two polls of a status word that is not there yet
+    uint32_t poll_ns; // back-off between two polls of a status word that is not there yet ...
+    uint32_t poll_free; // ... after this many polls without one
 };
 __device__ __forceinline__ uint64_t ld_state_sys(const uint64_t *p) {
     uint64_t v;
@@ -224,8 +225,11 @@ __device__ __forceinline__ uint64_t lookback_resolve_multi(const PeerStates &ps,
             v = ld_state_sys(state + idx);
             // a rank that is ahead of the chain waits here with every warp it has: back off between polls, or thousands
             // of warps hammer the few L2 lines of the chain's front -- the very lines the peers' status stores must reach
+            // (the first polls go out back to back: a predecessor that is merely a little late -- the only kind of wait
+            // there is on one GPU -- should not cost a sleep)
+            uint32_t tries = 0;
             while ((v >> 62) == B200SK_FLAG_EMPTY || ((v >> 48) & 0x3fffu) != want_epoch) {
-                __nanosleep(ps.poll_ns);
+                if (++tries > ps.poll_free) __nanosleep(ps.poll_ns);
                 v = ld_state_sys(state + idx);
             }
         }

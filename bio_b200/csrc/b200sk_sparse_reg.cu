@@ -717,8 +717,13 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
 // SHARD: this rank's tiles are chunks of ONE tile chain shared by several GPUs (b200sk_enqueue_device_sharded): the
 // look-back runs over the ranks' replicated status words, the output arrays are the root's, indexed globally.  A
 // template parameter, not a run-time branch: kept in the single-GPU kernel it cost 5 % (registers 118 -> 122).
+// Warps per CTA an instantiation is launched with at most.  The register file is split over the four schedulers: with
+// four warps on a scheduler a thread gets 128 registers whatever the CTA size, with three 168.  Wide syncmer windows
+// (3 W words of window state + two hashers) spill at 128, and shared memory holds only 13-14 of their warps anyway --
+// 13 or 14 warps run no faster than 12 (the ordered chain moves at the pace of the schedulers that hold four).
+template <int MODE, int W> constexpr int max_warps() { return MODE == B200SK_MODE_SYNCMER && W >= 16 ? 12 : 16; }
 template <int MODE, int W, bool KEYED, bool SHARD>
-__global__ void __launch_bounds__(512, 1) k_sparse_warp(const KArgs a) {
+__global__ void __launch_bounds__(32 * max_warps<MODE, W>(), 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     constexpr bool SYNC = MODE == B200SK_MODE_SYNCMER;
@@ -1168,6 +1173,13 @@ cudaError_t launch_sparse_reg(const KArgs &a, int threads, int blocks, cudaStrea
     e = launch_sparse_reg_part4(a, window, threads, blocks, st, occ, &has);
     if (has) return e;
     return cudaErrorInvalidValue;
+}
+
+int sparse_reg_max_warps(int mode, int k, int w, int s) {
+    // protein minimizers: measured, not derived -- 16 warps 4.08 ms, 14 4.35, 12 3.63, 10 3.81 per 10 M reads
+    // (profiles/r02af_warps.txt); an odd number of warps per scheduler pair always loses to the next multiple of four
+    if (mode == B200SK_MODE_PROTEIN_MINIMIZER) return 12;
+    return mode == B200SK_MODE_SYNCMER && window_of(mode, k, w, s) >= 16 ? 12 : 16; // max_warps<MODE, W>()
 }
 
 bool sparse_reg_supported(int mode, int k, int w, int s) {

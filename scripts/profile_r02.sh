@@ -21,4 +21,11 @@ tail -2 gpurun_out/ncu_full_$TAG.log | cut -c1-300
 ncu --set full --clock-control none --import-source on -k regex:"k_radix|k_filter|k_unique|k_scan_hist" -c 12 -f -o gpurun_out/prof_${TAG}_reduce \
     python bench.py --reads 20000000 --steps 1 --warmup 3 --no-e2e --no-cpu --no-secondary --parity-reads 2000 > gpurun_out/ncu_full_${TAG}_reduce.log 2>&1
 tail -2 gpurun_out/ncu_full_${TAG}_reduce.log | cut -c1-300
-ls -la gpurun_out | tail -6
+# the fused six-frame protein kernel (C5) and the long-read syncmer kernel (C4) at the bench's sizes
+ncu --set full --clock-control none --import-source on -k regex:"k_protein6_warp" -s 2 -c 1 -f -o gpurun_out/prof_${TAG}_c5 \
+    python bench.py --reads 2000000 --steps 1 --warmup 3 --no-e2e --no-cpu --no-reduce --parity-reads 2000 > gpurun_out/ncu_full_${TAG}_c5.log 2>&1
+tail -2 gpurun_out/ncu_full_${TAG}_c5.log | cut -c1-300
+ncu --set full --clock-control none --import-source on -k regex:"k_sparse_warp<\(int\)3" -s 2 -c 1 -f -o gpurun_out/prof_${TAG}_c4 \
+    python bench.py --reads 2000000 --steps 1 --warmup 3 --no-e2e --no-cpu --no-reduce --parity-reads 2000 > gpurun_out/ncu_full_${TAG}_c4.log 2>&1
+tail -2 gpurun_out/ncu_full_${TAG}_c4.log | cut -c1-300
+ls -la gpurun_out | tail -8

@@ -1,0 +1,7 @@
+#!/bin/bash
+# 2 GPUs: full ncu capture of the long-read syncmer kernel (C4 geometry, 200 k ONT-like reads), then the poll-policy sweep
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:k_sparse_warp -s 3 -c 1 -f -o gpurun_out/prof_r02z_c4 \
+    python scripts/run_ont.py syncmer 200000 3 > gpurun_out/ncu_full_r02z_c4.log 2>&1
+tail -2 gpurun_out/ncu_full_r02z_c4.log | cut -c1-200
+bash scripts/runs/r02ac.sh 2
