@@ -87,6 +87,43 @@ __device__ __forceinline__ uint64_t wyhash_window(uint64_t wlo, uint64_t whi, ui
     return wymum(h, (uint64_t)k ^ WYP5);
 }
 
+// The same for a k known only at run time, without a switch per k-mer: the tail word's byte shuffle (wy_tail_of) is a
+// permutation of the word's bytes with zero fill, i.e. two PRMTs whose selectors depend on the tail length alone --
+// computed once per item.  Selector nibble 7 picks the word's top byte, which is zero whenever the tail is shorter
+// than 8 bytes.
+struct WyPlan {
+    uint32_t k, sft, sel_lo, sel_hi;
+};
+__device__ __forceinline__ WyPlan wy_plan(uint32_t k) {
+    WyPlan p;
+    p.k = k;
+    p.sft = 8u * ((k <= 8u ? 8u : 16u) - k);
+    switch (k <= 8u ? k : k - 8u) {
+    case 3: p.sel_lo = 0x7102u; p.sel_hi = 0x7777u; break;
+    case 5: p.sel_lo = 0x2104u; p.sel_hi = 0x7773u; break;
+    case 6: p.sel_lo = 0x1054u; p.sel_hi = 0x7732u; break;
+    case 7: p.sel_lo = 0x0546u; p.sel_hi = 0x7321u; break;
+    case 8: p.sel_lo = 0x7654u; p.sel_hi = 0x3210u; break;
+    default: p.sel_lo = 0x3210u; p.sel_hi = 0x7654u; break; // 1, 2, 4: as is
+    }
+    return p;
+}
+__device__ __forceinline__ uint64_t wy_tail_perm(uint64_t v, const WyPlan &p) {
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    return ((uint64_t)__byte_perm(lo, hi, p.sel_hi) << 32) | __byte_perm(lo, hi, p.sel_lo);
+}
+__device__ __forceinline__ uint64_t wyhash_window(uint64_t wlo, uint64_t whi, const WyPlan &p) {
+    const uint64_t seed = 1ull ^ WYP0;
+    uint64_t h;
+    if (p.k <= 8u) {
+        h = wymum(seed, wy_tail_perm(whi >> p.sft, p) ^ WYP1);
+    } else {
+        const uint64_t first8 = p.sft ? ((wlo >> p.sft) | (whi << (64u - p.sft))) : wlo;
+        h = wymum(((first8 << 32) | (first8 >> 32)) ^ seed, wy_tail_perm(whi >> p.sft, p) ^ WYP2);
+    }
+    return wymum(h, (uint64_t)p.k ^ WYP5);
+}
+
 
 // ------------------------------------------------------------------ codon lookup
 // aux layout: [0,4096) matrix[i][j][k] over 4-bit IUPAC codes, [4096,4352) base2code (0xff = invalid),

@@ -670,6 +670,7 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
     }
     WinReg<W> wm;
     wm.init(w_runtime);
+    const WyPlan wp = wy_plan((uint32_t)k);
     uint32_t prev = W - 1; // frame-relative position of the previous window's minimum (none yet)
     uint32_t pin = sb + (uint32_t)k - 1;
     uint64_t mv;
@@ -679,7 +680,7 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
         const uint64_t aa = lds_u8(sm, pin + (J));                         \
         wlo = (wlo >> 8) | (whi << 56);                                    \
         whi = (whi >> 8) | (aa << 56);                                     \
-        if (wm.push(J, FIRST, wyhash_window(wlo, whi, (uint32_t)k), mv, mu)) { \
+        if (wm.push(J, FIRST, wyhash_window(wlo, whi, wp), mv, mu)) {          \
             sink.emit_if(mu != prev, mv, mu - prev);                       \
             prev = mu;                                                     \
         }                                                                  \
