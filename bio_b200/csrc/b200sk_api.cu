@@ -102,6 +102,8 @@ struct Plan {
 const uint32_t kChunk = 252;        // positions per chunk for long reads: 63 words, so the 32 lanes of a warp (consecutive
                                     // chunks of one read) start on 32 different shared-memory banks
 const uint32_t kChunkReg = 132;     // ... for the register-window kernels (shared memory per lane is the limit)
+// tuning knob, off by default: from this many ranks on the sharded chain stages a WHOLE tile per bulk store (make_plan)
+static const int kWholeTileRanks = [] { const char *e = getenv("B200SK_WHOLE_TILE_RANKS"); return e ? atoi(e) : 1000; }();
 const uint32_t kSingleMaxLen = 384; // reads up to this length are one item each
 const uint32_t kSmemCtl = 14336 + 256;
 const uint32_t kSmemLimit = 227 * 1024;
@@ -179,7 +181,13 @@ int cuda_fail(b200sk_ctx *ctx, cudaError_t e, const char *what) {
     } while (0)
 
 // Build the tile plan for a batch whose longest read is max_len (0 = unknown -> chunked geometry).
-int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
+inline uint32_t pos_width_of(const b200sk_params &p) { return p.pos_width == 1 ? 1u : p.pos_width == 2 ? 2u : 4u; }
+
+// whole_tile_stage: size the register-window kernels' tile buffer so that a WHOLE tile's output fits it (the sharded
+// chain: one bulk store per array and tile instead of two rounds, at the price of two warps per SM).  Measured at
+// N = 4 (profiles/r02_multi_gpu.md): 26.8 vs 28.0 ms with the uint8 positions, but 26.6 vs 23.4 ms without them --
+// one 5.6 KB store per warp in flight does not keep the link as busy as two shorter ones.  Off by default.
+int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl, bool whole_tile_stage = false) {
     const int mode = p.mode;
     const int k = p.k, w = p.w, s = p.s;
     const int d = mode == B200SK_MODE_SYNCMER ? k - s : 0;
@@ -244,12 +252,12 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
         }
         return pl.sm_total <= kSmemLimit ? 0 : B200SK_ERR_UNSUPPORTED;
     }
+    const double slack = mode == B200SK_MODE_SYNCMER ? 1.15 : 1.45;
     if (sparse) {
         // staged-list capacity: the first window always emits, later ones at the density; +45% (about four
         // standard deviations on random reads) keeps the overflow path to ~1e-4 of the items
         // (bounded closed syncmers come out rarer and far more evenly spaced than 2/(d+1) suggests: 16.8 +- 1.4 per
         // 150-bp read, at most 25 in 300 k reads for k=21 s=11 -- a tighter factor buys one to three more warps per SM)
-        const double slack = mode == B200SK_MODE_SYNCMER ? 1.15 : 1.45;
         double e = (1.0 + (pl.C - 1) * density) * slack + 2.0;
         pl.lcap = (uint32_t)std::min<double>(pl.C, e);
         if (pl.lcap < 1) pl.lcap = 1;
@@ -266,6 +274,11 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl) {
             c.lcap = pl.lcap - shave;
             c.sm_tile = mode == B200SK_MODE_SYNCMER ? 3584u + 1024u : 4096u; // tables (+ the syncmer's fast tables)
             c.sm_tile_bytes = up16(32u * c.span_max + 32);
+            if (whole_tile_stage) { // expected elements of a tile + 10 %, 8-byte value + position each, + alignment slack
+                const uint32_t pw = p.want_pos ? pos_width_of(p) : 0u;
+                const uint32_t need = (uint32_t)(32.0 * c.lcap / slack * 1.10) * (8u + pw) + 64u;
+                c.sm_tile_bytes = std::max(c.sm_tile_bytes, up16(need));
+            }
             c.sm_ring = 16 + c.sm_tile_bytes;
             c.sm_listv = c.sm_ring + (uint32_t)d * 256u;
             c.sm_listp = c.sm_listv + (c.lcap + 1) * 256u;
@@ -310,7 +323,6 @@ int ensure_meta(b200sk_ctx *ctx) {
 
 // Everything that runs on the device for one batch (no host synchronisation unless the longest
 // read must be measured).  d_flags: where the kernels OR their flags (device memory).
-inline uint32_t pos_width_of(const b200sk_params &p) { return p.pos_width == 1 ? 1u : p.pos_width == 2 ? 2u : 4u; }
 
 int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, const uint64_t *d_off,
             uint64_t n_reads, uint64_t n_bases, uint64_t *d_val, void *d_pos, uint64_t *d_ooff,
@@ -441,10 +453,10 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(cudaStreamSynchronize(st));
         max_len = hm[1] ? hm[1] : 1;
         if (q.circular) max_len = max_len > (uint64_t)(q.k - 1) ? max_len - (q.k - 1) : 1; // plan re-adds it
-        if ((rc = make_plan(q, max_len, pl))) return rc;
+        if ((rc = make_plan(q, max_len, pl, spec && spec->n_ranks >= kWholeTileRanks))) return rc;
         if (pl.chunked) n_items_host = hm[0];
     } else {
-        if ((rc = make_plan(q, max_len, pl))) return rc;
+        if ((rc = make_plan(q, max_len, pl, spec && spec->n_ranks >= kWholeTileRanks))) return rc;
         if (pl.chunked) {
             a.C = pl.C;
             CK(launch_prepass(a, meta + 2, st));
