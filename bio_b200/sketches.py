@@ -304,6 +304,23 @@ class Batch:
     def ProteinMinimizerSketch(self, k, codonTable, frame, w):
         return self._run(mode=cabi.MODE_PROTEIN_MINIMIZER, k=k, codon_table=codonTable, frame=frame, w=w)
 
+    def ProteinFrames(self, k, codonTable):
+        """Six NewProteinIterator loops -- frame 1, 2, 3, -1, -2, -3 -- over every record through ONE call
+        (b200sk_run_frames; go/sketchesgpu: Batch.ProteinFrames).  Returns six BatchResults in that order."""
+        p = cabi.make_params(mode=cabi.MODE_PROTEIN, k=k, codon_table=codonTable, frame=1, want_pos=False,
+                             alphabet=_ALPHA[self.alphabet], max_read_len=self._max)
+        rc = cabi.lib().b200sk_check_params(__import__("ctypes").byref(p))
+        if rc != 0:
+            _raise(rc)
+        bases = np.frombuffer(b"".join(self._chunks), dtype=np.uint8)
+        out = []
+        for res in self.ctx.run_frames(p, bases, np.array(self._off, dtype=np.uint64)):
+            # Index() of a dense iterator is the running position
+            res["pos"] = np.concatenate([np.arange(int(res["off"][i + 1] - res["off"][i]), dtype=np.uint32)
+                                         for i in range(len(res["status"]))]) if res["total"] else np.zeros(0, np.uint32)
+            out.append(BatchResult(res, cabi.MODE_PROTEIN))
+        return out
+
 
 class BatchResult:
     def __init__(self, res, mode):

@@ -217,3 +217,36 @@ def test_TestSimHashIterator():
         assert len(codes) == len(_s) - k + 1
         ref, err = oracle.simhash_iterator(_s, k, 5, 5, True, False)
         assert err == 0 and codes == [int(x) for x in ref]
+
+
+def test_batch_protein_frames_equals_six_iterators():
+    """Batch.ProteinFrames (one call, b200sk_run_frames) replays like six NewProteinIterator loops per record
+    (sketches/iterator-protein.go:46-90), frame 1, 2, 3, -1, -2, -3; too-short records raise ErrShortSeq."""
+    rng = np.random.default_rng(11)
+    reads = ["".join(rng.choice(list("ACGTN"), size=int(n), p=[.24, .24, .24, .24, .04])) for n in rng.integers(10, 200, size=60)]
+    b = sk.Batch()
+    for r in reads:
+        b.Add(r)
+    k = 7
+    frames = b.ProteinFrames(k, 1)
+    assert len(frames) == 6
+    for fi, frame in enumerate((1, 2, 3, -1, -2, -3)):
+        for i, r in enumerate(reads):
+            if len(r) < 3 * k:
+                with pytest.raises(sk.ErrShortSeq):
+                    frames[fi].iterator(i)
+                continue
+            it = frames[fi].iterator(i)
+            single = sk.NewProteinIterator(sk.NewSeq(sk.DNAredundant, r), k, 1, frame)
+            got, want = [], []
+            while True:
+                v, ok = it.Next()
+                if not ok:
+                    break
+                got.append((v, it.Index()))
+            while True:
+                v, ok = single.Next()
+                if not ok:
+                    break
+                want.append((v, single.Index()))
+            assert got == want, (frame, i)
