@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 K, W, S, READ_LEN = 21, 11, 11, 150
 SEED = 43
 BLOCK = 1 << 19   # reads per generator block (one seed each)
-CHUNK = 1 << 15   # reads per chunk of the sharded C3 batch: chunk c belongs to rank c % N (1024 tiles of 32 reads)
+CHUNK = int(os.environ.get("B200SK_BENCH_CHUNK", 1 << 15))   # reads per chunk of the sharded C3 batch: chunk c belongs to rank c % N (1024 tiles of 32 reads)
 METRIC = "bases/sec sketched (k=21,w=11 minimizer)"
 
 
