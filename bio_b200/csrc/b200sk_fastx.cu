@@ -99,10 +99,14 @@ enum { M_FORMAT = 0, M_START, M_NL, M_HDR, M_LAST, M_TICKET, M_BADREC, M_MAXLEN,
 
 // ------------------------------------------------------------------ kernels
 // reader.go:271-304: the first byte that is not '\n' decides
-__global__ void k_fx_detect(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta) {
+// limit: how far to look.  While the format is still unknown the reader gives up after 10 241 newlines anyway
+// (reader.go:286-294), so 1 MiB is plenty; a chunk that CONTINUES a file (format given) may start with any number of
+// blank lines and is searched to its end -- eight bytes per lane and trip beyond the first MiB.
+__global__ void k_fx_detect(const uint8_t *__restrict__ t, uint64_t n, unsigned long long *meta, uint64_t limit) {
     const unsigned lane = threadIdx.x;
     uint64_t fmt = 0, start = n;
-    for (uint64_t base = 0; base < n && base < (1ull << 20); base += 32) {
+    uint64_t base = 0;
+    for (; base < n && base < limit && base < (1ull << 20); base += 32) {
         const uint64_t i = base + lane;
         const uint8_t b = i < n ? t[i] : (uint8_t)'\n';
         const unsigned other = __ballot_sync(0xffffffffu, b != '\n');
@@ -112,6 +116,27 @@ __global__ void k_fx_detect(const uint8_t *__restrict__ t, uint64_t n, unsigned 
             start = base + f;
             fmt = c == '>' ? B200SK_FASTX_FASTA : c == '@' ? B200SK_FASTX_FASTQ : 0;
             break;
+        }
+    }
+    if (start == n) {
+        for (; base < n && base < limit; base += 256) { // lane l: bytes base + 8 l .. + 7
+            uint32_t firstbad = 8;
+            uint8_t cb = 0;
+#pragma unroll
+            for (int j = 7; j >= 0; j--) {
+                const uint64_t i = base + 8ull * lane + (uint64_t)j;
+                const uint8_t b = i < n ? t[i] : (uint8_t)'\n';
+                if (b != '\n') { firstbad = (uint32_t)j; cb = b; }
+            }
+            const unsigned other = __ballot_sync(0xffffffffu, firstbad < 8);
+            if (other) {
+                const int f = __ffs(other) - 1;
+                const uint32_t j = __shfl_sync(0xffffffffu, firstbad, f);
+                const uint8_t c = (uint8_t)__shfl_sync(0xffffffffu, (unsigned)cb, f);
+                start = base + 8ull * (uint64_t)f + j;
+                fmt = c == '>' ? B200SK_FASTX_FASTA : c == '@' ? B200SK_FASTX_FASTQ : 0;
+                break;
+            }
         }
     }
     if (lane == 0) {
@@ -637,7 +662,7 @@ int b200sk_fastx_parse_device(b200sk_ctx *ctx, const uint8_t *d_text, uint64_t n
         info->format = format;
         return 0;
     }
-    k_fx_detect<<<1, 32, 0, st>>>(d_text, n_bytes, meta);
+    k_fx_detect<<<1, 32, 0, st>>>(d_text, n_bytes, meta, (format & 0xff) ? n_bytes : (1ull << 20));
     ctx_add_launches(ctx, 1);
     // The line table is sized from a bound (a line per 32 bytes of text) and filled in the same pass that
     // counts the lines; only a text with shorter lines on average pays a second pass with the exact size.

@@ -442,3 +442,28 @@ def test_alphabet_guess_and_validation():
             recs = list(fastx.Reader(text, ctx=ctx, chunk_bytes=1500))  # the alphabet travels with the later chunks
             assert [r.Err is not None for r in recs] == want_bad and all(r.Alphabet == want_alpha for r in recs)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_fxstream_long_run_of_blank_lines_mid_file():
+    """More than 1 MiB of blank lines between two records of a file read in small chunks: a chunk that continues the
+    file may start with any number of newlines (the format is known by then), so the search for its first record byte
+    goes to the end of the chunk -- no record behind the run may be lost."""
+    cabi, _ = _ctx()
+    a, sa = make_fasta(150, 41)
+    b, sb = make_fasta(150, 42)
+    text = a + b"\n" * (3 << 19) + b
+    kw = dict(k=15, w=7)
+    p = cabi.make_params(cabi.MODE_MINIMIZER, **kw)
+    o = oracle.fastx_parse(text)
+    assert o["n_records"] == 300
+    ref = oracle.run_batch(o["bases"], o["read_off"], oracle.MODE_MINIMIZER, threads=4, **kw)
+    stream = cabi.FastxStream(p, text, chunk_bytes=64 << 10)
+    nrec, nval, consumed = 0, 0, 0
+    for c in stream:
+        n, t = int(c["info"].n_records), c["total"]
+        assert np.array_equal(c["val"], ref["val"][nval:nval + t])
+        assert np.array_equal(c["status"], ref["status"][nrec:nrec + n])
+        nrec, nval, consumed = nrec + n, nval + t, consumed + int(c["info"].consumed)
+    assert nrec == 300 and nval == len(ref["val"]) and consumed == len(text)
+    stream.close()
