@@ -452,6 +452,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
         CK(cudaMemcpyAsync(hm, meta + 2, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         max_len = hm[1] ? hm[1] : 1;
+        if (max_len > 0xfffffff0ull) return B200SK_ERR_UNSUPPORTED; // positions of one record are 32-bit (read_positions)
         if (q.circular) max_len = max_len > (uint64_t)(q.k - 1) ? max_len - (q.k - 1) : 1; // plan re-adds it
         if ((rc = make_plan(q, max_len, pl, spec && spec->n_ranks >= kWholeTileRanks))) return rc;
         if (pl.chunked) n_items_host = hm[0];
@@ -1122,7 +1123,9 @@ static int run_host(b200sk_ctx *ctx, const b200sk_params *p_in, const uint8_t *b
                 if (want_pos) CKS(sl.pos.reserve(cap * 4 + 64));
                 sl.cap = cap;
             }
-            const uint8_t *dbase = (const uint8_t *)sl.bases.p - b0; // offsets stay absolute
+            // offsets stay absolute: the kernels add read_off[r] >= b0 to a base address b0 bytes below the slot's
+            // buffer (formed in integer arithmetic: it is not a pointer into any object until an offset is added)
+            const uint8_t *dbase = (const uint8_t *)((uintptr_t)sl.bases.p - (uintptr_t)b0);
             rc = enqueue(ctx, *p, dbase, (const uint64_t *)sl.off.p, nr, nb, (uint64_t *)sl.val.p,
                          want_pos ? sl.pos.p : nullptr, (uint64_t *)sl.ooff.p, (int32_t *)sl.status.p,
                          sl.cap, running, s_k, nullptr);
