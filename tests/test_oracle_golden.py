@@ -2,6 +2,8 @@
 (tests/golden/reference_vectors.json, extracted from the reference test sources by
 tests/golden/make_golden.py), plus the derived KATs of SURVEY.md 8c and the property
 'literal Go state machine == closed form'."""
+import os
+
 import numpy as np
 import pytest
 
@@ -170,3 +172,26 @@ def test_simhash_literal_equals_closed_form(golden):
     assert oracle.simhash_iterator(s, 21, 3, 1)[1] == oracle.ERR_INVALID_M
     assert oracle.simhash_iterator(s, 21, 5, 18)[1] == oracle.ERR_INVALID_SCALE
     assert oracle.simhash_iterator(s, 65535, 5, 1)[1] == oracle.ERR_K_TOO_LARGE
+
+
+def test_codon_rows_equal_the_reference_source():
+    """include/b200sk_codon_data.h is shared by the product and the oracle, so GPU == oracle cannot see a typo in it:
+    every amino-acid row is compared with the text the reference registers (seq/codon_tables.go:431-640), and the
+    codon order the header assumes (base1/base2/base3 cycling T, C, A, G) with the reference's three base rows.
+    Runs where /root/reference exists (this container); the GPU box has no reference tree."""
+    import re
+    src = "/root/reference/seq/codon_tables.go"
+    if not os.path.exists(src):
+        pytest.skip("no reference tree here")
+    go = open(src).read()
+    ref = {}
+    for m in re.finditer(r"CodonTables\[(\d+)\] = codonTableFromText\(\1,\s*\"[^\"]*\",\s*`([^`]*)`\)", go):
+        rows = m.group(2).split("\n")
+        assert len(rows) == 5 and all(len(r) == 64 for r in rows), m.group(1)
+        assert rows[2] == "".join(b * 16 for b in "TCAG")
+        assert rows[3] == "".join(b * 4 for b in "TCAG") * 4
+        assert rows[4] == "TCAG" * 16
+        ref[int(m.group(1))] = rows[0]
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b200sk_codon_data.h")).read()
+    ours = {int(i): aas for i, aas in re.findall(r"\{(\d+), \"([A-Z*]{64})\"\}", hdr)}
+    assert len(ref) == 24 and ours == ref
