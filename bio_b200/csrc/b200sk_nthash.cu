@@ -133,9 +133,13 @@ __device__ __forceinline__ void block16_kmer(uint8_t *smem, const Bytes16 &win, 
 // 64-entry tables at smem + 4608 (forward) / + 4672 (reverse) give the amino acid; else CodonTable.Get over the
 // copy of the aux block at smem + 0.  cb: shared offset of the first base of amino acid 0 (forward) or of the base
 // the first codon starts from (reverse).
-template <int DIR, bool FAST>
+// FAST == 2 (k_protein6_warp): the tile holds, at every position p, the index of the codon that STARTS there,
+// c[p] * 16 + c[p+1] * 4 + c[p+2] -- one byte load per amino acid; the reverse strand reads the codon that starts two
+// bases down through a table with the fields swapped (smem + 4736).
+template <int DIR, int FAST>
 __device__ __forceinline__ uint32_t protein_aa(const uint8_t *smem, uint32_t cb, uint32_t t) {
     if (DIR == 0) return lds8(smem, cb + t);
+    if (FAST == 2) return DIR == 1 ? smem[4608u + lds8(smem, cb + 3u * t)] : smem[4736u + lds8(smem, cb - 3u * t - 2u)];
     if (DIR == 1) {
         const uint32_t p = cb + 3u * t;
         const uint32_t b0 = lds8(smem, p), b1 = lds8(smem, p + 1), b2 = lds8(smem, p + 2);
@@ -148,7 +152,7 @@ __device__ __forceinline__ uint32_t protein_aa(const uint8_t *smem, uint32_t cb,
     const uint8_t *pl = smem + 4352; // DNA pair letters; other bytes pass through (codon_tables.go:222-226)
     return codon_aa(smem, pl[b0], pl[b1], pl[b2]);
 }
-template <int DIR, bool FAST, bool FULL>
+template <int DIR, int FAST, bool FULL>
 __device__ __forceinline__ void block16_protein(uint8_t *smem, uint32_t cb, uint32_t t0, uint32_t lo, uint32_t hi,
                                                 uint32_t s_row, uint32_t k, uint64_t &wlo, uint64_t &whi) {
 #pragma unroll 4 // ~60 instructions per step: fully unrolled, the variants of this block do not fit the instruction cache
@@ -162,7 +166,7 @@ __device__ __forceinline__ void block16_protein(uint8_t *smem, uint32_t cb, uint
     }
 }
 
-template <int DIR, bool FAST>
+template <int DIR, int FAST>
 __device__ __forceinline__ void protein_warm(const uint8_t *smem, uint32_t cb, uint32_t k, uint64_t &wlo, uint64_t &whi) {
     for (uint32_t t = 0; t + 1 < k; t++) { // the k-1 amino acids before the first k-mer is complete
         const uint64_t aa = protein_aa<DIR, FAST>(smem, cb, t);
@@ -499,6 +503,8 @@ __global__ void __launch_bounds__(768, 1) k_protein6_warp(const KArgs a, uint32_
         const uint32_t c0 = tid >> 4, c1 = (tid >> 2) & 3u, c2 = tid & 3u;
         smem[4608 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c0], (uint32_t)letter[c1], (uint32_t)letter[c2]);
         smem[4672 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c0 ^ 2u], (uint32_t)letter[c1 ^ 2u], (uint32_t)letter[c2 ^ 2u]);
+        // reverse strand by the index of the codon two bases DOWN (fields swapped: c0 is that codon's third base)
+        smem[4736 + tid] = (uint8_t)codon_aa(smem, (uint32_t)letter[c2 ^ 2u], (uint32_t)letter[c1 ^ 2u], (uint32_t)letter[c0 ^ 2u]);
     }
     const uint32_t region = NH_TABLES + wid * warp_stride;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + region);
@@ -557,6 +563,31 @@ __global__ void __launch_bounds__(768, 1) k_protein6_warp(const KArgs a, uint32_
                 *reinterpret_cast<uint4 *>(tilebuf + o) = v;
             }
             fast = !__any_sync(0xffffffffu, bad != 0);
+            if (fast) {
+                // classes -> codon indices in place: position p gets c[p] * 16 + c[p+1] * 4 + c[p+2] (bytes <= 63: no
+                // carries between the bytes of a word).  Every lane reads its 16 bytes and the next word before any
+                // lane writes; the word behind the tile's last chunk is slack (its two codons are never looked up).
+                for (uint32_t base = 0; base < bytes; base += 512u) { // (every lane takes every trip: __syncwarp)
+                    const uint32_t o = base + lane * 16u;
+                    const bool mine = o < bytes;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    uint32_t nx = 0;
+                    if (mine) {
+                        v = *reinterpret_cast<const uint4 *>(tilebuf + o);
+                        nx = *reinterpret_cast<const uint32_t *>(tilebuf + o + 16u);
+                    }
+                    __syncwarp();
+                    if (mine) {
+                        uint4 c;
+                        c.x = v.x * 16u + __funnelshift_r(v.x, v.y, 8) * 4u + __funnelshift_r(v.x, v.y, 16);
+                        c.y = v.y * 16u + __funnelshift_r(v.y, v.z, 8) * 4u + __funnelshift_r(v.y, v.z, 16);
+                        c.z = v.z * 16u + __funnelshift_r(v.z, v.w, 8) * 4u + __funnelshift_r(v.z, v.w, 16);
+                        c.w = v.w * 16u + __funnelshift_r(v.w, nx, 8) * 4u + __funnelshift_r(v.w, nx, 16);
+                        *reinterpret_cast<uint4 *>(tilebuf + o) = c;
+                    }
+                    __syncwarp();
+                }
+            }
             if (!fast) { // some other byte: the original bytes again, CodonTable.Get over the IUPAC matrix
                 __syncwarp();
                 if (lane == 0) {
@@ -587,8 +618,8 @@ __global__ void __launch_bounds__(768, 1) k_protein6_warp(const KArgs a, uint32_
             const uint32_t cb = !nstep ? s_tile + 8u : frame > 0 ? sb0 + (uint32_t)(frame - 1) : sb0 + (uint32_t)L - (uint32_t)(-frame);
             uint64_t wlo = 0, whi = 0;
             if (nstep) {
-                if (frame > 0) { if (fast) protein_warm<1, true>(smem, cb, k, wlo, whi); else protein_warm<1, false>(smem, cb, k, wlo, whi); }
-                else { if (fast) protein_warm<2, true>(smem, cb, k, wlo, whi); else protein_warm<2, false>(smem, cb, k, wlo, whi); }
+                if (frame > 0) { if (fast) protein_warm<1, 2>(smem, cb, k, wlo, whi); else protein_warm<1, 0>(smem, cb, k, wlo, whi); }
+                else { if (fast) protein_warm<2, 2>(smem, cb, k, wlo, whi); else protein_warm<2, 0>(smem, cb, k, wlo, whi); }
             }
             const uint32_t last_block = vend ? ((vend - 1) / 16u) * 16u : 0u;
             __syncwarp();
@@ -605,8 +636,8 @@ __global__ void __launch_bounds__(768, 1) k_protein6_warp(const KArgs a, uint32_
 #define B200SK_PBLOCK(DIR, FAST_)                                                                          \
     if (full) block16_protein<DIR, FAST_, true>(smem, cb, t0, lo_s, hi_s, s_row, k, wlo, whi);             \
     else block16_protein<DIR, FAST_, false>(smem, cb, t0, lo_s, hi_s, s_row, k, wlo, whi);
-                if (frame > 0) { if (fast) { B200SK_PBLOCK(1, true) } else { B200SK_PBLOCK(1, false) } }
-                else { if (fast) { B200SK_PBLOCK(2, true) } else { B200SK_PBLOCK(2, false) } }
+                if (frame > 0) { if (fast) { B200SK_PBLOCK(1, 2) } else { B200SK_PBLOCK(1, 0) } }
+                else { if (fast) { B200SK_PBLOCK(2, 2) } else { B200SK_PBLOCK(2, 0) } }
 #undef B200SK_PBLOCK
                 __syncwarp();
                 const uint32_t half = lane >> 4, e = lane & 15u;
