@@ -101,7 +101,7 @@ struct Plan {
 
 const uint32_t kChunk = 252;        // positions per chunk for long reads: 63 words, so the 32 lanes of a warp (consecutive
                                     // chunks of one read) start on 32 different shared-memory banks
-const uint32_t kChunkReg = 132;     // ... for the register-window kernels (shared memory per lane is the limit)
+const uint32_t kChunkReg = 132;     // ... for the register-window kernels (shared memory per lane is the limit) -- the fallback: make_plan picks C
 // tuning knob, off by default: from this many ranks on the sharded chain stages a WHOLE tile per bulk store (make_plan)
 static const int kWholeTileRanks = [] { const char *e = getenv("B200SK_WHOLE_TILE_RANKS"); return e ? atoi(e) : 1000; }();
 const uint32_t kSingleMaxLen = 384; // reads up to this length are one item each
@@ -187,7 +187,46 @@ inline uint32_t pos_width_of(const b200sk_params &p) { return p.pos_width == 1 ?
 // chain: one bulk store per array and tile instead of two rounds, at the price of two warps per SM).  Measured at
 // N = 4 (profiles/r02_multi_gpu.md): 26.8 vs 28.0 ms with the uint8 positions, but 26.6 vs 23.4 ms without them --
 // one 5.6 KB store per warp in flight does not keep the link as busy as two shorter ones.  Off by default.
+int make_plan_c(const b200sk_params &p, uint64_t max_len, Plan &pl, bool whole_tile_stage, uint32_t chunk_reg);
+
+// Long reads are cut into chunks of C positions, one lane each.  A chunk pays for its halo again (window warm-up, the
+// k-1 folds) and for its share of the tile's fixed work, so C wants to be large; the lane's bases and staged lists
+// want it small (warps per SM).  The register-window kernels take the C that maximises
+//     warps(nw) x C / (C + 2 window + k)
+// over C = 4 (mod 8) -- consecutive lanes start C bytes apart in shared memory, and only an odd number of words between
+// them keeps the 32 lanes' word loads on 32 banks (C = 160: 8-way conflicts, syncmers 159 instead of 190 Gbases/s).
+// Both terms are fits to measurements on ONT-like reads (profiles/r02ax_chunk.txt): the per-chunk overhead 2 window + k
+// (43 steps for minimizers k=21 w=11, 61 for syncmers k=21 s=11), and the occupancy curve -- 1 at the cap (16 warps; 12
+// for wide syncmer windows and protein minimizers), 0.96 at 12 of 16, 0.92 for the counts that load the four schedulers
+// unevenly, 0.90 at 11 of 12.  Result: syncmers k=21 s=11 C = 156 (181 -> 190 Gbases/s against the fixed 132),
+// minimizers k=21 w=11 C = 172 at 12 warps (310 -> 338).
 int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl, bool whole_tile_stage = false) {
+    static const uint32_t forced = [] { const char *e = getenv("B200SK_CHUNK_REG"); return e ? (uint32_t)atoi(e) : 0u; }();
+    const int mode = p.mode;
+    const uint64_t ext = p.circular ? (uint64_t)(p.k - 1) : 0;
+    const bool chunked = !(max_len && max_len + ext <= kSingleMaxLen);
+    const bool sparse = mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER || mode == B200SK_MODE_PROTEIN_MINIMIZER;
+    if (!chunked || !sparse || !sparse_reg_supported(mode, p.k, p.w, p.s))
+        return make_plan_c(p, max_len, pl, whole_tile_stage, kChunkReg);
+    if (forced) return make_plan_c(p, max_len, pl, whole_tile_stage, forced);
+    const int cap = sparse_reg_max_warps(mode, p.k, p.w, p.s);
+    const double window = mode == B200SK_MODE_SYNCMER ? 2.0 * (p.k - p.s) : (double)p.w;
+    double best_score = -1.0;
+    for (uint32_t c = 100; c <= 196; c += 8) {
+        Plan cand;
+        if (make_plan_c(p, max_len, cand, whole_tile_stage, c) || !cand.reg) continue;
+        const int nw = cand.T / 32;
+        double warps;
+        if (nw >= cap) warps = 1.0;
+        else if (cap == 16) warps = nw >= 12 ? (nw % 4 == 0 ? 0.96 : 0.92) : 0.96 * nw / 12.0;
+        else warps = nw == cap - 1 ? 0.90 : 0.95 * nw / cap;
+        const double score = warps * c / (c + 2.0 * window + p.k);
+        if (score > best_score) { best_score = score; pl = cand; }
+    }
+    return best_score > 0 ? 0 : make_plan_c(p, max_len, pl, whole_tile_stage, kChunkReg);
+}
+
+int make_plan_c(const b200sk_params &p, uint64_t max_len, Plan &pl, bool whole_tile_stage, uint32_t chunk_reg) {
     const int mode = p.mode;
     const int k = p.k, w = p.w, s = p.s;
     const int d = mode == B200SK_MODE_SYNCMER ? k - s : 0;
@@ -216,7 +255,7 @@ int make_plan(const b200sk_params &p, uint64_t max_len, Plan &pl, bool whole_til
     } else {
         pl.C = (mode == B200SK_MODE_MINIMIZER || mode == B200SK_MODE_SYNCMER || mode == B200SK_MODE_PROTEIN_MINIMIZER) &&
                        sparse_reg_supported(mode, k, w, s)
-                   ? kChunkReg : kChunk;
+                   ? chunk_reg : kChunk;
         if ((uint64_t)pl.C + halo > 20000) return B200SK_ERR_UNSUPPORTED;
         pl.span_max = (uint32_t)(pl.C + halo);
         if (mode == B200SK_MODE_PROTEIN && p.alphabet != B200SK_ALPHABET_PROTEIN) pl.span_max *= 3; // codons
