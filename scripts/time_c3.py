@@ -7,9 +7,10 @@ dev = torch.device("cuda:0")
 ctx = cabi.Context(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 11
-bases, off = synth.device_uniform_reads(n, 150, 43, dev)
-nb = n * 150
-p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=w, max_read_len=150)
+RL = int(os.environ.get("READ_LEN", 150))
+bases, off = synth.device_uniform_reads(n, RL, 43, dev)
+nb = n * RL
+p = cabi.make_params(cabi.MODE_MINIMIZER, 21, w=w, max_read_len=RL)
 cap = int(cabi.lib().b200sk_output_bound(ctypes.byref(p), nb, n, 0))
 val = torch.empty(cap, dtype=torch.int64, device=dev)
 pos = torch.empty(cap, dtype=torch.int32, device=dev)
@@ -28,5 +29,5 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 chk = int(val[:total].sum().item()) ^ int(pos[:total].sum().item())
-print(json.dumps({"walker": os.environ.get("B200SK_WALKER", "exact"), "spin_ns": os.environ.get("B200SK_SPIN_NS", "0"), "w": w,
+print(json.dumps({"walker": os.environ.get("B200SK_WALKER", "exact"), "spin_ns": os.environ.get("B200SK_SPIN_NS", "0"), "w": w, "read_len": RL,
                   "ms": round(ms, 4), "Gbases_per_s": round(nb / ms / 1e6, 1), "elements": total, "checksum": chk}), flush=True)
