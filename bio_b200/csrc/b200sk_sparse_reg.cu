@@ -708,6 +708,34 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
 #undef B200SK_PM_STEP
 }
 
+// ------------------------------------------------------------------ skewed staging (uniform reads of n x 128 bytes)
+// The tile's rows of `rowlen` bytes (a multiple of 128) lie back to back at `landing` (where the bulk copy put them:
+// the staged-list area, dead between two tiles); they move to tilebuf at a row stride of rowlen + 4 and are rewritten
+// on the way: FASTB -> fast-path bytes (returns false when some byte is not one of ACGTacgt: the caller calls again
+// for 6-bit codes -- the landing area still holds the ASCII).  nvec 16-byte vectors cover the rows.
+// (Lanes fetching the rows from global memory themselves was tried first: 16 dependent trips per lane for a 256-byte
+// row tile, 289 Gbases/s; with the loads batched the registers of W >= 11 spill.)
+template <bool FASTB>
+__device__ __forceinline__ bool restage_skewed(uint8_t *tilebuf, const uint8_t *landing, uint32_t nvec, uint32_t rowlen,
+                                               uint32_t lane) {
+    const uint32_t vpr = rowlen >> 4; // vectors per row
+    uint32_t bad = 0;
+    for (uint32_t v = lane; v < nvec; v += 32u) {
+        uint4 x = *reinterpret_cast<const uint4 *>(landing + v * 16u);
+        const uint32_t row = v / vpr, col = v - row * vpr;
+        if (FASTB) {
+            x.x = fast_word(x.x, bad); x.y = fast_word(x.y, bad);
+            x.z = fast_word(x.z, bad); x.w = fast_word(x.w, bad);
+        } else {
+            x.x = codes_of_word(x.x); x.y = codes_of_word(x.y);
+            x.z = codes_of_word(x.z); x.w = codes_of_word(x.w);
+        }
+        uint32_t *d = reinterpret_cast<uint32_t *>(tilebuf + row * (rowlen + 4u) + col * 16u);
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    }
+    return !__any_sync(0xffffffffu, bad != 0);
+}
+
 // ------------------------------------------------------------------ kernel: one tile per WARP
 // A tile is 32 consecutive items; every warp runs its own ticket -> TMA -> walk -> look-back -> ordered
 // copy loop with no block-wide barrier, so warps drift freely and cover each other's latencies.
@@ -723,7 +751,11 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
 // (3 W words of window state + two hashers) spill at 128, and shared memory holds only 13-14 of their warps anyway --
 // 13 or 14 warps run no faster than 12 (the ordered chain moves at the pace of the schedulers that hold four).
 template <int MODE, int W> constexpr int max_warps() { return MODE == B200SK_MODE_SYNCMER && W >= 16 ? 12 : 16; }
-template <int MODE, int W, bool KEYED, bool SHARD>
+// SKEW: the instantiation the host picks for batches whose longest read is a multiple of 128 bytes (a.skew): tiles of
+// equally long reads are then staged with a word of skew per lane (restage_skewed).  Its own instantiation, so that the
+// kernel every other batch runs stays instruction for instruction what it was (in one kernel the extra code cost the
+// 150-bp headline 1.7 %: 416 vs 424 Gbases/s, profiles/r02bb_readlen.txt).
+template <int MODE, int W, bool KEYED, bool SHARD, bool SKEW = false>
 __global__ void __launch_bounds__(32 * max_warps<MODE, W>(), 1) k_sparse_warp(const KArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
@@ -787,6 +819,21 @@ __global__ void __launch_bounds__(32 * max_warps<MODE, W>(), 1) k_sparse_warp(co
         const uint64_t span = hi > lo_al ? hi - lo_al : 0;
         const uint32_t bytes = (uint32_t)((span + 15ULL) & ~15ULL);
         const bool span_ok = bytes <= a.sm_tile_bytes;
+        // Reads of ONE length that is a multiple of 128 bytes would start 32 lanes on the same shared-memory bank
+        // (lanes sit a read length apart): every word load of the walk a 32-way conflict, 235 instead of 425 Gbases/s
+        // at 128 bp (profiles/r02ba_readlen.txt).  For such a tile the bulk copy lands in the staged-list area and the
+        // rewriting pass moves row r to r * (length + 4) of the tile buffer: one word of skew per lane puts the lanes
+        // on 32 different banks.  (The bulk copy cannot skew by itself: its addresses move in 16-byte units, which
+        // would leave 4-way conflicts.)
+        uint64_t rowlen = 0;
+        bool skew = false;
+        if constexpr (SKEW) {
+            rowlen = __shfl_sync(0xffffffffu, it.gb0, 1) - lo;
+            const bool rows = __all_sync(0xffffffffu, !it.valid || it.gb0 == lo + (uint64_t)lane * rowlen);
+            skew = rows && nvalid > 1u && (lo & 15ULL) == 0 && rowlen != 0 && (rowlen & 127ULL) == 0 && bytes != 0 &&
+                   hi <= lo + (uint64_t)nvalid * rowlen && 32ULL * (rowlen + 4ULL) <= a.sm_tile_bytes &&
+                   bytes <= (a.lcap + 1u) * 288u; // the bulk copy lands in the list area (values + position bytes)
+        }
         if (SHARD) { // the previous tile's bulk stores must have read the buffer
             if (lane == 0) bulk_wait_read();
             __syncwarp();
@@ -794,12 +841,18 @@ __global__ void __launch_bounds__(32 * max_warps<MODE, W>(), 1) k_sparse_warp(co
         if (lane == 0 && bytes && span_ok) {
             fence_proxy_async(); // the previous tile's generic-proxy writes to this buffer precede the async write
             mbar_expect_tx(mbar, bytes);
-            tma_load_1d(tilebuf, a.bases + lo_al, bytes, mbar);
+            tma_load_1d(SKEW && skew ? reinterpret_cast<uint8_t *>(listv) : tilebuf, a.bases + lo_al, bytes, mbar);
         }
         if (!span_ok && lane == 0) atomicOr(a.flags, B200SK_FLAG_SPAN);
         if (it.valid && it.first_chunk && a.status) a.status[SHARD ? global_tile() * 32ull + lane : it.r] = it.status;
         bool fast = false;
-        if (bytes && span_ok) {
+        if (SKEW && skew) {
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            const uint8_t *landing = reinterpret_cast<const uint8_t *>(listv);
+            fast = restage_skewed<true>(tilebuf, landing, bytes >> 4, (uint32_t)rowlen, lane);
+            if (!fast) restage_skewed<false>(tilebuf, landing, bytes >> 4, (uint32_t)rowlen, lane);
+        } else if (bytes && span_ok) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
             if (!PROT) {
@@ -844,7 +897,7 @@ __global__ void __launch_bounds__(32 * max_warps<MODE, W>(), 1) k_sparse_warp(co
         sink.av = smem_base + region + a.sm_listv + lane * 8u;
         sink.ap = smem_base + region + a.sm_listp + lane;
         sink.cap = a.lcap; sink.cnt = 0;
-        const uint32_t sb = s_tile + (uint32_t)(it.gb0 - lo_al);
+        const uint32_t sb = s_tile + (SKEW && skew ? lane * ((uint32_t)rowlen + 4u) : (uint32_t)(it.gb0 - lo_al));
         const bool run = it.valid && it.nstep && span_ok;
         const int32_t lim0 = (int32_t)(it.end - it.q0);
         const uint32_t halo = it.q0 != it.p0 ? 1u : 0u;
@@ -1050,6 +1103,9 @@ static cudaError_t launch_w(const KArgs &a, int threads, int blocks, cudaStream_
     const void *fn = (const void *)k_sparse_warp<MODE, W, false, SHARD>;
     if constexpr (has_keyed<MODE, W>() && !SHARD) {
         if (a.keyed) fn = (const void *)k_sparse_warp<MODE, W, true, false>;
+    }
+    if constexpr (MODE != B200SK_MODE_PROTEIN_MINIMIZER && !SHARD) { // single-GPU minimizers and syncmers
+        if (a.skew && !a.keyed) fn = (const void *)k_sparse_warp<MODE, W, false, false, true>;
     }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.sm_total);
     if (e != cudaSuccess) return e;

@@ -116,6 +116,43 @@ def test_ont_like_long_reads(gpu_ctx, mode, kw):
     assert_same(res, ref)
 
 
+@pytest.mark.parametrize("read_len", [128, 256, 384])
+@pytest.mark.parametrize("mode,kw", [
+    (cabi.MODE_MINIMIZER, dict(k=21, w=11)),
+    (cabi.MODE_MINIMIZER, dict(k=31, w=15)),
+    (cabi.MODE_MINIMIZER, dict(k=21, w=20)),
+    (cabi.MODE_SYNCMER, dict(k=21, s=11)),
+    (cabi.MODE_SYNCMER, dict(k=15, s=11)),
+])
+def test_uniform_reads_of_a_multiple_of_128_bytes(gpu_ctx, mode, kw, read_len):
+    # the lanes of a tile sit one read apart in shared memory: such tiles are staged with a word of skew per lane
+    # (k_sparse_warp, stage_skewed) instead of one bulk copy.  Clean tiles, tiles with N / IUPAC bytes (staged twice:
+    # fast-path bytes, then codes), a last tile of ONE read, then the same reads behind an 8-byte record (tiles no
+    # longer start on a 16-byte boundary: bulk-copy path) and a batch whose last read is shorter / longer.
+    n = 32 * 40 + 1
+    b, o = synth.uniform_reads(n, read_len, 5)
+    b = b.copy()
+    rng = np.random.default_rng(6)
+    dirty = rng.integers(64 * read_len, 200 * read_len, size=300)   # tiles 2..6
+    b[dirty] = np.frombuffer(b"NnRYacgt", dtype=np.uint8)[rng.integers(0, 8, size=300)]
+    for hint in (read_len, 0):
+        res, ref = run_both(gpu_ctx, mode, b, o, hint=hint, **kw)
+        assert_same(res, ref, f"uniform {read_len} hint {hint}")
+    lens = np.array([8] + [read_len] * 100, dtype=np.uint64)
+    b2, o2 = synth.ragged_reads(lens, 7)
+    res, ref = run_both(gpu_ctx, mode, b2, o2, hint=read_len, **kw)
+    assert_same(res, ref, "behind an 8-byte record")
+    for last in (read_len - 28, 60):
+        lens = np.array([read_len] * 63 + [last], dtype=np.uint64)
+        b3, o3 = synth.ragged_reads(lens, 8)
+        res, ref = run_both(gpu_ctx, mode, b3, o3, hint=read_len, **kw)
+        assert_same(res, ref, f"last read of {last}")
+    lens = np.array([read_len] * 31 + [read_len + 128 if read_len < 384 else 300] + [read_len] * 32, dtype=np.uint64)
+    b4, o4 = synth.ragged_reads(lens, 9)
+    res, ref = run_both(gpu_ctx, mode, b4, o4, hint=int(lens.max()), **kw)
+    assert_same(res, ref, "one longer read at the end of a tile")
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_parameters_ragged_inputs(gpu_ctx, seed):
     """Random k/w/s over ragged batches that include empty and too-short reads, lowercase, N, IUPAC
