@@ -313,8 +313,8 @@ int make_plan_c(const b200sk_params &p, uint64_t max_len, Plan &pl, bool whole_t
             c.lcap = pl.lcap - shave;
             c.sm_tile = mode == B200SK_MODE_SYNCMER ? 3584u + 1024u : 4096u; // tables (+ the syncmer's fast tables)
             c.sm_tile_bytes = up16(32u * c.span_max + 32);
-            // reads of n x 128 bytes are staged with one word of skew per lane (k_sparse_warp: bank conflicts)
-            if (!c.chunked && c.span_max % 128u == 0 && mode != B200SK_MODE_PROTEIN_MINIMIZER) c.sm_tile_bytes += 128u;
+            // reads of n x 32 bytes are staged with one word of skew per lane (k_sparse_warp: bank conflicts)
+            if (!c.chunked && c.span_max % 32u == 0 && mode != B200SK_MODE_PROTEIN_MINIMIZER) c.sm_tile_bytes += 128u;
             if (whole_tile_stage) { // expected elements of a tile + 10 %, 8-byte value + position each, + alignment slack
                 const uint32_t pw = p.want_pos ? pos_width_of(p) : 0u;
                 const uint32_t need = (uint32_t)(32.0 * c.lcap / slack * 1.10) * (8u + pw) + 64u;
@@ -520,7 +520,7 @@ int enqueue(b200sk_ctx *ctx, const b200sk_params &p, const uint8_t *d_bases, con
     }
     a.C = pl.C; a.span_max = pl.span_max; a.lcap = pl.lcap;
     a.keyed = pl.keyed ? 1u : 0u;
-    a.skew = (pl.reg && !pl.chunked && !spec && pl.span_max % 128u == 0 && q.mode != B200SK_MODE_PROTEIN_MINIMIZER) ? 1u : 0u; // lanes a read apart would share a bank
+    a.skew = (pl.reg && !pl.chunked && !spec && pl.span_max % 32u == 0 && q.mode != B200SK_MODE_PROTEIN_MINIMIZER) ? 1u : 0u; // lanes a read apart would share a bank
     if (pl.keyed) {
         static const bool force_rewalk = [] { const char *e = getenv("B200SK_WALKER"); return e && strcmp(e, "rewalk") == 0; }();
         if (force_rewalk) a.keyed |= 2u; // testing knob: every item also takes the exact re-walk

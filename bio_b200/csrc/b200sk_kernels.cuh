@@ -55,7 +55,7 @@ struct KArgs {
     uint32_t keyed;    // minimizers, W <= 16: window minimum on 32-bit keys (b200sk_sparse_reg.cu)
     uint32_t key_mask; // 0xffffffc0, as a run-time value (see make_key)
     uint32_t spin_ns;  // look-back poll interval (0 = busy poll)
-    uint32_t skew;     // the longest read is a multiple of 128 bytes: the SKEW instantiation of k_sparse_warp
+    uint32_t skew;     // the longest read is a multiple of 32 bytes: the SKEW instantiation of k_sparse_warp
     unsigned long long *unordered; // timing experiment: allocate output ranges in completion order (null = ordered)
     // all six frames of ProteinIterator in one launch (b200sk_enqueue_device_frames): [i] = frame 1, 2, 3, -1, -2, -3
     uint64_t *fr_val[6];

@@ -708,8 +708,8 @@ __device__ __forceinline__ void protmin_item_reg(const uint8_t *sm, uint32_t sb,
 #undef B200SK_PM_STEP
 }
 
-// ------------------------------------------------------------------ skewed staging (uniform reads of n x 128 bytes)
-// The tile's rows of `rowlen` bytes (a multiple of 128) lie back to back at `landing` (where the bulk copy put them:
+// ------------------------------------------------------------------ skewed staging (uniform reads of n x 32 bytes)
+// The tile's rows of `rowlen` bytes (a multiple of 32) lie back to back at `landing` (where the bulk copy put them:
 // the staged-list area, dead between two tiles); they move to tilebuf at a row stride of rowlen + 4 and are rewritten
 // on the way: FASTB -> fast-path bytes (returns false when some byte is not one of ACGTacgt: the caller calls again
 // for 6-bit codes -- the landing area still holds the ASCII).  nvec 16-byte vectors cover the rows.
@@ -751,7 +751,7 @@ __device__ __forceinline__ bool restage_skewed(uint8_t *tilebuf, const uint8_t *
 // (3 W words of window state + two hashers) spill at 128, and shared memory holds only 13-14 of their warps anyway --
 // 13 or 14 warps run no faster than 12 (the ordered chain moves at the pace of the schedulers that hold four).
 template <int MODE, int W> constexpr int max_warps() { return MODE == B200SK_MODE_SYNCMER && W >= 16 ? 12 : 16; }
-// SKEW: the instantiation the host picks for batches whose longest read is a multiple of 128 bytes (a.skew): tiles of
+// SKEW: the instantiation the host picks for batches whose longest read is a multiple of 32 bytes (a.skew): tiles of
 // equally long reads are then staged with a word of skew per lane (restage_skewed).  Its own instantiation, so that the
 // kernel every other batch runs stays instruction for instruction what it was (in one kernel the extra code cost the
 // 150-bp headline 1.7 %: 416 vs 424 Gbases/s, profiles/r02bb_readlen.txt).
@@ -821,16 +821,16 @@ __global__ void __launch_bounds__(32 * max_warps<MODE, W>(), 1) k_sparse_warp(co
         const bool span_ok = bytes <= a.sm_tile_bytes;
         // Reads of ONE length that is a multiple of 128 bytes would start 32 lanes on the same shared-memory bank
         // (lanes sit a read length apart): every word load of the walk a 32-way conflict, 235 instead of 425 Gbases/s
-        // at 128 bp (profiles/r02ba_readlen.txt).  For such a tile the bulk copy lands in the staged-list area and the
-        // rewriting pass moves row r to r * (length + 4) of the tile buffer: one word of skew per lane puts the lanes
-        // on 32 different banks.  (The bulk copy cannot skew by itself: its addresses move in 16-byte units, which
-        // would leave 4-way conflicts.)
+        // at 128 bp (profiles/r02ba_readlen.txt); multiples of 64 and 32 bytes share 2 and 4 banks.  For such a tile
+        // the bulk copy lands in the staged-list area and the rewriting pass moves row r to r * (length + 4) of the
+        // tile buffer: length / 4 + 1 words between the lanes is odd, so the 32 lanes sit on 32 different banks.
+        // (The bulk copy cannot skew by itself: its addresses move in 16-byte units, which would leave 4-way conflicts.)
         uint64_t rowlen = 0;
         bool skew = false;
         if constexpr (SKEW) {
             rowlen = __shfl_sync(0xffffffffu, it.gb0, 1) - lo;
             const bool rows = __all_sync(0xffffffffu, !it.valid || it.gb0 == lo + (uint64_t)lane * rowlen);
-            skew = rows && nvalid > 1u && (lo & 15ULL) == 0 && rowlen != 0 && (rowlen & 127ULL) == 0 && bytes != 0 &&
+            skew = rows && nvalid > 1u && (lo & 15ULL) == 0 && rowlen != 0 && (rowlen & 31ULL) == 0 && bytes != 0 &&
                    hi <= lo + (uint64_t)nvalid * rowlen && 32ULL * (rowlen + 4ULL) <= a.sm_tile_bytes &&
                    bytes <= (a.lcap + 1u) * 288u; // the bulk copy lands in the list area (values + position bytes)
         }

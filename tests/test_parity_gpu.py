@@ -116,7 +116,7 @@ def test_ont_like_long_reads(gpu_ctx, mode, kw):
     assert_same(res, ref)
 
 
-@pytest.mark.parametrize("read_len", [128, 256, 384])
+@pytest.mark.parametrize("read_len", [128, 160, 192, 256, 384])
 @pytest.mark.parametrize("mode,kw", [
     (cabi.MODE_MINIMIZER, dict(k=21, w=11)),
     (cabi.MODE_MINIMIZER, dict(k=31, w=15)),
@@ -124,9 +124,9 @@ def test_ont_like_long_reads(gpu_ctx, mode, kw):
     (cabi.MODE_SYNCMER, dict(k=21, s=11)),
     (cabi.MODE_SYNCMER, dict(k=15, s=11)),
 ])
-def test_uniform_reads_of_a_multiple_of_128_bytes(gpu_ctx, mode, kw, read_len):
+def test_uniform_reads_of_a_multiple_of_32_bytes(gpu_ctx, mode, kw, read_len):
     # the lanes of a tile sit one read apart in shared memory: such tiles are staged with a word of skew per lane
-    # (k_sparse_warp, stage_skewed) instead of one bulk copy.  Clean tiles, tiles with N / IUPAC bytes (staged twice:
+    # (k_sparse_warp<.., SKEW>, restage_skewed).  Clean tiles, tiles with N / IUPAC bytes (staged twice:
     # fast-path bytes, then codes), a last tile of ONE read, then the same reads behind an 8-byte record (tiles no
     # longer start on a 16-byte boundary: bulk-copy path) and a batch whose last read is shorter / longer.
     n = 32 * 40 + 1
