@@ -195,3 +195,39 @@ def test_codon_rows_equal_the_reference_source():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b200sk_codon_data.h")).read()
     ours = {int(i): aas for i, aas in re.findall(r"\{(\d+), \"([A-Z*]{64})\"\}", hdr)}
     assert len(ref) == 24 and ours == ref
+
+
+def _reads_that_differ(a, b):
+    """reads whose (value, position) stream differs between two oracle results of the same batch"""
+    d = a["counts"] != b["counts"]
+    for r in np.nonzero(~d)[0]:
+        s0, e0, s1, e1 = int(a["off"][r]), int(a["off"][r + 1]), int(b["off"][r]), int(b["off"][r + 1])
+        if not (np.array_equal(a["val"][s0:e0], b["val"][s1:e1]) and np.array_equal(a["pos"][s0:e0], b["pos"][s1:e1])):
+            d[r] = True
+    return int(d.sum())
+
+
+def test_first_window_sort_order_only_matters_on_ties():
+    """The first window is sorted by twotwotwo/sorts.Quicksort (sketch.go:236,351), whose order of equal values nothing
+    in the reference pins.  Oracle and GPU take the leftmost (a stable sort).  The oracle also restates the sort the
+    module is believed to descend from (Go <= 1.5 sort.Sort: insertion sort up to 7 elements, else median-of-three
+    quicksort), which bounds what the choice can cost: windows of at most 7 elements come out the same by construction,
+    reads without a first-window tie come out the same, and on the bench's distributions the streams differ for
+    0 of 400 000 reads (C3: k=21 w=11), 2.4e-4 of 150-bp reads and 1.5e-4 of ONT-like reads (syncmers k=21 s=11)."""
+    from bio_b200 import synth
+    b, o = synth.uniform_reads(60000, 150, 43)
+    for mode, kw in ((oracle.MODE_MINIMIZER, dict(k=21, w=11)), (oracle.MODE_SYNCMER, dict(k=21, s=11))):
+        st = oracle.run_batch(b, o, mode, threads=4, sort_policy=oracle.SORT_STABLE, **kw)
+        go = oracle.run_batch(b, o, mode, threads=4, sort_policy=oracle.SORT_GO14, **kw)
+        assert st["ties"] == go["ties"]
+        assert _reads_that_differ(st, go) <= st["ties"]
+        if mode == oracle.MODE_MINIMIZER:
+            assert _reads_that_differ(st, go) == 0  # 64-bit hashes of 21-mers do not tie on random reads
+    # tie-heavy reads (two letters, k=5): w <= 7 is an insertion sort in both, w = 11 is not
+    b, o = synth.ragged_reads([150] * 3000, 9, alphabet=b"AC")
+    for w, same in ((3, True), (7, True), (11, False)):
+        st = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=5, w=w, sort_policy=oracle.SORT_STABLE)
+        go = oracle.run_batch(b, o, oracle.MODE_MINIMIZER, k=5, w=w, sort_policy=oracle.SORT_GO14)
+        assert st["ties"] > 100
+        nd = _reads_that_differ(st, go)
+        assert nd <= st["ties"] and (nd == 0) == same
